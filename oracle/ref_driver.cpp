@@ -1,0 +1,342 @@
+/* oracle/ref_driver.cpp - command-line driver around the UNMODIFIED reference GMG sources
+ * (compiled where they lie under /root/reference, see oracle/Makefile) so that its operator,
+ * smoother, transfer operators, V-cycle and BiCGStab can be run on raw input files.
+ *
+ * TEST INFRASTRUCTURE: this program is the parity oracle ("oracle/_ref/ref_gmg") and the CPU
+ * baseline binary.  It is never linked into, or called by, the product path.
+ *
+ * The set-up mirrors apps/3d/steady.cpp:211-215,292-310,482 and apps/2d/steady.cpp (Tree load,
+ * refineLeaves x divide, ThundereggDomGen, patch solver, GMG::CycleFactory{2,3}d::getCycle) and
+ * the RHS follows apps/3d/steady.cpp:253-265 / apps/2d/steady.cpp:314-316 through
+ * Init::initDirichlet{,2d}.
+ *
+ * usage: ref_gmg D mesh.bin divide n dft|fftw cmd [cmd...]
+ *   meta:OUT                         hierarchy metadata (format: see dump_meta)
+ *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
+ *   apply:L:U_IN:OUT                 OUT = A_L U                (level 0 = finest)
+ *   smooth:L:F_IN:U_IN:OUT           one block-Jacobi sweep on level L
+ *   restrict:L:FINE_IN:OUT           AvgRstr from level L to level L+1
+ *   interp:L:COARSE_IN:FINE_IN:OUT   DrctIntp from level L+1 into level L (adds)
+ *   vcycle:F_IN:OUT                  OUT = Cycle::apply(F)
+ *   vhist:F_IN:NCYC:U_OUT:HIST_OUT   u += V(f - A u), NCYC times from u = 0; HIST = ||f-Au||_2/||f||_2
+ *   bicgstab:F_IN:TOL:MAXIT:U_OUT:INFO_OUT   BiCGStab<D>::solve with Mr = V-cycle; INFO = its, relres
+ *   time:REPS                        times Cycle::apply on the trig RHS, prints one JSON line
+ */
+#include <algorithm>
+#include <array>
+#include <bitset>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <valarray>
+#include <vector>
+
+/* the reference keeps the level list and the finest Level private; open them for inspection */
+#define private public
+#define protected public
+#include <Thunderegg/GMG/Cycle.h>
+#include <Thunderegg/ThundereggDomGen.h>
+#undef private
+#undef protected
+#include <Thunderegg/BiCGStab.h>
+#include <Thunderegg/BilinearInterpolator.h>
+#include <Thunderegg/GMG/CycleFactory2d.h>
+#include <Thunderegg/GMG/CycleFactory3d.h>
+#include <Thunderegg/Operators/DomainWrapOp.h>
+#include <Thunderegg/PatchSolvers/DftPatchSolver.h>
+#include <Thunderegg/PatchSolvers/FftwPatchSolver.h>
+#include <Thunderegg/StarPatchOp.h>
+#include <Thunderegg/TriLinInterp.h>
+#include <Init.h>
+
+using namespace std;
+
+static vector<string> split(const string &s, char c)
+{
+	vector<string> out;
+	string         item;
+	stringstream   ss(s);
+	while (getline(ss, item, c)) out.push_back(item);
+	return out;
+}
+static void read_into(const string &path, Vec v)
+{
+	double *p;
+	int     n;
+	VecGetArray(v, &p);
+	VecGetLocalSize(v, &n);
+	ifstream in(path, ios::binary);
+	if (!in) { cerr << "cannot open " << path << "\n"; exit(2); }
+	in.read((char *) p, (streamsize) n * 8);
+	if (in.gcount() != (streamsize) n * 8) { cerr << "short read " << path << " want " << n << " doubles\n"; exit(2); }
+}
+static void write_from(const string &path, Vec v)
+{
+	double *p;
+	int     n;
+	VecGetArray(v, &p);
+	VecGetLocalSize(v, &n);
+	ofstream out(path, ios::binary);
+	out.write((const char *) p, (streamsize) n * 8);
+}
+
+template <size_t D> struct Traits;
+template <> struct Traits<3> {
+	using Factory = GMG::CycleFactory3d;
+	using Interp  = TriLinInterp;
+	static void rhs(Domain<3> &d, Vec f, Vec e)
+	{
+		auto ffun = [](double x, double y, double z) {
+			x += .3; y += .3; z += .3;
+			return -77.0 / 36 * M_PI * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+		};
+		auto gfun = [](double x, double y, double z) {
+			x += .3; y += .3; z += .3;
+			return sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+		};
+		Init::initDirichlet(d, f, e, ffun, gfun);
+	}
+};
+template <> struct Traits<2> {
+	using Factory = GMG::CycleFactory2d;
+	using Interp  = BilinearInterpolator;
+	static void rhs(Domain<2> &d, Vec f, Vec e)
+	{
+		auto ffun = [](double x, double y) { return (double) (-5 * M_PI * M_PI * sinl(M_PI * y) * cosl(2 * M_PI * x)); };
+		auto gfun = [](double x, double y) { return (double) (sinl(M_PI * y) * cosl(2 * M_PI * x)); };
+		Init::initDirichlet2d(d, f, e, ffun, gfun);
+	}
+};
+
+template <size_t D> struct Ctx {
+	shared_ptr<ThundereggDomGen<D>>  dcg;
+	shared_ptr<GMG::Cycle<D>>        cycle;
+	vector<shared_ptr<Domain<D>>>    domains; /* finest first */
+	vector<shared_ptr<GMG::Level<D>>> levels;
+	shared_ptr<Operator<D>>          A; /* DomainWrapOp on the finest level, as apps/3d/steady.cpp:453 */
+};
+
+/* metadata record, all little-endian:
+ *  header int32: magic 0x474d4731, D, n, nlevels
+ *  per level (finest first): int32 npatch; int32 ints[npatch][6 + 2D*(2 + 2*2^(D-1))];
+ *                            double reals[npatch][2D]  (starts[D], spacings[D])
+ *  ints per patch: id, refine_level, parent_id, orth_on_parent, parent_local_index (index of
+ *  parent_id in the next coarser level's local order, -1 on the coarsest), neumann bits, then
+ *  per side: type (-1 none, 0 normal, 1 coarse, 2 fine), orth_on_coarse (-1 unless coarse),
+ *  ids[2^(D-1)], local_indexes[2^(D-1)] (unused slots -1). */
+template <size_t D> static void dump_meta(Ctx<D> &c, int n, const string &path)
+{
+	ofstream      out(path, ios::binary);
+	const int     nq     = 1 << (D - 1);
+	const int32_t hdr[4] = {0x474d4731, (int32_t) D, n, (int32_t) c.domains.size()};
+	out.write((const char *) hdr, sizeof(hdr));
+	for (size_t l = 0; l < c.domains.size(); l++) {
+		auto &  vec = c.domains[l]->getPatchInfoVector();
+		int32_t np  = vec.size();
+		out.write((const char *) &np, 4);
+		vector<int32_t> ints;
+		vector<double>  reals;
+		for (auto &pi : vec) {
+			ints.push_back(pi->id);
+			ints.push_back(pi->refine_level);
+			ints.push_back(pi->parent_id);
+			ints.push_back(pi->orth_on_parent.toInt());
+			int pl = -1;
+			if (l + 1 < c.domains.size()) pl = c.domains[l + 1]->getPatchInfoMap().at(pi->parent_id)->local_index;
+			ints.push_back(pl);
+			ints.push_back((int32_t) pi->neumann.to_ulong());
+			for (Side<D> s : Side<D>::getValues()) {
+				int32_t type = -1, orth = -1;
+				vector<int32_t> ids(nq, -1), loc(nq, -1);
+				if (pi->hasNbr(s)) {
+					switch (pi->getNbrType(s)) {
+						case NbrType::Normal:
+							type   = 0;
+							ids[0] = pi->getNormalNbrInfo(s).id;
+							loc[0] = pi->getNormalNbrInfo(s).local_index;
+							break;
+						case NbrType::Coarse:
+							type   = 1;
+							ids[0] = pi->getCoarseNbrInfo(s).id;
+							loc[0] = pi->getCoarseNbrInfo(s).local_index;
+							orth   = pi->getCoarseNbrInfo(s).orth_on_coarse.toInt();
+							break;
+						case NbrType::Fine:
+							type = 2;
+							for (int q = 0; q < nq; q++) {
+								ids[q] = pi->getFineNbrInfo(s).ids[q];
+								loc[q] = pi->getFineNbrInfo(s).local_indexes[q];
+							}
+							break;
+					}
+				}
+				ints.push_back(type);
+				ints.push_back(orth);
+				ints.insert(ints.end(), ids.begin(), ids.end());
+				ints.insert(ints.end(), loc.begin(), loc.end());
+			}
+			for (size_t i = 0; i < D; i++) reals.push_back(pi->starts[i]);
+			for (size_t i = 0; i < D; i++) reals.push_back(pi->spacings[i]);
+		}
+		out.write((const char *) ints.data(), ints.size() * 4);
+		out.write((const char *) reals.data(), reals.size() * 8);
+	}
+}
+
+template <size_t D> static int run(int argc, char **argv)
+{
+	string mesh   = argv[2];
+	int    divide = atoi(argv[3]);
+	int    n      = atoi(argv[4]);
+	string solver = argv[5];
+
+	auto t0 = chrono::steady_clock::now();
+	Tree<D> t(mesh);
+	for (int i = 0; i < divide; i++) t.refineLeaves();
+	array<int, D> ns;
+	ns.fill(n);
+
+	Ctx<D> c;
+	c.dcg.reset(new ThundereggDomGen<D>(t, ns, false));
+	shared_ptr<Domain<D>>        finest = c.dcg->getFinestDomain();
+	shared_ptr<PatchOperator<D>> p_op(new StarPatchOp<D>());
+	shared_ptr<IfaceInterp<D>>   p_interp(new typename Traits<D>::Interp());
+	shared_ptr<PatchSolver<D>>   p_solver;
+	if (solver == "fftw") p_solver.reset(new FftwPatchSolver<D>(*finest));
+	else                  p_solver.reset(new DftPatchSolver<D>(*finest));
+	shared_ptr<SchurHelper<D>> sch(new SchurHelper<D>(finest, p_solver, p_op, p_interp));
+	c.A.reset(new DomainWrapOp<D>(sch));
+	GMG::CycleOpts opts; /* defaults: V, 1 pre, 1 post, 1 coarse sweep, all levels */
+	c.cycle = Traits<D>::Factory::getCycle(opts, c.dcg, p_solver, p_op, p_interp);
+	for (auto &d : c.dcg->domain_list) c.domains.push_back(d);
+	{
+		shared_ptr<GMG::Level<D>> l = c.cycle->finest_level;
+		while (l) { c.levels.push_back(l); l = l->coarser; }
+	}
+	double setup_s = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+	if (c.levels.size() != c.domains.size()) { cerr << "level/domain count mismatch\n"; return 3; }
+
+	auto newvec = [&](int l) { return c.domains[l]->getNewDomainVec(); };
+
+	for (int a = 6; a < argc; a++) {
+		vector<string> p = split(argv[a], ':');
+		const string & cmd = p[0];
+		if (cmd == "meta") {
+			dump_meta<D>(c, n, p[1]);
+		} else if (cmd == "rhs") {
+			auto f = newvec(0), e = newvec(0);
+			Traits<D>::rhs(*c.domains[0], f->vec, e->vec);
+			write_from(p[1], f->vec);
+			write_from(p[2], e->vec);
+		} else if (cmd == "apply") {
+			int  l = stoi(p[1]);
+			auto u = newvec(l), o = newvec(l);
+			read_into(p[2], u->vec);
+			c.levels[l]->getOperator().apply(u, o);
+			write_from(p[3], o->vec);
+		} else if (cmd == "smooth") {
+			int  l = stoi(p[1]);
+			auto f = newvec(l), u = newvec(l);
+			read_into(p[2], f->vec);
+			read_into(p[3], u->vec);
+			c.levels[l]->getSmoother().smooth(f, u);
+			write_from(p[4], u->vec);
+		} else if (cmd == "restrict") {
+			int  l = stoi(p[1]);
+			auto fine = newvec(l), coarse = newvec(l + 1);
+			read_into(p[2], fine->vec);
+			c.levels[l]->getRestrictor().restrict(coarse, fine);
+			write_from(p[3], coarse->vec);
+		} else if (cmd == "interp") {
+			int  l = stoi(p[1]);
+			auto coarse = newvec(l + 1), fine = newvec(l);
+			read_into(p[2], coarse->vec);
+			read_into(p[3], fine->vec);
+			c.levels[l + 1]->getInterpolator().interpolate(coarse, fine);
+			write_from(p[4], fine->vec);
+		} else if (cmd == "vcycle") {
+			auto f = newvec(0), u = newvec(0);
+			read_into(p[1], f->vec);
+			c.cycle->apply(f, u);
+			write_from(p[2], u->vec);
+		} else if (cmd == "vhist") {
+			int  ncyc = stoi(p[2]);
+			auto f = newvec(0), u = newvec(0), r = newvec(0), e = newvec(0);
+			read_into(p[1], f->vec);
+			vector<double> hist;
+			double         fn = f->twoNorm();
+			for (int k = 0; k <= ncyc; k++) {
+				c.A->apply(u, r);
+				r->scaleThenAdd(-1, f);
+				hist.push_back(r->twoNorm() / fn);
+				if (k == ncyc) break;
+				c.cycle->apply(r, e);
+				u->add(e);
+			}
+			write_from(p[3], u->vec);
+			ofstream out(p[4], ios::binary);
+			out.write((const char *) hist.data(), hist.size() * 8);
+		} else if (cmd == "bicgstab") {
+			double tol   = stod(p[2]);
+			int    maxit = stoi(p[3]);
+			auto   f = newvec(0), u = newvec(0), r = newvec(0);
+			read_into(p[1], f->vec);
+			shared_ptr<VectorGenerator<D>> vg(new DomainVG<D>(c.domains[0]));
+			auto   t1  = chrono::steady_clock::now();
+			int    its = BiCGStab<D>::solve(vg, c.A, u, f, c.cycle, maxit, tol);
+			double sec = chrono::duration<double>(chrono::steady_clock::now() - t1).count();
+			c.A->apply(u, r);
+			r->scaleThenAdd(-1, f);
+			double info[3] = {(double) its, r->twoNorm() / f->twoNorm(), sec};
+			write_from(p[4], u->vec);
+			ofstream out(p[5], ios::binary);
+			out.write((const char *) info, sizeof(info));
+		} else if (cmd == "time") {
+			int  reps = stoi(p[1]);
+			auto f = newvec(0), e = newvec(0), u = newvec(0);
+			Traits<D>::rhs(*c.domains[0], f->vec, e->vec);
+			c.cycle->apply(f, u); /* warm-up */
+			vector<double> secs;
+			for (int k = 0; k < reps; k++) {
+				auto t1 = chrono::steady_clock::now();
+				c.cycle->apply(f, u);
+				secs.push_back(chrono::duration<double>(chrono::steady_clock::now() - t1).count());
+			}
+			sort(secs.begin(), secs.end());
+			double med   = secs[secs.size() / 2];
+			long   cells = (long) c.domains[0]->getNumLocalPatches() * c.domains[0]->getNumCellsInPatch();
+			printf("{\"cells\": %ld, \"patches\": %d, \"levels\": %zu, \"reps\": %d, \"sec_per_vcycle_median\": %.6e, "
+			       "\"sec_per_vcycle_min\": %.6e, \"dof_per_s\": %.6e, \"setup_s\": %.3f, \"patch_solver\": \"%s\"}\n",
+			       cells, c.domains[0]->getNumLocalPatches(), c.levels.size(), reps, med, secs[0], cells / med,
+			       setup_s, solver.c_str());
+		} else {
+			cerr << "unknown command " << cmd << "\n";
+			return 2;
+		}
+	}
+	return 0;
+}
+
+int main(int argc, char **argv)
+{
+	if (argc < 6) {
+		cerr << "usage: ref_gmg D mesh.bin divide n dft|fftw cmd [cmd...]\n";
+		return 2;
+	}
+	PetscInitialize(nullptr, nullptr, nullptr, nullptr);
+	int D = atoi(argv[1]);
+	return D == 2 ? run<2>(argc, argv) : run<3>(argc, argv);
+}

@@ -1,0 +1,2 @@
+/* see petscsys.h (oracle shim) */
+#include <petscsys.h>
