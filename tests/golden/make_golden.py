@@ -1,0 +1,91 @@
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (oracle/_ref/ref_gmg = the
+reference's unmodified GMG sources compiled against single-rank shims, see oracle/Makefile)
+on seeded inputs.  Run from the repo root in the build container (needs /root/reference only to
+have built oracle/_ref):
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The mesh files under tests/golden/meshes/ are byte copies of the reference's octree fixtures
+(test/*.bin, apps/{2d,3d}/meshes/*.bin: data, not source) so that nothing reads /root/reference
+at test time.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import gmg_oracle as go  # noqa: E402  (only used to read the reference's metadata dump)
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_gmg")
+
+# name, D, mesh, divide, n
+CASES = [
+    ("3d_2uni_n8", 3, "2uni.bin", 0, 8),
+    ("3d_2refine_n8", 3, "2refine.bin", 0, 8),
+    ("3d_2refine_d1_n4", 3, "2refine.bin", 1, 4),
+    ("3d_multi_refine_n4", 3, "multi_refine.bin", 0, 4),
+    ("2d_2d2ref_d1_n8", 2, "2d2ref.bin", 1, 8),
+    ("2d_multi_refine_8_n4", 2, "2d_multi_refine_8.bin", 0, 4),
+]
+
+
+def ref(D, mesh, div, n, *cmds, solver="dft"):
+    subprocess.check_call([REF, str(D), os.path.join(HERE, "meshes", mesh), str(div), str(n), solver, *cmds])
+
+
+def main():
+    for name, D, mesh, div, n in CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            t = lambda f: os.path.join(tmp, f)  # noqa: E731
+            ref(D, mesh, div, n, "meta:" + t("meta"), "rhs:%s:%s" % (t("f"), t("e")))
+            levels = go.read_ref_meta(t("meta"))
+            out = {"D": D, "n": n, "divide": div, "mesh": mesh, "nlevels": len(levels)}
+            for l, L in enumerate(levels):
+                for k in ("ids", "refine_level", "parent_id", "orth_on_parent", "parent_idx", "neumann",
+                          "starts", "spacings", "nbr_type", "nbr_ids", "nbr_idx", "orth_on_coarse"):
+                    out["L%d_%s" % (l, k)] = getattr(L, k)
+            out["rhs_f"] = np.fromfile(t("f"))
+            out["rhs_exact"] = np.fromfile(t("e"))
+            rng = np.random.default_rng(1234)
+            for l, L in enumerate(levels):
+                u = rng.standard_normal(L.cells)
+                f = rng.standard_normal(L.cells)
+                u.tofile(t("u"))
+                f.tofile(t("ff"))
+                cmds = ["apply:%d:%s:%s" % (l, t("u"), t("au")), "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("su"))]
+                out["L%d_in_u" % l] = u
+                out["L%d_in_f" % l] = f
+                if l + 1 < len(levels):
+                    uc = rng.standard_normal(levels[l + 1].cells)
+                    uc.tofile(t("uc"))
+                    out["L%d_in_uc" % l] = uc
+                    cmds += ["restrict:%d:%s:%s" % (l, t("u"), t("rc")),
+                             "interp:%d:%s:%s:%s" % (l, t("uc"), t("u"), t("pi"))]
+                ref(D, mesh, div, n, *cmds)
+                out["L%d_apply" % l] = np.fromfile(t("au"))
+                out["L%d_smooth" % l] = np.fromfile(t("su"))
+                if l + 1 < len(levels):
+                    out["L%d_restrict" % l] = np.fromfile(t("rc"))
+                    out["L%d_interp" % l] = np.fromfile(t("pi"))
+                # the FFTW-planned solver path (through the naive r2r stand-in) must agree too
+                ref(D, mesh, div, n, "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("su2")), solver="fftw")
+                out["L%d_smooth_fftw" % l] = np.fromfile(t("su2"))
+            ref(D, mesh, div, n, "vcycle:%s:%s" % (t("f"), t("v")),
+                "vhist:%s:6:%s:%s" % (t("f"), t("vu"), t("vh")),
+                "bicgstab:%s:1e-12:100:%s:%s" % (t("f"), t("bu"), t("bi")))
+            out["vcycle"] = np.fromfile(t("v"))
+            out["vhist_u"] = np.fromfile(t("vu"))
+            out["vhist"] = np.fromfile(t("vh"))
+            out["bicgstab_u"] = np.fromfile(t("bu"))
+            out["bicgstab_info"] = np.fromfile(t("bi"))[:2]  # iterations, final relative residual
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+            print(name, [L.P for L in levels], "its", out["bicgstab_info"][0])
+
+
+if __name__ == "__main__":
+    main()
