@@ -1,0 +1,237 @@
+#!/usr/bin/env python
+"""bench.py - fp64 GMG V-cycle DOF/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config B|A|C|small]
+
+A "step" is one V(1,1) cycle (GMG::Cycle::apply, zero initial guess) over the whole finest level.
+N = 1 workload: config B of BASELINE.md (apps/3d/steady GMG, uniform octree 4uni.bin --divide 1,
+4096 patches of 16^3 = 16,777,216 cells, 5 levels), trig manufactured RHS resident in HBM.
+One JSON line is printed by rank 0; see README/DESIGN.md for the keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MESHES = os.path.join(ROOT, "tests", "golden", "meshes")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_gmg")
+
+# name -> (D, mesh file, divide, n, description)
+CONFIGS = {
+    "B": (3, "4uni.bin", 1, 16, "config B: apps/3d/steady GMG, uniform octree 4uni.bin --divide 1, 4096 patches of 16^3 (16,777,216 cells), 5 levels, trig RHS"),
+    "A": (2, "2d2uni.bin", 6, 32, "config A: apps/2d/steady2d GMG, uniform quadtree 2d2uni.bin --divide 6, 16384 patches of 32^2 (16,777,216 cells), 8 levels, trig RHS"),
+    "C": (3, "2refine.bin", 3, 16, "config C: apps/3d/steady GMG, refined octree 2refine.bin --divide 3, 7680 patches of 16^3 (31,457,280 cells), 6 levels, trig RHS"),
+    "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
+}
+ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
+SMOOTH_BYTES_PER_CELL = 16.0      # dominant kernel: read f, write u
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_run(cfg_name, reps, replicas):
+    """times the reference's own CPU implementation (oracle/_ref/ref_gmg = the unmodified reference GMG
+    sources on single-rank shims) of one V-cycle; `replicas` concurrent single-rank processes stand in
+    for the MPI ranks the reference would use (no MPI runtime here): an optimistic, comm-free bound."""
+    D, mesh, div, n, desc = CONFIGS[cfg_name]
+    cmd = [REF_BIN, str(D), os.path.join(MESHES, mesh), str(div), str(n), "dft", "time:%d" % reps]
+    t0 = time.time()
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True) for _ in range(replicas)]
+    outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+    wall = time.time() - t0
+    sec = max(o["sec_per_vcycle_median"] for o in outs)
+    cells = outs[0]["cells"]
+    return {"cells_per_replica": cells, "replicas": replicas, "sec_per_vcycle": sec, "dof_per_s": replicas * cells / sec,
+            "wall_s": wall, "desc": desc}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_gmg not built (run `make -C oracle ref` where /root/reference exists)"}))
+        return
+    cores = os.cpu_count() or 1
+    res = cpu_reference_run("small", max(1, args.steps), cores)
+    sample = ("%d concurrent single-rank replicas (one per host core, standing in for MPI ranks; no comm cost) of the reference's "
+              "Cycle::apply on %s; DftPatchSolver; median of %d cycles after 1 warm-up" % (cores, res["desc"], max(1, args.steps)))
+    line = {"impl": "reference", "metric": "fp64 GMG V-cycle DOF/s", "value": res["dof_per_s"], "unit": "DOF/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_vcycle"] * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config][4], "sample": sample},
+            "cpu_baseline": {"value": res["dof_per_s"], "unit": "DOF/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": res["dof_per_s"], "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="B")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import pressurepoissonsolver_b200 as pps
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    D, mesh_file, divide, n, desc = CONFIGS[args.config]
+    ctx = pps.Context(local_rank)
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+    cells = h.ncells(0)
+    level_cells = [h.ncells(l) for l in range(h.nlevels)]
+    f, u = h.new_vec(0), h.new_vec(0)
+    h.init_trig_rhs(f)
+    opts = pps.CycleOpts.default()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        h.vcycle(f, u, opts)
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    l0 = ctx.kernel_launches()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        h.vcycle(f, u, opts)
+    ms = ctx.timer_stop()
+    launches = ctx.kernel_launches() - l0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+    sampler.join()
+    ms_per_step = ms / args.steps
+    total_cells = cells * world  # replicas: every rank runs the same single-GPU problem (multi-GPU sharding: see DESIGN.md)
+    value = total_cells / (ms_per_step * 1e-3)
+
+    # ---- per-kernel profile of the same steps (CUDA events around every launch, graph bypassed) ----
+    ctx.profile_begin()
+    for _ in range(args.steps):
+        h.vcycle(f, u, opts)
+    prof = ctx.profile_end()
+    agg = {}
+    for name, lvl, kms in prof:
+        a = agg.setdefault((name, lvl), [0, 0.0])
+        a[0] += 1
+        a[1] += kms
+    prof_total = sum(v[1] for v in agg.values())
+    smooth_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name == "smooth"]
+    smooth0_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name == "smooth_zero_guess"]
+    dom_ms = (smooth_ms[0] + smooth0_ms[0]) / 2 if smooth_ms and smooth0_ms else None
+    peak, peak_src = measured_peaks()
+    achieved = SMOOTH_BYTES_PER_CELL * cells / (dom_ms * 1e-3) / 1e9 if dom_ms else None
+    smooth_share = sum(v[1] for (name, lvl), v in agg.items() if name.startswith("smooth")) / prof_total if prof_total else None
+    cycle_bytes = ALGO_BYTES_PER_CELL_VISIT * sum(level_cells)
+    cycle_gbs = cycle_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI (H2D of f, cycle, D2H of u inside the timed region) ----
+    fp, up = pps.PinnedBuffer(cells), pps.PinnedBuffer(cells)
+    fp.array[:] = f.download()
+    for _ in range(2):
+        h.vcycle_host(fp, up, opts)
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        h.vcycle_host(fp, up, opts)
+    e2e_ms = ctx.timer_stop() / e2e_steps
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_ms = max(e2e_ms, e2e_wall_ms)
+    assert np.isfinite(up.array).all()
+
+    line = {
+        "metric": "fp64 GMG V-cycle DOF/s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "cycle": "V(1,1), 1 coarse sweep, all levels down to the root patch", "cells": cells,
+                   "levels": level_cells, "l2": "inputs larger than L2 (f and u are %.0f MB each, L2 is 126 MB)" % (cells * 8 / 1e6),
+                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+        "roofline": {"bound": "hbm", "kernel": "smooth_kernel (block-Jacobi DST patch solve) on the finest level",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "peak_source": peak_src, "ms_per_launch": dom_ms,
+                     "algorithmic_bytes_per_launch": SMOOTH_BYTES_PER_CELL * cells, "share_of_step": smooth_share,
+                     "vcycle_algorithmic_gbs": cycle_gbs, "vcycle_frac": cycle_gbs / peak,
+                     "vcycle_bytes_per_dof": cycle_bytes / cells},
+        "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": cells * 8, "d2h_bytes_per_step": cells * 8,
+                "ms_per_step": e2e_ms, "api": "tgpu_vcycle_host (pinned host f -> device, V-cycle, u -> pinned host)"},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "kernel_profile_ms_per_step": {"%s@L%d" % k: round(v[1] / args.steps, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
+        res = cpu_reference_run("small", 3, 1)
+        line["cpu_baseline"] = {"value": res["dof_per_s"], "unit": "DOF/s", "cores": 1, "kind": "reference",
+                                "sample": "reference Cycle::apply (oracle/_ref/ref_gmg, DftPatchSolver, 1 rank = 1 core) on " + res["desc"]
+                                          + "; median of 3 cycles after 1 warm-up; DOF/s per V-cycle is size-independent to ~5% (3.56e6 at 2.1M cells vs 3.42e6 at 16.8M cells measured in the build container)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

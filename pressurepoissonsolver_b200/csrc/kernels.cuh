@@ -1,0 +1,729 @@
+// kernels.cuh - hand-written sm_100a kernels of the GMG hot path (fp64, patch-contiguous storage).
+//
+// Kernel inventory (reference function each one replaces; paths relative to src/Thunderegg/):
+//   smooth_kernel        SchurHelper::solveWithSolution (SchurHelper.h:319-331) =
+//                        interface interpolation (TriLinInterp.cpp:60-172 / BilinearInterpolator.cpp:61-117)
+//                        + StarPatchOp::addInterfaceToRHS (StarPatchOp.h:185-203)
+//                        + patch solve (PatchSolvers/FftwPatchSolver.h:174-206, DftPatchSolver.h:173-216)
+//   apply_kernel         SchurHelper::apply (SchurHelper.h:361-376) + StarPatchOp::applyWithInterface
+//                        (StarPatchOp.h:28-184), optionally fused with r = f - Au (GMG/Cycle.h:59-61)
+//                        and AvgRstr::restrict (GMG/AvgRstr.h:78-113)
+//   extract_faces_kernel the boundary-cell slices LocalData::getSliceOnSide yields (Vector.h:153-177)
+//   prolong_faces_kernel / prolong_add_kernel   DrctIntp::interpolate (GMG/DrctIntp.h:80-113)
+//   restrict_kernel      AvgRstr::restrict (GMG/AvgRstr.h:78-113)
+//   blas1 / reduce       Vector<D> ops (Vector.h:190-321)
+//
+// Ghost fill: the reference couples patches through interface values gamma.
+// Here every kernel that produces a level vector also emits the 2D boundary-cell slices of each
+// patch into a contiguous "face buffer" F[patch][side][N^(D-1)]; gamma for a patch side is then
+// evaluated on the fly from the patch's own face and its neighbours' opposite faces (normal,
+// coarse and fine neighbours) with the reference's weights.  No interface vector is stored.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace tgpu
+{
+enum { NBR_NONE = -1, NBR_NORMAL = 0, NBR_COARSE = 1, NBR_FINE = 2 };
+
+// Device-side neighbour table entry: everything a kernel needs to know about one patch.
+struct __align__(16) PatchMeta {
+	double  inv_h2; // 1 / h^2
+	double  h2;     // h^2
+	int32_t parent_idx;
+	int8_t  orth_on_parent; // -1: same patch on the coarser level
+	uint8_t neumann;
+	int8_t  nbr_type[6];
+	int8_t  orth_on_coarse[6];
+	int8_t  pad_[2];
+	int32_t nbr_idx[6][4];
+	int32_t pad2_[3];
+};
+
+constexpr int TGPU_THREADS = 256;
+#ifndef SMOOTH_MIN_BLOCKS
+#define SMOOTH_MIN_BLOCKS 2
+#endif
+
+template <int D, int N> struct Geo {
+	static constexpr int M   = (D == 2) ? N : N * N;     // pencils per patch = face size
+	static constexpr int NC  = M * N;                    // cells per patch
+	static constexpr int S   = 2 * D;                    // sides
+	static constexpr int Q   = 1 << (D - 1);             // fine neighbours per side
+	static constexpr int PPB = TGPU_THREADS / M;         // patches per block
+	static constexpr int ROW = N + 1;                    // padded row (bank-conflict-free pencils)
+	static constexpr int SP  = M * ROW;                  // padded patch size in smem (doubles)
+	static constexpr int NG  = N + 2;                    // row with ghosts
+	static constexpr int GP  = (D == 2) ? NG * NG : NG * NG * NG;
+	static_assert(M <= TGPU_THREADS, "patch face larger than the block");
+};
+
+// ---------------------------------------------------------------------------------------------
+// transform tables (DftPatchSolver.h:237-289), symmetric halves only.
+//   fwd[k*H + j] = sin(pi/N (k+1)(j+1/2)),            k < N, j < H = N/2      (DST-II rows)
+//   inv[i*N + j] = sin(pi/N (i+1/2)(j+1)), j < N-1;  inv[i*N + N-1] = 0.5 (-1)^i,  i < H  (DST-III rows)
+// ---------------------------------------------------------------------------------------------
+__constant__ double c_fwd4[4 * 2], c_inv4[2 * 4];
+__constant__ double c_fwd8[8 * 4], c_inv8[4 * 8];
+__constant__ double c_fwd16[16 * 8], c_inv16[8 * 16];
+__constant__ double c_fwd32[32 * 16], c_inv32[16 * 32];
+
+template <int N> __device__ __forceinline__ double cfwd(int i)
+{
+	if (N == 4) return c_fwd4[i];
+	if (N == 8) return c_fwd8[i];
+	if (N == 16) return c_fwd16[i];
+	return c_fwd32[i];
+}
+template <int N> __device__ __forceinline__ double cinv(int i)
+{
+	if (N == 4) return c_inv4[i];
+	if (N == 8) return c_inv8[i];
+	if (N == 16) return c_inv16[i];
+	return c_inv32[i];
+}
+
+// DST-II of a register pencil using S[k][N-1-j] = (-1)^k S[k][j]: N adds + N*N/2 FMAs.
+template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N])
+{
+	constexpr int H = N / 2;
+	double        e[H], o[H];
+#pragma unroll
+	for (int j = 0; j < H; j++) {
+		e[j] = v[j] + v[N - 1 - j];
+		o[j] = v[j] - v[N - 1 - j];
+	}
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		double acc = 0.0;
+#pragma unroll
+		for (int j = 0; j < H; j++) acc = fma(cfwd<N>(k * H + j), (k & 1) ? o[j] : e[j], acc);
+		v[k] = acc;
+	}
+}
+// DST-III using T[N-1-i][j] = (-1)^j T[i][j]: y_i = E_i + O_i, y_{N-1-i} = E_i - O_i.
+template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N])
+{
+	constexpr int H = N / 2;
+	double        E[H], O[H];
+#pragma unroll
+	for (int i = 0; i < H; i++) {
+		double ea = 0.0, oa = 0.0;
+#pragma unroll
+		for (int j = 0; j < N; j += 2) {
+			ea = fma(cinv<N>(i * N + j), v[j], ea);
+			oa = fma(cinv<N>(i * N + j + 1), v[j + 1], oa);
+		}
+		E[i] = ea;
+		O[i] = oa;
+	}
+#pragma unroll
+	for (int i = 0; i < H; i++) {
+		v[i]         = E[i] + O[i];
+		v[N - 1 - i] = E[i] - O[i];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// interface value gamma for entry m of side s of patch p, from the face buffer F.
+// Weights: SURVEY App. A.2 (TriLinInterp.cpp:60-172, BilinearInterpolator.cpp:61-117);
+// which contributions meet on an interface: SchurInfo.h:141-150,253-259,363-370.
+// ---------------------------------------------------------------------------------------------
+template <int D, int N>
+__device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s, int m, const double *__restrict__ F)
+{
+	using G           = Geo<D, N>;
+	const double *own = F + ((size_t) p * G::S + s) * G::M;
+	const double  a   = own[m];
+	const int     t   = pm.nbr_type[s];
+	if (t == NBR_NORMAL) {
+		const double *nb = F + ((size_t) pm.nbr_idx[s][0] * G::S + (s ^ 1)) * G::M;
+		return 0.5 * a + 0.5 * nb[m];
+	}
+	if (t == NBR_COARSE) {
+		const int     orth = pm.orth_on_coarse[s];
+		const double *nb   = F + ((size_t) pm.nbr_idx[s][0] * G::S + (s ^ 1)) * G::M;
+		if (D == 2) {
+			const double f2f = 5.0 / 6 * a - 1.0 / 6 * own[m ^ 1];
+			return f2f + 2.0 / 6 * nb[(m + (orth & 1) * N) / 2];
+		} else {
+			const int    i = m % N, j = m / N;
+			const int    i0 = i & ~1, j0 = j & ~1;
+			const double b[4] = {own[j0 * N + i0], own[j0 * N + i0 + 1], own[(j0 + 1) * N + i0], own[(j0 + 1) * N + i0 + 1]};
+			const int    self = (i & 1) | ((j & 1) << 1);
+			double       acc  = 11 * a;
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+				if (q != self) acc -= b[q];
+			const int ci = (i + (orth & 1) * N) / 2, cj = (j + ((orth >> 1) & 1) * N) / 2;
+			return acc / 12.0 + 4.0 * nb[cj * N + ci] / 12.0;
+		}
+	}
+	// NBR_FINE: I am the coarse side
+	if (D == 2) {
+		const int     q  = m >= N / 2;
+		const int     fi = 2 * (m % (N / 2));
+		const double *nb = F + ((size_t) pm.nbr_idx[s][q] * G::S + (s ^ 1)) * G::M;
+		return 1.0 / 3 * a + (1.0 / 3 * nb[fi] + 1.0 / 3 * nb[fi + 1]);
+	} else {
+		const int     i = m % N, j = m / N;
+		const int     q  = (i >= N / 2) | ((j >= N / 2) << 1);
+		const int     fi = 2 * (i % (N / 2)), fj = 2 * (j % (N / 2));
+		const double *nb = F + ((size_t) pm.nbr_idx[s][q] * G::S + (s ^ 1)) * G::M;
+		double        g  = 2.0 / 6.0 * a;
+		g += 1.0 / 6.0 * nb[fj * N + fi];
+		g += 1.0 / 6.0 * nb[fj * N + fi + 1];
+		g += 1.0 / 6.0 * nb[(fj + 1) * N + fi];
+		g += 1.0 / 6.0 * nb[(fj + 1) * N + fi + 1];
+		return g;
+	}
+}
+
+// cell index inside a patch of face entry m on side s (Vector.h:153-177: the slice drops axis s/2
+// and keeps the remaining axes in order)
+template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, int (&c)[3])
+{
+	const int ax  = s >> 1;
+	const int pos = (s & 1) ? N - 1 : 0;
+	if (D == 2) {
+		c[ax]     = pos;
+		c[1 - ax] = m;
+		c[2]      = 0;
+	} else {
+		const int i = m % N, j = m / N;
+		if (ax == 0) c[0] = pos, c[1] = i, c[2] = j;
+		else if (ax == 1) c[0] = i, c[1] = pos, c[2] = j;
+		else c[0] = i, c[1] = j, c[2] = pos;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-Jacobi smoother: u_p <- S_p^-1 (f_p - (2/h^2) E^T gamma(F_in)),  one exact DST patch solve
+// per patch, all in shared memory / registers.  256 threads handle PPB = 256 / N^(D-1) patches.
+//   ZERO_GUESS: gamma == 0 (first sweep of a cycle, GMG/Cycle.h:118 u->set(0)), F_in is not read.
+//   EMIT:       also write the new boundary-cell slices to F_out.
+// eig[k] = (2/N)^D / sum_axes(-4 sin^2((k_a+1) pi / 2N))   (FftwPatchSolver.h:152-170, DftPatchSolver.h:214)
+// ---------------------------------------------------------------------------------------------
+template <int D, int N, bool ZERO_GUESS, bool EMIT>
+__global__ void __launch_bounds__(TGPU_THREADS, SMOOTH_MIN_BLOCKS)
+smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ f, double *__restrict__ u,
+              const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig)
+{
+	using G = Geo<D, N>;
+	extern __shared__ double smem[];
+	double *Sall = smem;                  // [PPB][SP]
+	double *Gall = smem + G::PPB * G::SP; // [PPB][S][M]   (unused when ZERO_GUESS)
+
+	const int  t     = threadIdx.x;
+	const int  pb    = blockIdx.x * G::PPB;
+	const int  pp    = t / G::M;
+	const int  m     = t % G::M;
+	const int  p     = pb + pp;
+	const bool valid = p < P;
+
+	// ---- load f (coalesced over the PPB contiguous patches of this block) ----
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		const int    e  = t + TGPU_THREADS * k;
+		const int    lp = e / G::NC, c = e % G::NC;
+		const double val = (pb + lp < P) ? __ldg(f + (size_t) (pb + lp) * G::NC + c) : 0.0;
+		Sall[lp * G::SP + (c / N) * G::ROW + (c % N)] = val;
+	}
+	double *S = Sall + pp * G::SP;
+	double  cfac = 0.0, h2 = 0.0;
+	int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
+	if (valid) {
+		const PatchMeta &pm = meta[p];
+		cfac                = 2.0 * pm.inv_h2;
+		h2                  = pm.h2;
+		if (!ZERO_GUESS) {
+			double *Gp = Gall + pp * G::S * G::M;
+#pragma unroll
+			for (int s = 0; s < G::S; s++) {
+				ntype[s] = pm.nbr_type[s];
+				if (ntype[s] != NBR_NONE) Gp[s * G::M + m] = iface_gamma<D, N>(pm, p, s, m, Fin);
+			}
+		}
+	}
+	__syncthreads();
+
+	if (!ZERO_GUESS) {
+		const double *Gp = Gall + pp * G::S * G::M;
+		// x faces: face entry m <-> row m (2D: y; 3D: y + N z)
+		if (ntype[0] != NBR_NONE) S[m * G::ROW] -= cfac * Gp[0 * G::M + m];
+		if (ntype[1] != NBR_NONE) S[m * G::ROW + N - 1] -= cfac * Gp[1 * G::M + m];
+		__syncthreads();
+		if (D == 3) {
+			// y faces: entry m = x + N z
+			const int x = m % N, z = m / N;
+			if (ntype[2] != NBR_NONE) S[(z * N) * G::ROW + x] -= cfac * Gp[2 * G::M + m];
+			if (ntype[3] != NBR_NONE) S[(z * N + N - 1) * G::ROW + x] -= cfac * Gp[3 * G::M + m];
+			__syncthreads();
+		}
+	}
+
+	double v[N];
+	// ---- forward along the last axis (pencil = plane index m) ----
+	{
+		const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
+		const int step = (D == 2) ? G::ROW : N * G::ROW;
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+		if (!ZERO_GUESS) {
+			const double *Gp = Gall + pp * G::S * G::M;
+			if (ntype[G::S - 2] != NBR_NONE) v[0] -= cfac * Gp[(G::S - 2) * G::M + m];
+			if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= cfac * Gp[(G::S - 1) * G::M + m];
+		}
+		dst2_forward<N>(v);
+#pragma unroll
+		for (int k = 0; k < N; k++) S[base + k * step] = v[k];
+	}
+	__syncthreads();
+	if (D == 3) { // forward along y: pencil (x, z)
+		const int base = (m / N) * N * G::ROW + (m % N);
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
+		dst2_forward<N>(v);
+#pragma unroll
+		for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+		__syncthreads();
+	}
+	// ---- x: forward, divide by the eigenvalues, inverse (pencil = row m) ----
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
+		dst2_forward<N>(v);
+		const double *er = eig + (size_t) m * N;
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k);
+		dst3_inverse<N>(v);
+#pragma unroll
+		for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
+	}
+	__syncthreads();
+	if (D == 3) { // inverse along y
+		const int base = (m / N) * N * G::ROW + (m % N);
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
+		dst3_inverse<N>(v);
+#pragma unroll
+		for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+		__syncthreads();
+	}
+	// ---- inverse along the last axis, write u (and the new faces) ----
+	{
+		const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
+		const int step = (D == 2) ? G::ROW : N * G::ROW;
+#pragma unroll
+		for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+		dst3_inverse<N>(v);
+		if (valid) {
+			double *up = u + (size_t) p * G::NC + m;
+#pragma unroll
+			for (int k = 0; k < N; k++) up[k * G::M] = v[k];
+			if (EMIT) {
+				double *Fp = Fout + (size_t) p * G::S * G::M;
+				Fp[(G::S - 2) * G::M + m] = v[0];
+				Fp[(G::S - 1) * G::M + m] = v[N - 1];
+				if (D == 2) {
+					if (m == 0) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[0 * G::M + k] = v[k];
+					}
+					if (m == N - 1) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[1 * G::M + k] = v[k];
+					}
+				} else {
+					const int x = m % N, y = m / N;
+					if (x == 0) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[0 * G::M + k * N + y] = v[k];
+					}
+					if (x == N - 1) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[1 * G::M + k * N + y] = v[k];
+					}
+					if (y == 0) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[2 * G::M + k * N + x] = v[k];
+					}
+					if (y == N - 1) {
+#pragma unroll
+						for (int k = 0; k < N; k++) Fp[3 * G::M + k * N + x] = v[k];
+					}
+				}
+			}
+		}
+	}
+}
+template <int D, int N, bool ZERO_GUESS> constexpr size_t smooth_smem_bytes()
+{
+	using G = Geo<D, N>;
+	return sizeof(double) * (size_t) (G::PPB * G::SP + (ZERO_GUESS ? 0 : G::PPB * G::S * G::M));
+}
+
+// ---------------------------------------------------------------------------------------------
+// operator apply with fused ghost fill; MODE 0: out = A u, 1: out = f - A u,
+// 2: coarse = AvgRstr(f - A u) (the fine residual is never written to memory).
+// The patch plus a ghost layer is staged in shared memory; ghost = 2 gamma - a on sides with a
+// neighbour, -a on Dirichlet and +a on Neumann domain sides (StarPatchOp.h:46-64).
+// ---------------------------------------------------------------------------------------------
+template <int D, int N> __device__ __forceinline__ int gidx(int x, int y, int z)
+{
+	using G = Geo<D, N>;
+	return (D == 2) ? (y + 1) * G::NG + (x + 1) : ((z + 1) * G::NG + (y + 1)) * G::NG + (x + 1);
+}
+
+template <int D, int N, int MODE>
+__global__ void __launch_bounds__(TGPU_THREADS)
+apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ u, const double *__restrict__ f,
+             const double *__restrict__ F, double *__restrict__ out, double *__restrict__ coarse)
+{
+	using G = Geo<D, N>;
+	extern __shared__ double smem[];
+	const int  t     = threadIdx.x;
+	const int  pb    = blockIdx.x * G::PPB;
+	const int  pp    = t / G::M;
+	const int  m     = t % G::M;
+	const int  p     = pb + pp;
+	const bool valid = p < P;
+
+	// ---- interior (coalesced) ----
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		const int    e  = t + TGPU_THREADS * k;
+		const int    lp = e / G::NC, c = e % G::NC;
+		const double val = (pb + lp < P) ? __ldg(u + (size_t) (pb + lp) * G::NC + c) : 0.0;
+		const int    x = c % N, y = (c / N) % N, z = (D == 2) ? 0 : c / (N * N);
+		smem[lp * G::GP + gidx<D, N>(x, y, z)] = val;
+	}
+	double *U = smem + pp * G::GP;
+	// ---- ghost layer ----
+	double inv_h2 = 0.0;
+	if (valid) {
+		const PatchMeta &pm = meta[p];
+		inv_h2              = pm.inv_h2;
+#pragma unroll
+		for (int s = 0; s < G::S; s++) {
+			const double a = __ldg(F + ((size_t) p * G::S + s) * G::M + m);
+			double       g;
+			if (pm.nbr_type[s] == NBR_NONE) g = ((pm.neumann >> s) & 1) ? a : -a;
+			else g = 2.0 * iface_gamma<D, N>(pm, p, s, m, F) - a;
+			int c[3];
+			face_cell<D, N>(s, m, c);
+			c[s >> 1] += (s & 1) ? 1 : -1;
+			U[gidx<D, N>(c[0], c[1], c[2])] = g;
+		}
+	}
+	__syncthreads();
+
+	// ---- stencil, marching along the last axis ----
+	const int x = m % N, y = (D == 2) ? 0 : m / N;
+	double    r[N];
+	{
+		double lo = (D == 2) ? U[gidx<D, N>(x, -1, 0)] : U[gidx<D, N>(x, y, -1)];
+		double ce = (D == 2) ? U[gidx<D, N>(x, 0, 0)] : U[gidx<D, N>(x, y, 0)];
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			const double hi = (D == 2) ? U[gidx<D, N>(x, k + 1, 0)] : U[gidx<D, N>(x, y, k + 1)];
+			double       acc;
+			if (D == 2) {
+				acc = (U[gidx<D, N>(x - 1, k, 0)] - 2 * ce + U[gidx<D, N>(x + 1, k, 0)]) + (lo - 2 * ce + hi);
+			} else {
+				acc = (U[gidx<D, N>(x - 1, y, k)] - 2 * ce + U[gidx<D, N>(x + 1, y, k)])
+				      + (U[gidx<D, N>(x, y - 1, k)] - 2 * ce + U[gidx<D, N>(x, y + 1, k)]) + (lo - 2 * ce + hi);
+			}
+			r[k] = acc * inv_h2;
+			lo   = ce;
+			ce   = hi;
+		}
+	}
+	if (MODE == 0) {
+		if (valid) {
+			double *op = out + (size_t) p * G::NC + m;
+#pragma unroll
+			for (int k = 0; k < N; k++) op[k * G::M] = r[k];
+		}
+		return;
+	}
+	if (valid) {
+		const double *fp = f + (size_t) p * G::NC + m;
+#pragma unroll
+		for (int k = 0; k < N; k++) r[k] = __ldg(fp + k * G::M) - r[k];
+	}
+	if (MODE == 1) {
+		if (valid) {
+			double *op = out + (size_t) p * G::NC + m;
+#pragma unroll
+			for (int k = 0; k < N; k++) op[k * G::M] = r[k];
+		}
+		return;
+	}
+	// ---- MODE 2: restrict.  Stage r densely in smem (aliasing U), then average 2^D cells ----
+	__syncthreads();
+	double *R = smem; // [PPB][NC]
+#pragma unroll
+	for (int k = 0; k < N; k++) R[pp * G::NC + k * G::M + m] = r[k];
+	__syncthreads();
+	constexpr int H     = N / 2;
+	constexpr int CC    = G::NC >> D;      // coarse cells per patch
+	constexpr int ITEMS = G::PPB * G::NC;  // fine cells per block
+	// copy patches (present on both levels) move all NC cells; refined patches write CC averages.
+	for (int e = t; e < ITEMS; e += TGPU_THREADS) {
+		const int lp = e / G::NC, c = e % G::NC;
+		const int q  = pb + lp;
+		if (q >= P) continue;
+		const PatchMeta &qm   = meta[q];
+		const int        orth = qm.orth_on_parent;
+		double *         dst  = coarse + (size_t) qm.parent_idx * G::NC;
+		if (orth < 0) {
+			dst[c] = R[lp * G::NC + c];
+		} else if (c < CC) {
+			const int cx = c % H, cy = (c / H) % H, cz = (D == 2) ? 0 : c / (H * H);
+			double    acc = 0.0;
+			// reference accumulation order: x fastest, then y, then z (GMG/AvgRstr.h:95-102)
+#pragma unroll
+			for (int dz = 0; dz < (D == 2 ? 1 : 2); dz++)
+#pragma unroll
+				for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+					for (int dx = 0; dx < 2; dx++) {
+						const int fi = ((2 * cz + dz) * N + (2 * cy + dy)) * N + (2 * cx + dx);
+						acc += R[lp * G::NC + fi] / (1 << D);
+					}
+			const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
+			dst[((cz + oz) * N + (cy + oy)) * N + (cx + ox)] = acc;
+		}
+	}
+}
+template <int D, int N> constexpr size_t apply_smem_bytes() { return sizeof(double) * (size_t) (Geo<D, N>::PPB * Geo<D, N>::GP); }
+
+// ---------------------------------------------------------------------------------------------
+// face buffer helpers
+// ---------------------------------------------------------------------------------------------
+template <int D, int N>
+__global__ void extract_faces_kernel(int P, const double *__restrict__ u, double *__restrict__ F)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::S * G::M;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int    m = (int) (i % G::M), s = (int) ((i / G::M) % G::S);
+		const size_t p = i / ((size_t) G::M * G::S);
+		int          c[3];
+		face_cell<D, N>(s, m, c);
+		F[i] = __ldg(u + p * G::NC + (c[2] * N + c[1]) * N + c[0]);
+	}
+}
+// coarse cell that fine cell c of a patch with orthant `orth` on its parent lies in (DrctIntp.h:92-111)
+template <int D, int N> __device__ __forceinline__ int parent_cell(int orth, const int (&c)[3])
+{
+	if (orth < 0) return (c[2] * N + c[1]) * N + c[0];
+	const int cx = (c[0] + (orth & 1) * N) / 2, cy = (c[1] + ((orth >> 1) & 1) * N) / 2;
+	const int cz = (D == 2) ? 0 : (c[2] + ((orth >> 2) & 1) * N) / 2;
+	return (cz * N + cy) * N + cx;
+}
+// F_fine += (P u_coarse) restricted to the boundary cells: all the post-smoother ever reads of the
+// prolonged correction (SchurHelper.h:319-331 only uses u through its face slices).
+template <int D, int N>
+__global__ void prolong_faces_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ uc,
+                                     double *__restrict__ F)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::S * G::M;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int    m = (int) (i % G::M), s = (int) ((i / G::M) % G::S);
+		const size_t p = i / ((size_t) G::M * G::S);
+		int          c[3];
+		face_cell<D, N>(s, m, c);
+		const PatchMeta &pm = meta[p];
+		F[i] += __ldg(uc + (size_t) pm.parent_idx * G::NC + parent_cell<D, N>(pm.orth_on_parent, c));
+	}
+}
+template <int D, int N>
+__global__ void prolong_add_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ uc,
+                                   double *__restrict__ uf)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int    ci = (int) (i % G::NC);
+		const size_t p  = i / G::NC;
+		const int    c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
+		const PatchMeta &pm = meta[p];
+		uf[i] += __ldg(uc + (size_t) pm.parent_idx * G::NC + parent_cell<D, N>(pm.orth_on_parent, c));
+	}
+}
+// thread per destination (coarse-resolution) cell of every fine patch; bit-exact w.r.t. AvgRstr.h:88-107
+template <int D, int N>
+__global__ void restrict_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ fine,
+                                double *__restrict__ coarse)
+{
+	using G            = Geo<D, N>;
+	constexpr int H    = N / 2;
+	constexpr int CC   = G::NC >> D;
+	const size_t total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int        c = (int) (i % G::NC);
+		const size_t     p = i / G::NC;
+		const PatchMeta &pm = meta[p];
+		const int        orth = pm.orth_on_parent;
+		double *         dst  = coarse + (size_t) pm.parent_idx * G::NC;
+		const double *   src  = fine + p * G::NC;
+		if (orth < 0) {
+			dst[c] = src[c];
+		} else if (c < CC) {
+			const int cx = c % H, cy = (c / H) % H, cz = (D == 2) ? 0 : c / (H * H);
+			double    acc = 0.0;
+			for (int dz = 0; dz < (D == 2 ? 1 : 2); dz++)
+				for (int dy = 0; dy < 2; dy++)
+					for (int dx = 0; dx < 2; dx++)
+						acc += src[((2 * cz + dz) * N + (2 * cy + dy)) * N + (2 * cx + dx)] / (1 << D);
+			const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
+			dst[((cz + oz) * N + (cy + oy)) * N + (cx + ox)] = acc;
+		}
+	}
+}
+
+// weighted point-Jacobi sweep u <- u + omega D^-1 (f - A u); the residual comes from apply_kernel MODE 1
+// and the diagonal of the ghost-eliminated operator is -(2D + #closed sides)/h^2 per cell; provided as
+// the "weighted-Jacobi option" of the north star (no reference counterpart).
+template <int D, int N>
+__global__ void jacobi_update_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ r,
+                                     double *__restrict__ u, double omega)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int        ci = (int) (i % G::NC);
+		const size_t     p  = i / G::NC;
+		const PatchMeta &pm = meta[p];
+		const int        c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
+		double           diag = -2.0 * D;
+		for (int a = 0; a < D; a++) {
+			if (c[a] == 0) diag += (pm.nbr_type[2 * a] == NBR_NONE) ? (((pm.neumann >> (2 * a)) & 1) ? 1.0 : -1.0) : 0.0;
+			if (c[a] == N - 1)
+				diag += (pm.nbr_type[2 * a + 1] == NBR_NONE) ? (((pm.neumann >> (2 * a + 1)) & 1) ? 1.0 : -1.0) : 0.0;
+		}
+		u[i] += omega * r[i] / (diag * pm.inv_h2);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// BLAS-1 (Vector.h:190-262) and reductions (Vector.h:283-321, warp-shuffle + block partials)
+// ---------------------------------------------------------------------------------------------
+enum Blas1Op { B_SET, B_SCALE, B_SHIFT, B_COPY, B_ADD, B_AXPY, B_AXPBY2, B_SCALE_ADD, B_SCALE_ADDS, B_SCALE_ADDS2 };
+template <int OP>
+__global__ void blas1_kernel(size_t n, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ b,
+                             double alpha, double beta, double gamma)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		if (OP == B_SET) v[i] = alpha;
+		else if (OP == B_SCALE) v[i] *= alpha;
+		else if (OP == B_SHIFT) v[i] += alpha;
+		else if (OP == B_COPY) v[i] = a[i];
+		else if (OP == B_ADD) v[i] += a[i];
+		else if (OP == B_AXPY) v[i] += a[i] * alpha;
+		else if (OP == B_AXPBY2) v[i] += a[i] * alpha + b[i] * beta;
+		else if (OP == B_SCALE_ADD) v[i] = alpha * v[i] + a[i];
+		else if (OP == B_SCALE_ADDS) v[i] = alpha * v[i] + beta * a[i];
+		else if (OP == B_SCALE_ADDS2) v[i] = alpha * v[i] + beta * a[i] + gamma * b[i];
+	}
+}
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+	return x;
+}
+__device__ __forceinline__ double warp_max(double x)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+	return x;
+}
+// OP 0: sum a*b, 1: max |a|.  Stage 1 writes one partial per block; stage 2 (one block) finishes.
+template <int OP>
+__global__ void reduce_stage1(size_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ partial)
+{
+	double acc = 0.0;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		if (OP == 0) acc = fma(a[i], b[i], acc);
+		else acc = fmax(acc, fabs(a[i]));
+	}
+	__shared__ double ws[32];
+	acc = OP == 0 ? warp_sum(acc) : warp_max(acc);
+	if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double x = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+		x        = OP == 0 ? warp_sum(x) : warp_max(x);
+		if (threadIdx.x == 0) partial[blockIdx.x] = x;
+	}
+}
+template <int OP> __global__ void reduce_stage2(int nb, const double *__restrict__ partial, double *__restrict__ result)
+{
+	double acc = 0.0;
+	for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+		if (OP == 0) acc += partial[i];
+		else acc = fmax(acc, partial[i]);
+	}
+	__shared__ double ws[32];
+	acc = OP == 0 ? warp_sum(acc) : warp_max(acc);
+	if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double x = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+		x        = OP == 0 ? warp_sum(x) : warp_max(x);
+		if (threadIdx.x == 0) *result = x;
+	}
+}
+
+// manufactured trig problem (apps/3d/steady.cpp:253-265, apps/2d/steady.cpp:314-316) with the
+// Dirichlet data folded into f on domain-boundary cells (apps/shared/Init.cpp:183-241,329-357)
+template <int D> __device__ __forceinline__ double trig_exact(double x, double y, double z)
+{
+	if (D == 2) return sin(M_PI * y) * cos(2 * M_PI * x);
+	x += .3, y += .3, z += .3;
+	return sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+}
+template <int D> __device__ __forceinline__ double trig_rhs(double x, double y, double z)
+{
+	if (D == 2) return -5 * M_PI * M_PI * sin(M_PI * y) * cos(2 * M_PI * x);
+	x += .3, y += .3, z += .3;
+	return -77.0 / 36 * M_PI * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+}
+template <int D, int N>
+__global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ starts,
+                                 const double *__restrict__ spacing, double *__restrict__ f, double *__restrict__ exact)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int        ci = (int) (i % G::NC);
+		const size_t     p  = i / G::NC;
+		const PatchMeta &pm = meta[p];
+		const int        c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
+		double           h[3] = {0, 0, 0}, st[3] = {0, 0, 0}, x[3] = {0, 0, 0};
+		for (int a = 0; a < D; a++) {
+			h[a]  = spacing[p * D + a];
+			st[a] = starts[p * D + a];
+			x[a]  = st[a] + h[a] / 2.0 + h[a] * c[a];
+		}
+		double val = trig_rhs<D>(x[0], x[1], x[2]);
+		for (int a = 0; a < D; a++) {
+			double xb[3] = {x[0], x[1], x[2]};
+			if (c[a] == 0 && pm.nbr_type[2 * a] == NBR_NONE) {
+				xb[a] = st[a];
+				val -= 2 * trig_exact<D>(xb[0], xb[1], xb[2]) / (h[a] * h[a]);
+			}
+			if (c[a] == N - 1 && pm.nbr_type[2 * a + 1] == NBR_NONE) {
+				xb[a] = st[a] + h[a] * N;
+				val -= 2 * trig_exact<D>(xb[0], xb[1], xb[2]) / (h[a] * h[a]);
+			}
+		}
+		f[i] = val;
+		if (exact) exact[i] = trig_exact<D>(x[0], x[1], x[2]);
+	}
+}
+} // namespace tgpu

@@ -1,0 +1,1082 @@
+// tgpu.cu - C-ABI implementation (include/tgpu.h) on top of the kernels in kernels.cuh.
+// Host-side structure: context (stream, scratch), hierarchy (device neighbour tables, per-level
+// work vectors and face buffers, eigenvalue table), vectors, cycle driver with CUDA-graph replay.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tgpu.h"
+#include "kernels.cuh"
+#include "mesh.h"
+
+using namespace tgpu;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg)
+{
+	g_last_error = msg;
+	return code;
+}
+#define CU(call)                                                                                           \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess)                                                                             \
+			return fail(TGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" \
+			                           + std::to_string(__LINE__) + ")");                                  \
+	} while (0)
+#define TRY(expr)                   \
+	do {                            \
+		int rc_ = (expr);           \
+		if (rc_ != TGPU_OK) return rc_; \
+	} while (0)
+#define API_BEGIN try {
+#define API_END                                            \
+	}                                                      \
+	catch (const std::exception &ex)                       \
+	{                                                      \
+		return fail(TGPU_ERR_ARG, ex.what());              \
+	}                                                      \
+	catch (...)                                            \
+	{                                                      \
+		return fail(TGPU_ERR_ARG, "unknown C++ exception"); \
+	}
+
+extern "C" const char *tgpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *tgpu_version(void) { return "tgpu 0.1 (sm_100a, fp64)"; }
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct tgpu_ctx {
+	int          device     = 0;
+	cudaStream_t stream     = nullptr;
+	bool         own_stream = false;
+	int          sm_count   = 148;
+	double *     d_partial  = nullptr; // [MAX_PARTIAL]
+	double *     d_result   = nullptr; // [8]
+	double *     h_result   = nullptr; // pinned [8]
+	cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+	int64_t      launches  = 0;
+	bool         capturing = false;
+	int64_t      captured  = 0;
+	// per-launch profiling
+	bool                          profiling = false;
+	const char *                  tag_name  = "kernel";
+	int                           tag_level = -1;
+	std::vector<cudaEvent_t>      prof_events;
+	std::vector<TgpuProfileEntry> prof_entries;
+};
+struct Tag {
+	tgpu_ctx *  ctx;
+	const char *old_name;
+	int         old_level;
+	Tag(tgpu_ctx *c, const char *name, int level) : ctx(c), old_name(c->tag_name), old_level(c->tag_level)
+	{
+		c->tag_name  = name;
+		c->tag_level = level;
+	}
+	~Tag()
+	{
+		ctx->tag_name  = old_name;
+		ctx->tag_level = old_level;
+	}
+};
+static constexpr int MAX_PARTIAL = 2048;
+
+struct tgpu_mesh {
+	Mesh                       mesh;
+	std::vector<HostLevel>     levels;
+	std::vector<TgpuLevelDesc> descs;
+};
+
+struct LevelDev {
+	int        P      = 0;
+	size_t     ncells = 0, nface = 0;
+	PatchMeta *meta    = nullptr;
+	double *   starts  = nullptr;
+	double *   spacing = nullptr;
+	double *   Fa = nullptr, *Fb = nullptr; // face buffers
+	double *   u = nullptr, *f = nullptr, *r = nullptr; // cycle work vectors (lazily allocated)
+	bool       has_neumann = false;
+};
+
+struct GraphEntry {
+	const double *  f;
+	double *        u;
+	TgpuCycleOpts   opts;
+	cudaGraphExec_t exec;
+	int64_t         kernels;
+};
+
+struct tgpu_hier {
+	tgpu_ctx *            ctx = nullptr;
+	int                   D = 0, N = 0;
+	std::vector<LevelDev> levels;
+	double *              eig = nullptr; // [N^D]
+	std::vector<GraphEntry> graphs;
+	std::vector<tgpu_vec *> krylov_ws;
+	tgpu_vec *            host_f = nullptr, *host_u = nullptr;
+};
+
+struct tgpu_vec {
+	tgpu_hier *h     = nullptr;
+	int        level = 0;
+	double *   d     = nullptr;
+	size_t     n     = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static int launch(tgpu_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (ctx->profiling) {
+		cudaEventCreate(&e0);
+		cudaEventCreate(&e1);
+		cudaEventRecord(e0, ctx->stream);
+	}
+	kernel<<<grid, block, smem, ctx->stream>>>(args...);
+	if (ctx->profiling) {
+		cudaEventRecord(e1, ctx->stream);
+		ctx->prof_events.push_back(e0);
+		ctx->prof_events.push_back(e1);
+		ctx->prof_entries.push_back(TgpuProfileEntry{ctx->tag_name, ctx->tag_level, 0.f});
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(TGPU_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+	if (ctx->capturing) ctx->captured++;
+	else ctx->launches++;
+	return TGPU_OK;
+}
+static int grid_for(tgpu_ctx *ctx, size_t n, int block = 256, int per_sm = 8)
+{
+	size_t want = (n + block - 1) / block;
+	size_t cap  = (size_t) ctx->sm_count * per_sm;
+	return (int) std::max<size_t>(1, std::min(want, cap));
+}
+
+#define DISPATCH_DN(D_, N_, ...)                                                      \
+	do {                                                                                \
+		if ((D_) == 2 && (N_) == 4) { constexpr int DD = 2, NN = 4; __VA_ARGS__; }             \
+		else if ((D_) == 2 && (N_) == 8) { constexpr int DD = 2, NN = 8; __VA_ARGS__; }        \
+		else if ((D_) == 2 && (N_) == 16) { constexpr int DD = 2, NN = 16; __VA_ARGS__; }      \
+		else if ((D_) == 2 && (N_) == 32) { constexpr int DD = 2, NN = 32; __VA_ARGS__; }      \
+		else if ((D_) == 3 && (N_) == 4) { constexpr int DD = 3, NN = 4; __VA_ARGS__; }        \
+		else if ((D_) == 3 && (N_) == 8) { constexpr int DD = 3, NN = 8; __VA_ARGS__; }        \
+		else if ((D_) == 3 && (N_) == 16) { constexpr int DD = 3, NN = 16; __VA_ARGS__; }      \
+		else return fail(TGPU_ERR_UNSUPPORTED, "unsupported (D, n) combination");       \
+	} while (0)
+
+static bool supported_dn(int D, int N)
+{
+	return (D == 2 && (N == 4 || N == 8 || N == 16 || N == 32)) || (D == 3 && (N == 4 || N == 8 || N == 16));
+}
+
+template <int D, int N> static int set_smem_attrs()
+{
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                        (int) smooth_smem_bytes<D, N, true>()));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                        (int) smooth_smem_bytes<D, N, true>()));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                        (int) smooth_smem_bytes<D, N, false>()));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                        (int) smooth_smem_bytes<D, N, false>()));
+	CU(cudaFuncSetAttribute(apply_kernel<D, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_kernel<D, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_kernel<D, N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
+	return TGPU_OK;
+}
+
+// transform tables, evaluated exactly like DftPatchSolver.h:237-289 (M_PI / n * (...))
+static int init_constant_tables()
+{
+	for (int n : {4, 8, 16, 32}) {
+		const int           H = n / 2;
+		std::vector<double> fwd((size_t) n * H), inv((size_t) H * n);
+		for (int k = 0; k < n; k++)
+			for (int j = 0; j < H; j++) fwd[(size_t) k * H + j] = sin(M_PI / n * ((k + 1) * (j + 0.5)));
+		for (int i = 0; i < H; i++) {
+			for (int j = 0; j < n - 1; j++) inv[(size_t) i * n + j] = sin(M_PI / n * ((i + 0.5) * (j + 1)));
+			inv[(size_t) i * n + n - 1] = (i % 2 == 0) ? 0.5 : -0.5;
+		}
+		if (n == 4) {
+			CU(cudaMemcpyToSymbol(c_fwd4, fwd.data(), fwd.size() * 8));
+			CU(cudaMemcpyToSymbol(c_inv4, inv.data(), inv.size() * 8));
+		} else if (n == 8) {
+			CU(cudaMemcpyToSymbol(c_fwd8, fwd.data(), fwd.size() * 8));
+			CU(cudaMemcpyToSymbol(c_inv8, inv.data(), inv.size() * 8));
+		} else if (n == 16) {
+			CU(cudaMemcpyToSymbol(c_fwd16, fwd.data(), fwd.size() * 8));
+			CU(cudaMemcpyToSymbol(c_inv16, inv.data(), inv.size() * 8));
+		} else {
+			CU(cudaMemcpyToSymbol(c_fwd32, fwd.data(), fwd.size() * 8));
+			CU(cudaMemcpyToSymbol(c_inv32, inv.data(), inv.size() * 8));
+		}
+	}
+	return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" int tgpu_init(int device, tgpu_ctx **out)
+{
+	API_BEGIN
+	if (!out) return fail(TGPU_ERR_ARG, "tgpu_init: null output pointer");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return fail(TGPU_ERR_CUDA, std::string("tgpu_init: no CUDA device available (") + cudaGetErrorString(e)
+		                           + "); this library has no CPU fallback");
+	if (device < 0 || device >= ndev) return fail(TGPU_ERR_ARG, "tgpu_init: device index out of range");
+	CU(cudaSetDevice(device));
+	std::unique_ptr<tgpu_ctx> ctx(new tgpu_ctx());
+	ctx->device = device;
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, device));
+	ctx->sm_count = prop.multiProcessorCount;
+	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	ctx->own_stream = true;
+	CU(cudaMalloc(&ctx->d_partial, MAX_PARTIAL * sizeof(double)));
+	CU(cudaMalloc(&ctx->d_result, 8 * sizeof(double)));
+	CU(cudaMallocHost(&ctx->h_result, 8 * sizeof(double)));
+	CU(cudaEventCreate(&ctx->ev0));
+	CU(cudaEventCreate(&ctx->ev1));
+	TRY(init_constant_tables());
+	*out = ctx.release();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_finalize(tgpu_ctx *ctx)
+{
+	if (!ctx) return TGPU_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->d_partial);
+	cudaFree(ctx->d_result);
+	cudaFreeHost(ctx->h_result);
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return TGPU_OK;
+}
+extern "C" int tgpu_set_stream(tgpu_ctx *ctx, void *s)
+{
+	if (!ctx) return fail(TGPU_ERR_ARG, "null context");
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	ctx->stream     = (cudaStream_t) s;
+	ctx->own_stream = false;
+	return TGPU_OK;
+}
+extern "C" int tgpu_sync(tgpu_ctx *ctx)
+{
+	if (!ctx) return fail(TGPU_ERR_ARG, "null context");
+	CU(cudaStreamSynchronize(ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_kernel_launches(tgpu_ctx *ctx, int64_t *count)
+{
+	if (!ctx || !count) return fail(TGPU_ERR_ARG, "null argument");
+	*count = ctx->launches;
+	return TGPU_OK;
+}
+extern "C" int tgpu_timer_start(tgpu_ctx *ctx)
+{
+	if (!ctx) return fail(TGPU_ERR_ARG, "null context");
+	CU(cudaEventRecord(ctx->ev0, ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_timer_stop(tgpu_ctx *ctx, double *ms)
+{
+	if (!ctx || !ms) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaEventRecord(ctx->ev1, ctx->stream));
+	CU(cudaEventSynchronize(ctx->ev1));
+	float f = 0;
+	CU(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+	*ms = f;
+	return TGPU_OK;
+}
+
+extern "C" int tgpu_profile_begin(tgpu_ctx *ctx)
+{
+	if (!ctx) return fail(TGPU_ERR_ARG, "null context");
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+	ctx->prof_events.clear();
+	ctx->prof_entries.clear();
+	ctx->profiling = true;
+	return TGPU_OK;
+}
+extern "C" int tgpu_profile_end(tgpu_ctx *ctx, int *n, const TgpuProfileEntry **entries)
+{
+	if (!ctx || !n || !entries) return fail(TGPU_ERR_ARG, "null argument");
+	ctx->profiling = false;
+	CU(cudaStreamSynchronize(ctx->stream));
+	for (size_t i = 0; i < ctx->prof_entries.size(); i++)
+		CU(cudaEventElapsedTime(&ctx->prof_entries[i].ms, ctx->prof_events[2 * i], ctx->prof_events[2 * i + 1]));
+	*n       = (int) ctx->prof_entries.size();
+	*entries = ctx->prof_entries.data();
+	return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mesh
+// ------------------------------------------------------------------------------------------
+extern "C" int tgpu_mesh_load(const char *path, int D, tgpu_mesh **out)
+{
+	API_BEGIN
+	if (!path || !out) return fail(TGPU_ERR_ARG, "tgpu_mesh_load: null argument");
+	std::unique_ptr<tgpu_mesh> m(new tgpu_mesh());
+	try {
+		m->mesh = Mesh::load(path, D);
+	} catch (const std::exception &ex) {
+		return fail(TGPU_ERR_IO, ex.what());
+	}
+	*out = m.release();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_mesh_uniform(int D, int num_levels, tgpu_mesh **out)
+{
+	API_BEGIN
+	if (!out || num_levels < 1) return fail(TGPU_ERR_ARG, "tgpu_mesh_uniform: bad argument");
+	std::unique_ptr<tgpu_mesh> m(new tgpu_mesh());
+	m->mesh = Mesh::uniform(D, num_levels);
+	*out    = m.release();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_mesh_refine_leaves(tgpu_mesh *m)
+{
+	API_BEGIN
+	if (!m) return fail(TGPU_ERR_ARG, "null mesh");
+	m->mesh.refineLeaves();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_mesh_destroy(tgpu_mesh *m)
+{
+	delete m;
+	return TGPU_OK;
+}
+extern "C" int tgpu_mesh_info(const tgpu_mesh *m, int *D, int *num_levels, int *num_nodes)
+{
+	if (!m) return fail(TGPU_ERR_ARG, "null mesh");
+	if (D) *D = m->mesh.D;
+	if (num_levels) *num_levels = m->mesh.num_levels;
+	if (num_nodes) *num_nodes = m->mesh.numNodes();
+	return TGPU_OK;
+}
+extern "C" int tgpu_mesh_extract_levels(tgpu_mesh *m, int n, int *nlevels, const TgpuLevelDesc **levels)
+{
+	API_BEGIN
+	if (!m || !nlevels || !levels) return fail(TGPU_ERR_ARG, "null argument");
+	if (n < 2 || (n & 1)) return fail(TGPU_ERR_ARG, "n must be even and >= 2");
+	m->levels = m->mesh.extractLevels(n);
+	m->descs.clear();
+	for (const HostLevel &L : m->levels) m->descs.push_back(L.desc());
+	*nlevels = (int) m->descs.size();
+	*levels  = m->descs.data();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_mesh_level_ids(const tgpu_mesh *m, int level, const int32_t **ids, const int32_t **parent_ids,
+                                   const int32_t **refine_levels)
+{
+	if (!m || level < 0 || level >= (int) m->levels.size()) return fail(TGPU_ERR_ARG, "bad level");
+	if (ids) *ids = m->levels[level].ids.data();
+	if (parent_ids) *parent_ids = m->levels[level].parent_ids.data();
+	if (refine_levels) *refine_levels = m->levels[level].refine_levels.data();
+	return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hierarchy
+// ------------------------------------------------------------------------------------------
+template <typename T> static int dev_upload(T **dst, const T *src, size_t count)
+{
+	CU(cudaMalloc(dst, std::max<size_t>(1, count) * sizeof(T)));
+	if (count) CU(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+	return TGPU_OK;
+}
+
+extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLevelDesc *levels, tgpu_hier **out)
+{
+	API_BEGIN
+	if (!ctx || !levels || !out || nlevels < 1) return fail(TGPU_ERR_ARG, "tgpu_hierarchy_create: bad argument");
+	if (!supported_dn(D, n))
+		return fail(TGPU_ERR_UNSUPPORTED, "tgpu_hierarchy_create: (D, n) must be one of 2D n=4/8/16/32, 3D n=4/8/16");
+	CU(cudaSetDevice(ctx->device));
+	std::unique_ptr<tgpu_hier> h(new tgpu_hier());
+	h->ctx = ctx;
+	h->D   = D;
+	h->N   = n;
+	const int S = 2 * D, Q = 1 << (D - 1);
+	size_t    M = 1;
+	for (int i = 0; i < D - 1; i++) M *= n;
+	const size_t NC = M * n;
+	for (int l = 0; l < nlevels; l++) {
+		const TgpuLevelDesc &d = levels[l];
+		if (d.npatch < 1) return fail(TGPU_ERR_ARG, "level without patches");
+		LevelDev L;
+		L.P      = d.npatch;
+		L.ncells = (size_t) d.npatch * NC;
+		L.nface  = (size_t) d.npatch * S * M;
+		std::vector<PatchMeta> meta(d.npatch);
+		const int              Pc = (l + 1 < nlevels) ? levels[l + 1].npatch : 0;
+		for (int p = 0; p < d.npatch; p++) {
+			PatchMeta &pm = meta[p];
+			memset(&pm, 0, sizeof(pm));
+			const double hx = d.spacing[(size_t) p * D];
+			for (int a = 1; a < D; a++)
+				if (std::fabs(d.spacing[(size_t) p * D + a] - hx) > 1e-12 * std::fabs(hx))
+					return fail(TGPU_ERR_UNSUPPORTED, "patches must be cubic with isotropic spacing (SURVEY App. A.1)");
+			pm.h2             = hx * hx;
+			pm.inv_h2         = 1.0 / (hx * hx);
+			pm.neumann        = d.neumann_bits ? d.neumann_bits[p] : 0;
+			if (pm.neumann) L.has_neumann = true;
+			pm.parent_idx     = d.parent_idx ? d.parent_idx[p] : -1;
+			pm.orth_on_parent = d.orth_on_parent ? d.orth_on_parent[p] : -1;
+			if (l + 1 < nlevels) {
+				if (pm.parent_idx < 0 || pm.parent_idx >= Pc) return fail(TGPU_ERR_ARG, "parent_idx out of range");
+				if (pm.orth_on_parent >= (1 << D)) return fail(TGPU_ERR_ARG, "orth_on_parent out of range");
+			}
+			for (int s = 0; s < 6; s++) {
+				pm.nbr_type[s]       = NBR_NONE;
+				pm.orth_on_coarse[s] = -1;
+				for (int q = 0; q < 4; q++) pm.nbr_idx[s][q] = -1;
+			}
+			for (int s = 0; s < S; s++) {
+				const int t    = d.nbr_type[(size_t) p * S + s];
+				pm.nbr_type[s] = (int8_t) t;
+				if (t == NBR_NONE) continue;
+				if (t < 0 || t > 2) return fail(TGPU_ERR_ARG, "bad neighbour type");
+				const int cnt = (t == NBR_FINE) ? Q : 1;
+				for (int q = 0; q < cnt; q++) {
+					const int j = d.nbr_idx[((size_t) p * S + s) * Q + q];
+					if (j < 0 || j >= d.npatch) return fail(TGPU_ERR_ARG, "nbr_idx out of range");
+					pm.nbr_idx[s][q] = j;
+				}
+				if (t == NBR_COARSE) {
+					const int o = d.orth_on_coarse[(size_t) p * S + s];
+					if (o < 0 || o >= Q) return fail(TGPU_ERR_ARG, "orth_on_coarse out of range");
+					pm.orth_on_coarse[s] = (int8_t) o;
+				}
+			}
+		}
+		TRY(dev_upload(&L.meta, meta.data(), meta.size()));
+		TRY(dev_upload(&L.spacing, d.spacing, (size_t) d.npatch * D));
+		if (d.starts) TRY(dev_upload(&L.starts, d.starts, (size_t) d.npatch * D));
+		CU(cudaMalloc(&L.Fa, L.nface * sizeof(double)));
+		CU(cudaMalloc(&L.Fb, L.nface * sizeof(double)));
+		h->levels.push_back(L);
+	}
+	// eigenvalue table: (2/n)^D / sum_axes(-4 sin^2((k+1) pi / (2n)))  [the 1/h^2 factor is applied per patch]
+	{
+		std::vector<double> lam(n), eig(NC);
+		for (int k = 0; k < n; k++) lam[k] = -4.0 * pow(sin((k + 1) * M_PI / (2 * n)), 2);
+		const double scale = pow(2.0 / n, D);
+		for (size_t i = 0; i < NC; i++) {
+			double sum = 0;
+			size_t r   = i;
+			for (int a = 0; a < D; a++) {
+				sum += lam[r % n];
+				r /= n;
+			}
+			eig[i] = scale / sum;
+		}
+		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
+	}
+	DISPATCH_DN(D, n, TRY((set_smem_attrs<DD, NN>())));
+	*out = h.release();
+	return TGPU_OK;
+	API_END
+}
+
+static void free_graphs(tgpu_hier *h)
+{
+	for (GraphEntry &g : h->graphs) cudaGraphExecDestroy(g.exec);
+	h->graphs.clear();
+}
+extern "C" int tgpu_vec_destroy(tgpu_vec *v);
+extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
+{
+	if (!h) return TGPU_OK;
+	cudaSetDevice(h->ctx->device);
+	cudaStreamSynchronize(h->ctx->stream);
+	free_graphs(h);
+	for (tgpu_vec *v : h->krylov_ws) tgpu_vec_destroy(v);
+	tgpu_vec_destroy(h->host_f);
+	tgpu_vec_destroy(h->host_u);
+	for (LevelDev &L : h->levels) {
+		cudaFree(L.meta);
+		cudaFree(L.starts);
+		cudaFree(L.spacing);
+		cudaFree(L.Fa);
+		cudaFree(L.Fb);
+		cudaFree(L.u);
+		cudaFree(L.f);
+		cudaFree(L.r);
+	}
+	cudaFree(h->eig);
+	delete h;
+	return TGPU_OK;
+}
+extern "C" int tgpu_hierarchy_info(const tgpu_hier *h, int *D, int *n, int *nlevels)
+{
+	if (!h) return fail(TGPU_ERR_ARG, "null hierarchy");
+	if (D) *D = h->D;
+	if (n) *n = h->N;
+	if (nlevels) *nlevels = (int) h->levels.size();
+	return TGPU_OK;
+}
+extern "C" int tgpu_level_npatch(const tgpu_hier *h, int level, int64_t *npatch, int64_t *ncells)
+{
+	if (!h || level < 0 || level >= (int) h->levels.size()) return fail(TGPU_ERR_ARG, "bad level");
+	if (npatch) *npatch = h->levels[level].P;
+	if (ncells) *ncells = (int64_t) h->levels[level].ncells;
+	return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// vectors
+// ------------------------------------------------------------------------------------------
+extern "C" int tgpu_vec_create(tgpu_hier *h, int level, tgpu_vec **out)
+{
+	if (!h || !out || level < 0 || level >= (int) h->levels.size()) return fail(TGPU_ERR_ARG, "tgpu_vec_create: bad argument");
+	CU(cudaSetDevice(h->ctx->device));
+	std::unique_ptr<tgpu_vec> v(new tgpu_vec());
+	v->h     = h;
+	v->level = level;
+	v->n     = h->levels[level].ncells;
+	CU(cudaMalloc(&v->d, v->n * sizeof(double)));
+	CU(cudaMemsetAsync(v->d, 0, v->n * sizeof(double), h->ctx->stream));
+	*out = v.release();
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_destroy(tgpu_vec *v)
+{
+	if (!v) return TGPU_OK;
+	cudaStreamSynchronize(v->h->ctx->stream);
+	// cached graphs may reference this storage
+	free_graphs(v->h);
+	cudaFree(v->d);
+	delete v;
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_upload(tgpu_vec *v, const double *host)
+{
+	if (!v || !host) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaMemcpyAsync(v->d, host, v->n * sizeof(double), cudaMemcpyHostToDevice, v->h->ctx->stream));
+	CU(cudaStreamSynchronize(v->h->ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_download(const tgpu_vec *v, double *host)
+{
+	if (!v || !host) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaMemcpyAsync(host, v->d, v->n * sizeof(double), cudaMemcpyDeviceToHost, v->h->ctx->stream));
+	CU(cudaStreamSynchronize(v->h->ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_upload_async(tgpu_vec *v, const double *host)
+{
+	if (!v || !host) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaMemcpyAsync(v->d, host, v->n * sizeof(double), cudaMemcpyHostToDevice, v->h->ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_download_async(const tgpu_vec *v, double *host)
+{
+	if (!v || !host) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaMemcpyAsync(host, v->d, v->n * sizeof(double), cudaMemcpyDeviceToHost, v->h->ctx->stream));
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_device_ptr(const tgpu_vec *v, void **dptr, int64_t *ncells)
+{
+	if (!v) return fail(TGPU_ERR_ARG, "null vector");
+	if (dptr) *dptr = v->d;
+	if (ncells) *ncells = (int64_t) v->n;
+	return TGPU_OK;
+}
+extern "C" int tgpu_host_alloc(size_t bytes, void **p)
+{
+	if (!p) return fail(TGPU_ERR_ARG, "null argument");
+	CU(cudaMallocHost(p, bytes));
+	return TGPU_OK;
+}
+extern "C" int tgpu_host_free(void *p)
+{
+	CU(cudaFreeHost(p));
+	return TGPU_OK;
+}
+
+static int same_shape(const tgpu_vec *a, const tgpu_vec *b)
+{
+	if (!a || !b) return fail(TGPU_ERR_ARG, "null vector");
+	if (a->h != b->h || a->level != b->level || a->n != b->n)
+		return fail(TGPU_ERR_ARG, "vectors belong to different levels/hierarchies");
+	return TGPU_OK;
+}
+template <int OP>
+static int blas1(tgpu_vec *v, const tgpu_vec *a, const tgpu_vec *b, double alpha, double beta, double gamma)
+{
+	if (!v) return fail(TGPU_ERR_ARG, "null vector");
+	if (a) TRY(same_shape(v, a));
+	if (b) TRY(same_shape(v, b));
+	tgpu_ctx *ctx = v->h->ctx;
+	Tag       tg(ctx, "blas1", v->level);
+	return launch(ctx, blas1_kernel<OP>, dim3(grid_for(ctx, v->n)), dim3(256), 0, v->n, v->d, a ? a->d : (const double *) nullptr,
+	              b ? b->d : (const double *) nullptr, alpha, beta, gamma);
+}
+extern "C" int tgpu_vec_set(tgpu_vec *v, double alpha) { return blas1<B_SET>(v, nullptr, nullptr, alpha, 0, 0); }
+extern "C" int tgpu_vec_scale(tgpu_vec *v, double alpha) { return blas1<B_SCALE>(v, nullptr, nullptr, alpha, 0, 0); }
+extern "C" int tgpu_vec_shift(tgpu_vec *v, double delta) { return blas1<B_SHIFT>(v, nullptr, nullptr, delta, 0, 0); }
+extern "C" int tgpu_vec_copy(tgpu_vec *v, const tgpu_vec *b) { return b ? blas1<B_COPY>(v, b, nullptr, 0, 0, 0) : fail(TGPU_ERR_ARG, "null vector"); }
+extern "C" int tgpu_vec_add(tgpu_vec *v, const tgpu_vec *b) { return b ? blas1<B_ADD>(v, b, nullptr, 0, 0, 0) : fail(TGPU_ERR_ARG, "null vector"); }
+extern "C" int tgpu_vec_add_scaled(tgpu_vec *v, double alpha, const tgpu_vec *b)
+{
+	return b ? blas1<B_AXPY>(v, b, nullptr, alpha, 0, 0) : fail(TGPU_ERR_ARG, "null vector");
+}
+extern "C" int tgpu_vec_add_scaled2(tgpu_vec *v, double alpha, const tgpu_vec *a, double beta, const tgpu_vec *b)
+{
+	return (a && b) ? blas1<B_AXPBY2>(v, a, b, alpha, beta, 0) : fail(TGPU_ERR_ARG, "null vector");
+}
+extern "C" int tgpu_vec_scale_then_add(tgpu_vec *v, double alpha, const tgpu_vec *b)
+{
+	return b ? blas1<B_SCALE_ADD>(v, b, nullptr, alpha, 0, 0) : fail(TGPU_ERR_ARG, "null vector");
+}
+extern "C" int tgpu_vec_scale_then_add_scaled(tgpu_vec *v, double alpha, double beta, const tgpu_vec *b)
+{
+	return b ? blas1<B_SCALE_ADDS>(v, b, nullptr, alpha, beta, 0) : fail(TGPU_ERR_ARG, "null vector");
+}
+extern "C" int tgpu_vec_scale_then_add_scaled2(tgpu_vec *v, double alpha, double beta, const tgpu_vec *b, double gamma,
+                                               const tgpu_vec *c)
+{
+	return (b && c) ? blas1<B_SCALE_ADDS2>(v, b, c, alpha, beta, gamma) : fail(TGPU_ERR_ARG, "null vector");
+}
+
+template <int OP> static int reduce(const tgpu_vec *a, const tgpu_vec *b, double *result)
+{
+	if (!a || !b || !result) return fail(TGPU_ERR_ARG, "null argument");
+	TRY(same_shape(a, b));
+	tgpu_ctx *ctx = a->h->ctx;
+	const int nb  = std::min(MAX_PARTIAL, grid_for(ctx, a->n, 256, 8));
+	Tag       tg(ctx, "reduce", a->level);
+	TRY(launch(ctx, reduce_stage1<OP>, dim3(nb), dim3(256), 0, a->n, (const double *) a->d, (const double *) b->d, ctx->d_partial));
+	TRY(launch(ctx, reduce_stage2<OP>, dim3(1), dim3(256), 0, nb, (const double *) ctx->d_partial, ctx->d_result));
+	CU(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	*result = ctx->h_result[0];
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_dot(const tgpu_vec *v, const tgpu_vec *b, double *result) { return reduce<0>(v, b, result); }
+extern "C" int tgpu_vec_two_norm(const tgpu_vec *v, double *result)
+{
+	double s = 0;
+	TRY(reduce<0>(v, v, &s));
+	*result = sqrt(s);
+	return TGPU_OK;
+}
+extern "C" int tgpu_vec_inf_norm(const tgpu_vec *v, double *result) { return reduce<1>(v, v, result); }
+
+// ------------------------------------------------------------------------------------------
+// level operators (raw-pointer versions used by the cycle + vector-checked API wrappers)
+// ------------------------------------------------------------------------------------------
+static int check_level_vec(const tgpu_hier *h, int level, const tgpu_vec *v, const char *what)
+{
+	if (!h || !v) return fail(TGPU_ERR_ARG, std::string(what) + ": null argument");
+	if (level < 0 || level >= (int) h->levels.size()) return fail(TGPU_ERR_ARG, std::string(what) + ": bad level");
+	if (v->h != h || v->level != level) return fail(TGPU_ERR_ARG, std::string(what) + ": vector does not live on this level");
+	return TGPU_OK;
+}
+static int need_smoother(const tgpu_hier *h, int level)
+{
+	if (h->levels[level].has_neumann)
+		return fail(TGPU_ERR_UNSUPPORTED, "patch solver: Neumann domain sides (DCT variants) are not implemented yet");
+	return TGPU_OK;
+}
+
+static int k_extract_faces(tgpu_hier *h, int l, const double *u, double *F)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, "extract_faces", l);
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, extract_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, L.P, u, F));
+}
+// mode 0: out = A u; 1: out = f - A u; 2: coarse = R (f - A u).  F must hold the faces of u.
+static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double *f, const double *F, double *out, double *coarse)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : "residual_restrict"), l);
+	DISPATCH_DN(h->D, h->N, {
+		using G        = Geo<DD, NN>;
+		const int grid = (L.P + G::PPB - 1) / G::PPB;
+		const size_t sm = apply_smem_bytes<DD, NN>();
+		if (mode == 0) return launch(h->ctx, apply_kernel<DD, NN, 0>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
+		if (mode == 1) return launch(h->ctx, apply_kernel<DD, NN, 1>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
+		return launch(h->ctx, apply_kernel<DD, NN, 2>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
+	});
+}
+// zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout
+static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout)
+{
+	LevelDev &L = h->levels[l];
+	TRY(need_smoother(h, l));
+	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : "smooth", l);
+	DISPATCH_DN(h->D, h->N, {
+		using G        = Geo<DD, NN>;
+		const int grid = (L.P + G::PPB - 1) / G::PPB;
+		const PatchMeta *meta = L.meta;
+		const double *   eig  = h->eig;
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, true>(), meta, L.P, f, u, Fin, Fout, eig);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, true>(), meta, L.P, f, u, Fin, Fout, eig);
+		if (!zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, false>(), meta, L.P, f, u, Fin, Fout, eig);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, false>(), meta, L.P, f, u, Fin, Fout, eig);
+	});
+}
+static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, "restrict", l);
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, restrict_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, fine, coarse));
+}
+static int k_prolong_add(tgpu_hier *h, int l, const double *coarse, double *fine)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, "prolong_add", l);
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, prolong_add_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, fine));
+}
+static int k_prolong_faces(tgpu_hier *h, int l, const double *coarse, double *F)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, "prolong_faces", l);
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, prolong_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, F));
+}
+static int k_set(tgpu_hier *h, double *v, size_t n, double alpha)
+{
+	return launch(h->ctx, blas1_kernel<B_SET>, dim3(grid_for(h->ctx, n)), dim3(256), 0, n, v, (const double *) nullptr, (const double *) nullptr, alpha, 0.0, 0.0);
+}
+
+extern "C" int tgpu_apply(tgpu_hier *h, int level, const tgpu_vec *u, tgpu_vec *out)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, level, u, "tgpu_apply"));
+	TRY(check_level_vec(h, level, out, "tgpu_apply"));
+	if (u == out) return fail(TGPU_ERR_ARG, "tgpu_apply: in-place apply is not supported");
+	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	return k_apply(h, level, 0, u->d, nullptr, h->levels[level].Fa, out->d, nullptr);
+	API_END
+}
+extern "C" int tgpu_residual(tgpu_hier *h, int level, const tgpu_vec *f, const tgpu_vec *u, tgpu_vec *r)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, level, f, "tgpu_residual"));
+	TRY(check_level_vec(h, level, u, "tgpu_residual"));
+	TRY(check_level_vec(h, level, r, "tgpu_residual"));
+	if (u == r) return fail(TGPU_ERR_ARG, "tgpu_residual: r must not alias u");
+	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	return k_apply(h, level, 1, u->d, f->d, h->levels[level].Fa, r->d, nullptr);
+	API_END
+}
+extern "C" int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec *u)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, level, f, "tgpu_smooth"));
+	TRY(check_level_vec(h, level, u, "tgpu_smooth"));
+	if (f == u) return fail(TGPU_ERR_ARG, "tgpu_smooth: f must not alias u");
+	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	return k_smooth(h, level, false, false, f->d, u->d, h->levels[level].Fa, nullptr);
+	API_END
+}
+static int ensure_work(tgpu_hier *h, int l, bool need_r)
+{
+	LevelDev &L = h->levels[l];
+	if (!L.u) CU(cudaMalloc(&L.u, L.ncells * sizeof(double)));
+	if (!L.f) CU(cudaMalloc(&L.f, L.ncells * sizeof(double)));
+	if (need_r && !L.r) CU(cudaMalloc(&L.r, L.ncells * sizeof(double)));
+	return TGPU_OK;
+}
+extern "C" int tgpu_smooth_jacobi(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec *u, double omega)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, level, f, "tgpu_smooth_jacobi"));
+	TRY(check_level_vec(h, level, u, "tgpu_smooth_jacobi"));
+	TRY(ensure_work(h, level, true));
+	LevelDev &L = h->levels[level];
+	TRY(k_extract_faces(h, level, u->d, L.Fa));
+	TRY(k_apply(h, level, 1, u->d, f->d, L.Fa, L.r, nullptr));
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, jacobi_update_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, u->d, omega));
+	API_END
+}
+extern "C" int tgpu_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *fine, tgpu_vec *coarse)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, fine_level, fine, "tgpu_restrict"));
+	TRY(check_level_vec(h, fine_level + 1, coarse, "tgpu_restrict"));
+	return k_restrict(h, fine_level, fine->d, coarse->d);
+	API_END
+}
+extern "C" int tgpu_prolong_add(tgpu_hier *h, int fine_level, const tgpu_vec *coarse, tgpu_vec *fine)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, fine_level, fine, "tgpu_prolong_add"));
+	TRY(check_level_vec(h, fine_level + 1, coarse, "tgpu_prolong_add"));
+	return k_prolong_add(h, fine_level, coarse->d, fine->d);
+	API_END
+}
+extern "C" int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *f, const tgpu_vec *u, tgpu_vec *coarse_f)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, fine_level, f, "tgpu_residual_restrict"));
+	TRY(check_level_vec(h, fine_level, u, "tgpu_residual_restrict"));
+	TRY(check_level_vec(h, fine_level + 1, coarse_f, "tgpu_residual_restrict"));
+	TRY(k_extract_faces(h, fine_level, u->d, h->levels[fine_level].Fa));
+	return k_apply(h, fine_level, 2, u->d, f->d, h->levels[fine_level].Fa, nullptr, coarse_f->d);
+	API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// cycle
+// ------------------------------------------------------------------------------------------
+extern "C" int tgpu_cycle_opts_default(TgpuCycleOpts *o)
+{
+	if (!o) return fail(TGPU_ERR_ARG, "null argument");
+	o->pre_sweeps = o->post_sweeps = o->mid_sweeps = o->coarse_sweeps = 1;
+	o->cycle_type                                                   = 0;
+	o->fused                                                        = 1;
+	o->use_graph                                                    = 1;
+	return TGPU_OK;
+}
+
+// API-granular schedule, statement for statement GMG/Cycle.h:56-126 + VCycle.h:44-62 / WCycle.h:45-68
+static int generic_smooth(tgpu_hier *h, int l, const double *f, double *u)
+{
+	TRY(k_extract_faces(h, l, u, h->levels[l].Fa));
+	return k_smooth(h, l, false, false, f, u, h->levels[l].Fa, nullptr);
+}
+static int generic_prep_coarser(tgpu_hier *h, int l, const double *f, const double *u)
+{
+	LevelDev &L = h->levels[l], &C = h->levels[l + 1];
+	TRY(k_extract_faces(h, l, u, L.Fa));
+	TRY(k_apply(h, l, 1, u, f, L.Fa, L.r, nullptr)); // r = A u; r = -r + f
+	TRY(k_set(h, C.u, C.ncells, 0.0));               // new_u (zero-initialised Vec)
+	return k_restrict(h, l, L.r, C.f);               // new_f = R r
+}
+static int generic_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u)
+{
+	const int last = (int) h->levels.size() - 1;
+	if (l == last) {
+		for (int i = 0; i < o.coarse_sweeps; i++) TRY(generic_smooth(h, l, f, u));
+	} else {
+		LevelDev &C = h->levels[l + 1];
+		for (int i = 0; i < o.pre_sweeps; i++) TRY(generic_smooth(h, l, f, u));
+		TRY(generic_prep_coarser(h, l, f, u));
+		TRY(generic_visit(h, o, l + 1, C.f, C.u));
+		TRY(k_prolong_add(h, l, C.u, u));
+		if (o.cycle_type == 1) {
+			for (int i = 0; i < o.mid_sweeps; i++) TRY(generic_smooth(h, l, f, u));
+			TRY(generic_prep_coarser(h, l, f, u));
+			TRY(generic_visit(h, o, l + 1, C.f, C.u));
+			TRY(k_prolong_add(h, l, C.u, u));
+		}
+		for (int i = 0; i < o.post_sweeps; i++) TRY(generic_smooth(h, l, f, u));
+	}
+	return TGPU_OK;
+}
+// Fused schedule for V cycles with >= 1 pre and post sweep.  Per level visit:
+//   smooth(zero guess) -> u, faces | residual+restrict -> f_coarse | (coarser) |
+//   faces += P u_coarse on boundary cells only | smooth(f, faces) -> u
+// Identical arithmetic to the generic schedule except that dead stores (the interior of the
+// prolonged u, the fine residual vector, the zero fill of u) are never materialised.
+static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces)
+{
+	const int last = (int) h->levels.size() - 1;
+	LevelDev &L    = h->levels[l];
+	double *  Fcur = L.Fa, *Falt = L.Fb;
+	if (l == last) {
+		for (int i = 0; i < o.coarse_sweeps; i++) {
+			const bool emit = (i + 1 < o.coarse_sweeps);
+			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt));
+			if (i > 0 && emit) std::swap(Fcur, Falt);
+		}
+		return TGPU_OK;
+	}
+	LevelDev &C = h->levels[l + 1];
+	for (int i = 0; i < o.pre_sweeps; i++) {
+		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt));
+		if (i > 0) std::swap(Fcur, Falt);
+	}
+	TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
+	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
+	TRY(k_prolong_faces(h, l, C.u, Fcur));
+	for (int i = 0; i < o.post_sweeps; i++) {
+		const bool emit = (i + 1 < o.post_sweeps) || want_faces;
+		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt));
+		std::swap(Fcur, Falt);
+	}
+	(void) want_faces;
+	return TGPU_OK;
+}
+static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u)
+{
+	const bool fused = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+	if (fused) return fused_visit(h, o, 0, f, u, false);
+	TRY(k_set(h, u, h->levels[0].ncells, 0.0)); // Cycle::apply: u->set(0)
+	return generic_visit(h, o, 0, f, u);
+}
+static bool same_opts(const TgpuCycleOpts &a, const TgpuCycleOpts &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, double *u)
+{
+	TgpuCycleOpts o;
+	if (opts) o = *opts;
+	else tgpu_cycle_opts_default(&o);
+	if (o.pre_sweeps < 0 || o.post_sweeps < 0 || o.coarse_sweeps < 0 || o.mid_sweeps < 0 || (o.cycle_type != 0 && o.cycle_type != 1))
+		return fail(TGPU_ERR_ARG, "tgpu_vcycle: bad cycle options"); /* reference: throw 3, GMG/CycleFactory3d.cpp:131 */
+	tgpu_ctx *ctx = h->ctx;
+	for (size_t l = 0; l < h->levels.size(); l++) {
+		TRY(need_smoother(h, (int) l));
+		TRY(ensure_work(h, (int) l, true));
+	}
+	if (!o.use_graph || ctx->profiling) return run_cycle(h, o, f, u);
+	for (GraphEntry &g : h->graphs)
+		if (g.f == f && g.u == u && same_opts(g.opts, o)) {
+			CU(cudaGraphLaunch(g.exec, ctx->stream));
+			ctx->launches += g.kernels;
+			return TGPU_OK;
+		}
+	// capture
+	cudaGraph_t graph = nullptr;
+	ctx->capturing    = true;
+	ctx->captured     = 0;
+	CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	int         rc = run_cycle(h, o, f, u);
+	cudaError_t e  = cudaStreamEndCapture(ctx->stream, &graph);
+	ctx->capturing = false;
+	if (rc != TGPU_OK) {
+		if (graph) cudaGraphDestroy(graph);
+		return rc;
+	}
+	if (e != cudaSuccess) return fail(TGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+	GraphEntry g;
+	g.f = f, g.u = u, g.opts = o, g.kernels = ctx->captured;
+	CU(cudaGraphInstantiate(&g.exec, graph, 0));
+	cudaGraphDestroy(graph);
+	if (h->graphs.size() >= 8) {
+		cudaGraphExecDestroy(h->graphs.front().exec);
+		h->graphs.erase(h->graphs.begin());
+	}
+	h->graphs.push_back(g);
+	CU(cudaGraphLaunch(g.exec, ctx->stream));
+	ctx->launches += g.kernels;
+	return TGPU_OK;
+}
+extern "C" int tgpu_vcycle(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_vec *f, tgpu_vec *u)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, f, "tgpu_vcycle"));
+	TRY(check_level_vec(h, 0, u, "tgpu_vcycle"));
+	if (f == u) return fail(TGPU_ERR_ARG, "tgpu_vcycle: f must not alias u");
+	return cycle_ptr(h, opts, f->d, u->d);
+	API_END
+}
+extern "C" int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_host, double *u_host)
+{
+	API_BEGIN
+	if (!h || !f_host || !u_host) return fail(TGPU_ERR_ARG, "tgpu_vcycle_host: null argument");
+	if (!h->host_f) TRY(tgpu_vec_create(h, 0, &h->host_f));
+	if (!h->host_u) TRY(tgpu_vec_create(h, 0, &h->host_u));
+	TRY(tgpu_vec_upload_async(h->host_f, f_host));
+	TRY(cycle_ptr(h, opts, h->host_f->d, h->host_u->d));
+	TRY(tgpu_vec_download_async(h->host_u, u_host));
+	CU(cudaStreamSynchronize(h->ctx->stream));
+	return TGPU_OK;
+	API_END
+}
+
+// BiCGStab<D>::solve, statement for statement BiCGStab.h:45-106 (right-preconditioned)
+extern "C" int tgpu_bicgstab(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_vec *b, tgpu_vec *x, double tol, int max_it,
+                             int *iterations, double *rel_residual)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, b, "tgpu_bicgstab"));
+	TRY(check_level_vec(h, 0, x, "tgpu_bicgstab"));
+	while (h->krylov_ws.size() < 8) {
+		tgpu_vec *v = nullptr;
+		TRY(tgpu_vec_create(h, 0, &v));
+		h->krylov_ws.push_back(v);
+	}
+	tgpu_vec *resid = h->krylov_ws[0], *rhat = h->krylov_ws[1], *p = h->krylov_ws[2], *ap = h->krylov_ws[3];
+	tgpu_vec *as = h->krylov_ws[4], *s = h->krylov_ws[5], *ms = h->krylov_ws[6], *mp = h->krylov_ws[7];
+	const bool prec = opts != nullptr;
+	auto A = [&](const tgpu_vec *in, tgpu_vec *out) { return tgpu_apply(h, 0, in, out); };
+	auto M = [&](const tgpu_vec *in, tgpu_vec *out) { return cycle_ptr(h, opts, in->d, out->d); };
+	TRY(A(x, resid));
+	TRY(tgpu_vec_scale_then_add(resid, -1, b));
+	double r0_norm, rn, rho, tmp, tmp2;
+	TRY(tgpu_vec_two_norm(resid, &r0_norm));
+	TRY(tgpu_vec_copy(rhat, resid));
+	TRY(tgpu_vec_copy(p, resid));
+	TRY(tgpu_vec_dot(rhat, resid, &rho));
+	int its = 0;
+	TRY(tgpu_vec_two_norm(resid, &rn));
+	while (rn / r0_norm > tol && its < max_it) {
+		if (prec) {
+			TRY(M(p, mp));
+			TRY(A(mp, ap));
+		} else {
+			TRY(A(p, ap));
+		}
+		TRY(tgpu_vec_dot(rhat, ap, &tmp));
+		const double alpha = rho / tmp;
+		TRY(tgpu_vec_copy(s, resid));
+		TRY(tgpu_vec_add_scaled(s, -alpha, ap));
+		if (prec) {
+			TRY(M(s, ms));
+			TRY(A(ms, as));
+		} else {
+			TRY(A(s, as));
+		}
+		TRY(tgpu_vec_dot(as, s, &tmp));
+		TRY(tgpu_vec_dot(as, as, &tmp2));
+		const double omega = tmp / tmp2;
+		if (prec) TRY(tgpu_vec_add_scaled2(x, alpha, mp, omega, ms));
+		else TRY(tgpu_vec_add_scaled2(x, alpha, p, omega, s));
+		TRY(tgpu_vec_add_scaled2(resid, -alpha, ap, -omega, as));
+		double rho_new;
+		TRY(tgpu_vec_dot(resid, rhat, &rho_new));
+		const double beta = rho_new * alpha / (rho * omega);
+		TRY(tgpu_vec_add_scaled(p, -omega, ap));
+		TRY(tgpu_vec_scale_then_add(p, beta, resid));
+		its++;
+		rho = rho_new;
+		TRY(tgpu_vec_two_norm(resid, &rn));
+	}
+	if (iterations) *iterations = its;
+	if (rel_residual) *rel_residual = rn / r0_norm;
+	return TGPU_OK;
+	API_END
+}
+
+extern "C" int tgpu_init_trig_rhs(tgpu_hier *h, tgpu_vec *f, tgpu_vec *exact)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, f, "tgpu_init_trig_rhs"));
+	if (exact) TRY(check_level_vec(h, 0, exact, "tgpu_init_trig_rhs"));
+	LevelDev &L = h->levels[0];
+	if (!L.starts) return fail(TGPU_ERR_ARG, "tgpu_init_trig_rhs: hierarchy was created without patch starts");
+	DISPATCH_DN(h->D, h->N, return launch(h->ctx, init_trig_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, exact ? exact->d : (double *) nullptr));
+	API_END
+}
