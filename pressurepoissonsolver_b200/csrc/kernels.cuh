@@ -41,9 +41,8 @@ struct __align__(16) PatchMeta {
 };
 
 constexpr int TGPU_THREADS = 256;
-#ifndef SMOOTH_MIN_BLOCKS
-#define SMOOTH_MIN_BLOCKS 2
-#endif
+// resident smoother CTAs per SM the register budget is tuned for (N = 32 pencils need > 128 registers)
+template <int N> constexpr int smooth_min_blocks() { return N >= 32 ? 1 : 2; }
 
 template <int D, int N> struct Geo {
 	static constexpr int M   = (D == 2) ? N : N * N;     // pencils per patch = face size
@@ -83,8 +82,35 @@ template <int N> __device__ __forceinline__ double cinv(int i)
 	return c_inv32[i];
 }
 
+// Every entry of the DST-II / DST-III matrices is +-sin(i pi / 2N), i = 1..N: N distinct magnitudes.
+// For N <= 16 they live in registers for the whole kernel (loaded once from c_mag*), so the
+// transforms are pure register DFMA/DADD streams with no constant fetches; the sign is folded into
+// the DFMA operand modifier.  N = 32 (66 registers of magnitudes) keeps the constant-bank tables.
+__constant__ double c_mag4[5], c_mag8[9], c_mag16[17], c_mag32[33];
+template <int N> struct Mags {
+	static constexpr bool IN_REGS = (N <= 16);
+	double                m[IN_REGS ? N + 1 : 1];
+	__device__ __forceinline__ void load()
+	{
+		if (IN_REGS) {
+#pragma unroll
+			for (int i = 0; i <= N; i++) m[i] = (N == 4) ? c_mag4[i] : (N == 8) ? c_mag8[i] : c_mag16[i];
+		}
+	}
+	// sin(pi a / 2N) for a compile-time (after unrolling) integer a
+	__device__ __forceinline__ double sinq(int a) const
+	{
+		a %= 4 * N;
+		const bool neg = a >= 2 * N;
+		if (neg) a -= 2 * N;
+		if (a > N) a = 2 * N - a;
+		return neg ? -m[a] : m[a];
+	}
+};
+
 // DST-II of a register pencil using S[k][N-1-j] = (-1)^k S[k][j]: N adds + N*N/2 FMAs.
-template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N])
+//   S[k][j] = sin(pi (k+1)(j+1/2) / N) = sinq((k+1)(2j+1))        (DftPatchSolver.h:262-268)
+template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N], const Mags<N> &mg)
 {
 	constexpr int H = N / 2;
 	double        e[H], o[H];
@@ -97,12 +123,16 @@ template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N])
 	for (int k = 0; k < N; k++) {
 		double acc = 0.0;
 #pragma unroll
-		for (int j = 0; j < H; j++) acc = fma(cfwd<N>(k * H + j), (k & 1) ? o[j] : e[j], acc);
+		for (int j = 0; j < H; j++) {
+			const double c = Mags<N>::IN_REGS ? mg.sinq((k + 1) * (2 * j + 1)) : cfwd<N>(k * H + j);
+			acc            = fma(c, (k & 1) ? o[j] : e[j], acc);
+		}
 		v[k] = acc;
 	}
 }
 // DST-III using T[N-1-i][j] = (-1)^j T[i][j]: y_i = E_i + O_i, y_{N-1-i} = E_i - O_i.
-template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N])
+//   T[i][j] = sin(pi (i+1/2)(j+1) / N) = sinq((2i+1)(j+1)), T[i][N-1] = 0.5 (-1)^i  (DftPatchSolver.h:269-281)
+template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N], const Mags<N> &mg)
 {
 	constexpr int H = N / 2;
 	double        E[H], O[H];
@@ -111,8 +141,11 @@ template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N])
 		double ea = 0.0, oa = 0.0;
 #pragma unroll
 		for (int j = 0; j < N; j += 2) {
-			ea = fma(cinv<N>(i * N + j), v[j], ea);
-			oa = fma(cinv<N>(i * N + j + 1), v[j + 1], oa);
+			const double ce = Mags<N>::IN_REGS ? mg.sinq((2 * i + 1) * (j + 1)) : cinv<N>(i * N + j);
+			const double co = Mags<N>::IN_REGS ? ((j + 1 == N - 1) ? ((i & 1) ? -0.5 : 0.5) : mg.sinq((2 * i + 1) * (j + 2)))
+			                                   : cinv<N>(i * N + j + 1);
+			ea = fma(ce, v[j], ea);
+			oa = fma(co, v[j + 1], oa);
 		}
 		E[i] = ea;
 		O[i] = oa;
@@ -123,6 +156,16 @@ template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N])
 		v[N - 1 - i] = E[i] - O[i];
 	}
 }
+
+// cp.async (LDGSTS) 8-byte copy global -> shared; !valid zero-fills (src-size 0)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
+{
+	const unsigned s  = (unsigned) __cvta_generic_to_shared(smem_dst);
+	const int      sz = valid ? 8 : 0;
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // interface value gamma for entry m of side s of patch p, from the face buffer F.
@@ -202,165 +245,191 @@ template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, 
 // per patch, all in shared memory / registers.  256 threads handle PPB = 256 / N^(D-1) patches.
 //   ZERO_GUESS: gamma == 0 (first sweep of a cycle, GMG/Cycle.h:118 u->set(0)), F_in is not read.
 //   EMIT:       also write the new boundary-cell slices to F_out.
-// eig[k] = (2/N)^D / sum_axes(-4 sin^2((k_a+1) pi / 2N))   (FftwPatchSolver.h:152-170, DftPatchSolver.h:214)
+// eig[k_x * M + (k_y + N k_z)] = (2/N)^D / sum_axes(-4 sin^2((k_a+1) pi / 2N))   (FftwPatchSolver.h:152-170,
+// DftPatchSolver.h:214); transposed so that the x-pencil threads of a warp read it coalesced
 // ---------------------------------------------------------------------------------------------
 template <int D, int N, bool ZERO_GUESS, bool EMIT>
-__global__ void __launch_bounds__(TGPU_THREADS, SMOOTH_MIN_BLOCKS)
+__global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
 smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ f, double *__restrict__ u,
               const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig)
 {
+	// Persistent CTAs: each loops over groups of PPB patches (group g = blockIdx.x + k gridDim.x).
+	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
+	// cp.async while the current group is being solved (double buffering).
 	using G = Geo<D, N>;
 	extern __shared__ double smem[];
-	double *Sall = smem;                  // [PPB][SP]
-	double *Gall = smem + G::PPB * G::SP; // [PPB][S][M]   (unused when ZERO_GUESS)
+	double *Sbuf0 = smem;                      // [PPB][SP]
+	double *Sbuf1 = smem + G::PPB * G::SP;     // [PPB][SP]
+	double *Gall  = smem + 2 * G::PPB * G::SP; // [PPB][S][M]   (unused when ZERO_GUESS)
 
-	const int  t     = threadIdx.x;
-	const int  pb    = blockIdx.x * G::PPB;
-	const int  pp    = t / G::M;
-	const int  m     = t % G::M;
-	const int  p     = pb + pp;
-	const bool valid = p < P;
+	const int t    = threadIdx.x;
+	const int pp   = t / G::M;
+	const int m    = t % G::M;
+	const int nblk = (P + G::PPB - 1) / G::PPB;
 
-	// ---- load f (coalesced over the PPB contiguous patches of this block) ----
+	Mags<N> mg;
+	mg.load();
+
+	auto prefetch = [&](int g, double *Sdst) {
+		const int pb = g * G::PPB;
 #pragma unroll
-	for (int k = 0; k < N; k++) {
-		const int    e  = t + TGPU_THREADS * k;
-		const int    lp = e / G::NC, c = e % G::NC;
-		const double val = (pb + lp < P) ? __ldg(f + (size_t) (pb + lp) * G::NC + c) : 0.0;
-		Sall[lp * G::SP + (c / N) * G::ROW + (c % N)] = val;
-	}
-	double *S = Sall + pp * G::SP;
-	double  cfac = 0.0, h2 = 0.0;
-	int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
-	if (valid) {
-		const PatchMeta &pm = meta[p];
-		cfac                = 2.0 * pm.inv_h2;
-		h2                  = pm.h2;
-		if (!ZERO_GUESS) {
-			double *Gp = Gall + pp * G::S * G::M;
+		for (int k = 0; k < N; k++) {
+			const int  e  = t + TGPU_THREADS * k;
+			const int  lp = e / G::NC, c = e % G::NC;
+			const bool ok = pb + lp < P;
+			cp_async8(Sdst + lp * G::SP + (c / N) * G::ROW + (c % N), ok ? f + (size_t) (pb + lp) * G::NC + c : f, ok);
+		}
+	};
+
+	int g = blockIdx.x;
+	if (g < nblk) prefetch(g, Sbuf0);
+	cp_async_commit();
+
+	for (int it = 0; g < nblk; g += gridDim.x, it++) {
+		double *   Sall  = (it & 1) ? Sbuf1 : Sbuf0;
+		const int  p     = g * G::PPB + pp;
+		const bool valid = p < P;
+		// the other buffer was last read in the previous iteration, before its closing barrier
+		if (g + (int) gridDim.x < nblk) prefetch(g + gridDim.x, (it & 1) ? Sbuf0 : Sbuf1);
+		cp_async_commit();
+
+		double *S = Sall + pp * G::SP;
+		double  cfac = 0.0, h2 = 0.0;
+		int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
+		if (valid) {
+			const PatchMeta &pm = meta[p];
+			cfac                = 2.0 * pm.inv_h2;
+			h2                  = pm.h2;
+			if (!ZERO_GUESS) {
+				double *Gp = Gall + pp * G::S * G::M;
 #pragma unroll
-			for (int s = 0; s < G::S; s++) {
-				ntype[s] = pm.nbr_type[s];
-				if (ntype[s] != NBR_NONE) Gp[s * G::M + m] = iface_gamma<D, N>(pm, p, s, m, Fin);
+				for (int s = 0; s < G::S; s++) {
+					ntype[s] = pm.nbr_type[s];
+					if (ntype[s] != NBR_NONE) Gp[s * G::M + m] = iface_gamma<D, N>(pm, p, s, m, Fin);
+				}
 			}
 		}
-	}
-	__syncthreads();
-
-	if (!ZERO_GUESS) {
-		const double *Gp = Gall + pp * G::S * G::M;
-		// x faces: face entry m <-> row m (2D: y; 3D: y + N z)
-		if (ntype[0] != NBR_NONE) S[m * G::ROW] -= cfac * Gp[0 * G::M + m];
-		if (ntype[1] != NBR_NONE) S[m * G::ROW + N - 1] -= cfac * Gp[1 * G::M + m];
+		cp_async_wait<1>(); // this group's f has landed (only the newest prefetch may still be in flight)
 		__syncthreads();
-		if (D == 3) {
-			// y faces: entry m = x + N z
-			const int x = m % N, z = m / N;
-			if (ntype[2] != NBR_NONE) S[(z * N) * G::ROW + x] -= cfac * Gp[2 * G::M + m];
-			if (ntype[3] != NBR_NONE) S[(z * N + N - 1) * G::ROW + x] -= cfac * Gp[3 * G::M + m];
-			__syncthreads();
-		}
-	}
 
-	double v[N];
-	// ---- forward along the last axis (pencil = plane index m) ----
-	{
-		const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
-		const int step = (D == 2) ? G::ROW : N * G::ROW;
-#pragma unroll
-		for (int k = 0; k < N; k++) v[k] = S[base + k * step];
 		if (!ZERO_GUESS) {
 			const double *Gp = Gall + pp * G::S * G::M;
-			if (ntype[G::S - 2] != NBR_NONE) v[0] -= cfac * Gp[(G::S - 2) * G::M + m];
-			if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= cfac * Gp[(G::S - 1) * G::M + m];
+			// x faces: face entry m <-> row m (2D: y; 3D: y + N z)
+			if (ntype[0] != NBR_NONE) S[m * G::ROW] -= cfac * Gp[0 * G::M + m];
+			if (ntype[1] != NBR_NONE) S[m * G::ROW + N - 1] -= cfac * Gp[1 * G::M + m];
+			__syncthreads();
+			if (D == 3) {
+				// y faces: entry m = x + N z
+				const int x = m % N, z = m / N;
+				if (ntype[2] != NBR_NONE) S[(z * N) * G::ROW + x] -= cfac * Gp[2 * G::M + m];
+				if (ntype[3] != NBR_NONE) S[(z * N + N - 1) * G::ROW + x] -= cfac * Gp[3 * G::M + m];
+				__syncthreads();
+			}
 		}
-		dst2_forward<N>(v);
+
+		double v[N];
+		// ---- forward along the last axis (pencil = plane index m) ----
+		{
+			const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
+			const int step = (D == 2) ? G::ROW : N * G::ROW;
 #pragma unroll
-		for (int k = 0; k < N; k++) S[base + k * step] = v[k];
-	}
-	__syncthreads();
-	if (D == 3) { // forward along y: pencil (x, z)
-		const int base = (m / N) * N * G::ROW + (m % N);
+			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+			if (!ZERO_GUESS) {
+				const double *Gp = Gall + pp * G::S * G::M;
+				if (ntype[G::S - 2] != NBR_NONE) v[0] -= cfac * Gp[(G::S - 2) * G::M + m];
+				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= cfac * Gp[(G::S - 1) * G::M + m];
+			}
+			dst2_forward<N>(v, mg);
 #pragma unroll
-		for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-		dst2_forward<N>(v);
-#pragma unroll
-		for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			for (int k = 0; k < N; k++) S[base + k * step] = v[k];
+		}
 		__syncthreads();
-	}
-	// ---- x: forward, divide by the eigenvalues, inverse (pencil = row m) ----
-	{
+		if (D == 3) { // forward along y: pencil (x, z)
+			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
-		for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
-		dst2_forward<N>(v);
-		const double *er = eig + (size_t) m * N;
+			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
+			dst2_forward<N>(v, mg);
 #pragma unroll
-		for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k);
-		dst3_inverse<N>(v);
+			for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			__syncthreads();
+		}
+		// ---- x: forward, divide by the eigenvalues, inverse (pencil = row m) ----
+		{
 #pragma unroll
-		for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
-	}
-	__syncthreads();
-	if (D == 3) { // inverse along y
-		const int base = (m / N) * N * G::ROW + (m % N);
+			for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
+			dst2_forward<N>(v, mg);
+			// eig is stored transposed, [k_x][row m], so that a warp reads consecutive doubles
+			const double *er = eig + m;
 #pragma unroll
-		for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-		dst3_inverse<N>(v);
+			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
+			dst3_inverse<N>(v, mg);
 #pragma unroll
-		for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
+		}
 		__syncthreads();
-	}
-	// ---- inverse along the last axis, write u (and the new faces) ----
-	{
-		const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
-		const int step = (D == 2) ? G::ROW : N * G::ROW;
+		if (D == 3) { // inverse along y
+			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
-		for (int k = 0; k < N; k++) v[k] = S[base + k * step];
-		dst3_inverse<N>(v);
-		if (valid) {
-			double *up = u + (size_t) p * G::NC + m;
+			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
+			dst3_inverse<N>(v, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) up[k * G::M] = v[k];
-			if (EMIT) {
-				double *Fp = Fout + (size_t) p * G::S * G::M;
-				Fp[(G::S - 2) * G::M + m] = v[0];
-				Fp[(G::S - 1) * G::M + m] = v[N - 1];
-				if (D == 2) {
-					if (m == 0) {
+			for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			__syncthreads();
+		}
+		// ---- inverse along the last axis, write u (and the new faces) ----
+		{
+			const int base = (D == 2) ? m : (m / N) * G::ROW + (m % N);
+			const int step = (D == 2) ? G::ROW : N * G::ROW;
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[0 * G::M + k] = v[k];
-					}
-					if (m == N - 1) {
+			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+			__syncthreads(); // all reads of this buffer (and of Gall) are done: the next iteration may refill it
+			dst3_inverse<N>(v, mg);
+			if (valid) {
+				double *up = u + (size_t) p * G::NC + m;
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[1 * G::M + k] = v[k];
-					}
-				} else {
-					const int x = m % N, y = m / N;
-					if (x == 0) {
+				for (int k = 0; k < N; k++) up[k * G::M] = v[k];
+				if (EMIT) {
+					double *Fp = Fout + (size_t) p * G::S * G::M;
+					Fp[(G::S - 2) * G::M + m] = v[0];
+					Fp[(G::S - 1) * G::M + m] = v[N - 1];
+					if (D == 2) {
+						if (m == 0) {
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[0 * G::M + k * N + y] = v[k];
-					}
-					if (x == N - 1) {
+							for (int k = 0; k < N; k++) Fp[0 * G::M + k] = v[k];
+						}
+						if (m == N - 1) {
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[1 * G::M + k * N + y] = v[k];
-					}
-					if (y == 0) {
+							for (int k = 0; k < N; k++) Fp[1 * G::M + k] = v[k];
+						}
+					} else {
+						const int x = m % N, y = m / N;
+						if (x == 0) {
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[2 * G::M + k * N + x] = v[k];
-					}
-					if (y == N - 1) {
+							for (int k = 0; k < N; k++) Fp[0 * G::M + k * N + y] = v[k];
+						}
+						if (x == N - 1) {
 #pragma unroll
-						for (int k = 0; k < N; k++) Fp[3 * G::M + k * N + x] = v[k];
+							for (int k = 0; k < N; k++) Fp[1 * G::M + k * N + y] = v[k];
+						}
+						if (y == 0) {
+#pragma unroll
+							for (int k = 0; k < N; k++) Fp[2 * G::M + k * N + x] = v[k];
+						}
+						if (y == N - 1) {
+#pragma unroll
+							for (int k = 0; k < N; k++) Fp[3 * G::M + k * N + x] = v[k];
+						}
 					}
 				}
 			}
 		}
 	}
+	cp_async_wait<0>();
 }
 template <int D, int N, bool ZERO_GUESS> constexpr size_t smooth_smem_bytes()
 {
 	using G = Geo<D, N>;
-	return sizeof(double) * (size_t) (G::PPB * G::SP + (ZERO_GUESS ? 0 : G::PPB * G::S * G::M));
+	return sizeof(double) * (size_t) (2 * G::PPB * G::SP + (ZERO_GUESS ? 0 : G::PPB * G::S * G::M));
 }
 
 // ---------------------------------------------------------------------------------------------

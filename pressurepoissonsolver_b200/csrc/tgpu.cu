@@ -211,6 +211,13 @@ static int init_constant_tables()
 			for (int j = 0; j < n - 1; j++) inv[(size_t) i * n + j] = sin(M_PI / n * ((i + 0.5) * (j + 1)));
 			inv[(size_t) i * n + n - 1] = (i % 2 == 0) ? 0.5 : -0.5;
 		}
+		std::vector<double> mag(n + 1);
+		for (int i = 0; i <= n; i++) mag[i] = sin(M_PI / (2.0 * n) * i);
+		mag[n] = 1.0;
+		if (n == 4) CU(cudaMemcpyToSymbol(c_mag4, mag.data(), mag.size() * 8));
+		else if (n == 8) CU(cudaMemcpyToSymbol(c_mag8, mag.data(), mag.size() * 8));
+		else if (n == 16) CU(cudaMemcpyToSymbol(c_mag16, mag.data(), mag.size() * 8));
+		else CU(cudaMemcpyToSymbol(c_mag32, mag.data(), mag.size() * 8));
 		if (n == 4) {
 			CU(cudaMemcpyToSymbol(c_fwd4, fwd.data(), fwd.size() * 8));
 			CU(cudaMemcpyToSymbol(c_inv4, inv.data(), inv.size() * 8));
@@ -497,7 +504,8 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 				sum += lam[r % n];
 				r /= n;
 			}
-			eig[i] = scale / sum;
+			// transposed layout [k_x][remaining axes]: the x-pencil threads read it coalesced
+			eig[(i % n) * M + i / n] = scale / sum;
 		}
 		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
 	}
@@ -737,7 +745,8 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : "smooth", l);
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
-		const int grid = (L.P + G::PPB - 1) / G::PPB;
+		const int nblk = (L.P + G::PPB - 1) / G::PPB;
+		const int grid = std::min(nblk, h->ctx->sm_count * smooth_min_blocks<NN>());
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = h->eig;
 		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, true>(), meta, L.P, f, u, Fin, Fout, eig);
