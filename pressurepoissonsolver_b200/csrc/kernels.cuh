@@ -42,7 +42,10 @@ struct __align__(16) PatchMeta {
 
 constexpr int TGPU_THREADS = 256;
 // resident smoother CTAs per SM the register budget is tuned for (N = 32 pencils need > 128 registers)
-template <int N> constexpr int smooth_min_blocks() { return N >= 32 ? 1 : 2; }
+#ifndef SMOOTH_BLOCKS_16
+#define SMOOTH_BLOCKS_16 3
+#endif
+template <int N> constexpr int smooth_min_blocks() { return N >= 32 ? 1 : SMOOTH_BLOCKS_16; }
 
 template <int D, int N> struct Geo {
 	static constexpr int M   = (D == 2) ? N : N * N;     // pencils per patch = face size
@@ -108,52 +111,113 @@ template <int N> struct Mags {
 	}
 };
 
-// DST-II of a register pencil using S[k][N-1-j] = (-1)^k S[k][j]: N adds + N*N/2 FMAs.
-//   S[k][j] = sin(pi (k+1)(j+1/2) / N) = sinq((k+1)(2j+1))        (DftPatchSolver.h:262-268)
-template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N], const Mags<N> &mg)
-{
-	constexpr int H = N / 2;
-	double        e[H], o[H];
-#pragma unroll
-	for (int j = 0; j < H; j++) {
-		e[j] = v[j] + v[N - 1 - j];
-		o[j] = v[j] - v[N - 1 - j];
-	}
-#pragma unroll
-	for (int k = 0; k < N; k++) {
-		double acc = 0.0;
+// DST-II of a register pencil.  S[k][j] = sin(pi (k+1)(2j+1) / 2n)  (DftPatchSolver.h:262-268).
+// Symmetry S[k][n-1-j] = (-1)^k S[k][j] splits the transform into
+//   even k = 2m:   sum_j sin(pi (2m+1)(2j+1) / 2n) e_j        (dense n/2 x n/2, a DST-IV)
+//   odd  k = 2m+1: sum_j sin(pi (m+1)(2j+1) / n)   o_j        (= DST-II of size n/2 on o -> recursion)
+// with e_j = x_j + x_{n-1-j}, o_j = x_j - x_{n-1-j}.  Cost for n = 16: 116 fp64 ops instead of 256.
+// NT is the top-level pencil length (owner of the magnitude table), n the current size.
+template <int NT, int n> struct Dst2 {
+	static constexpr int SC = NT / n; // sin(pi a / 2n) = sinq_NT(SC a)
+	__device__ static __forceinline__ void run(double (&v)[n], const Mags<NT> &mg)
+	{
+		constexpr int H = n / 2;
+		double        e[H], o[H];
 #pragma unroll
 		for (int j = 0; j < H; j++) {
-			const double c = Mags<N>::IN_REGS ? mg.sinq((k + 1) * (2 * j + 1)) : cfwd<N>(k * H + j);
-			acc            = fma(c, (k & 1) ? o[j] : e[j], acc);
+			e[j] = v[j] + v[n - 1 - j];
+			o[j] = v[j] - v[n - 1 - j];
 		}
-		v[k] = acc;
+#pragma unroll
+		for (int mm = 0; mm < H; mm++) {
+			double acc = 0.0;
+#pragma unroll
+			for (int j = 0; j < H; j++) acc = fma(mg.sinq(SC * (2 * mm + 1) * (2 * j + 1)), e[j], acc);
+			v[2 * mm] = acc;
+		}
+		Dst2<NT, H>::run(o, mg);
+#pragma unroll
+		for (int mm = 0; mm < H; mm++) v[2 * mm + 1] = o[mm];
+	}
+};
+template <int NT> struct Dst2<NT, 1> {
+	__device__ static __forceinline__ void run(double (&v)[1], const Mags<NT> &) { /* sin(pi/2) x_0 */ }
+};
+// DST-III of a register pencil.  T[i][j] = sin(pi (2i+1)(j+1) / 2n), T[i][n-1] = 0.5 (-1)^i
+// (DftPatchSolver.h:269-281).  T[n-1-i][j] = (-1)^j T[i][j]  =>  y_i = E_i + O_i, y_{n-1-i} = E_i - O_i with
+//   E_i = sum_{j even} T[i][j] x_j                  (dense n/2 x n/2)
+//   O_i = sum_{l} sin(pi (2i+1)(l+1) / n) x_{2l+1}  (= DST-III of size n/2 on the odd inputs -> recursion)
+template <int NT, int n> struct Dst3 {
+	static constexpr int SC = NT / n;
+	__device__ static __forceinline__ void run(double (&v)[n], const Mags<NT> &mg)
+	{
+		constexpr int H = n / 2;
+		double        E[H], O[H];
+#pragma unroll
+		for (int l = 0; l < H; l++) O[l] = v[2 * l + 1];
+#pragma unroll
+		for (int i = 0; i < H; i++) {
+			double acc = 0.0;
+#pragma unroll
+			for (int l = 0; l < H; l++) acc = fma(mg.sinq(SC * (2 * i + 1) * (2 * l + 1)), v[2 * l], acc);
+			E[i] = acc;
+		}
+		Dst3<NT, H>::run(O, mg);
+#pragma unroll
+		for (int i = 0; i < H; i++) {
+			v[i]         = E[i] + O[i];
+			v[n - 1 - i] = E[i] - O[i];
+		}
+	}
+};
+template <int NT> struct Dst3<NT, 1> {
+	__device__ static __forceinline__ void run(double (&v)[1], const Mags<NT> &) { v[0] *= 0.5; }
+};
+
+template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N], const Mags<N> &mg)
+{
+	if (Mags<N>::IN_REGS) {
+		Dst2<N, N>::run(v, mg);
+	} else { // one symmetric split with constant-bank coefficients
+		constexpr int H = N / 2;
+		double        e[H], o[H];
+#pragma unroll
+		for (int j = 0; j < H; j++) {
+			e[j] = v[j] + v[N - 1 - j];
+			o[j] = v[j] - v[N - 1 - j];
+		}
+#pragma unroll
+		for (int k = 0; k < N; k++) {
+			double acc = 0.0;
+#pragma unroll
+			for (int j = 0; j < H; j++) acc = fma(cfwd<N>(k * H + j), (k & 1) ? o[j] : e[j], acc);
+			v[k] = acc;
+		}
 	}
 }
-// DST-III using T[N-1-i][j] = (-1)^j T[i][j]: y_i = E_i + O_i, y_{N-1-i} = E_i - O_i.
-//   T[i][j] = sin(pi (i+1/2)(j+1) / N) = sinq((2i+1)(j+1)), T[i][N-1] = 0.5 (-1)^i  (DftPatchSolver.h:269-281)
 template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N], const Mags<N> &mg)
 {
-	constexpr int H = N / 2;
-	double        E[H], O[H];
+	if (Mags<N>::IN_REGS) {
+		Dst3<N, N>::run(v, mg);
+	} else {
+		constexpr int H = N / 2;
+		double        E[H], O[H];
 #pragma unroll
-	for (int i = 0; i < H; i++) {
-		double ea = 0.0, oa = 0.0;
+		for (int i = 0; i < H; i++) {
+			double ea = 0.0, oa = 0.0;
 #pragma unroll
-		for (int j = 0; j < N; j += 2) {
-			const double ce = Mags<N>::IN_REGS ? mg.sinq((2 * i + 1) * (j + 1)) : cinv<N>(i * N + j);
-			const double co = Mags<N>::IN_REGS ? ((j + 1 == N - 1) ? ((i & 1) ? -0.5 : 0.5) : mg.sinq((2 * i + 1) * (j + 2)))
-			                                   : cinv<N>(i * N + j + 1);
-			ea = fma(ce, v[j], ea);
-			oa = fma(co, v[j + 1], oa);
+			for (int j = 0; j < N; j += 2) {
+				ea = fma(cinv<N>(i * N + j), v[j], ea);
+				oa = fma(cinv<N>(i * N + j + 1), v[j + 1], oa);
+			}
+			E[i] = ea;
+			O[i] = oa;
 		}
-		E[i] = ea;
-		O[i] = oa;
-	}
 #pragma unroll
-	for (int i = 0; i < H; i++) {
-		v[i]         = E[i] + O[i];
-		v[N - 1 - i] = E[i] - O[i];
+		for (int i = 0; i < H; i++) {
+			v[i]         = E[i] + O[i];
+			v[N - 1 - i] = E[i] - O[i];
+		}
 	}
 }
 
@@ -260,7 +324,6 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 	extern __shared__ double smem[];
 	double *Sbuf0 = smem;                      // [PPB][SP]
 	double *Sbuf1 = smem + G::PPB * G::SP;     // [PPB][SP]
-	double *Gall  = smem + 2 * G::PPB * G::SP; // [PPB][S][M]   (unused when ZERO_GUESS)
 
 	const int t    = threadIdx.x;
 	const int pp   = t / G::M;
@@ -296,16 +359,17 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 		double *S = Sall + pp * G::SP;
 		double  cfac = 0.0, h2 = 0.0;
 		int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
+		double  gam[6]   = {0, 0, 0, 0, 0, 0}; // (2/h^2) gamma of entry m on each side
 		if (valid) {
 			const PatchMeta &pm = meta[p];
 			cfac                = 2.0 * pm.inv_h2;
 			h2                  = pm.h2;
 			if (!ZERO_GUESS) {
-				double *Gp = Gall + pp * G::S * G::M;
+				// entry m of every side is both produced and consumed by thread m: no staging needed
 #pragma unroll
 				for (int s = 0; s < G::S; s++) {
 					ntype[s] = pm.nbr_type[s];
-					if (ntype[s] != NBR_NONE) Gp[s * G::M + m] = iface_gamma<D, N>(pm, p, s, m, Fin);
+					if (ntype[s] != NBR_NONE) gam[s] = cfac * iface_gamma<D, N>(pm, p, s, m, Fin);
 				}
 			}
 		}
@@ -313,16 +377,15 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 		__syncthreads();
 
 		if (!ZERO_GUESS) {
-			const double *Gp = Gall + pp * G::S * G::M;
 			// x faces: face entry m <-> row m (2D: y; 3D: y + N z)
-			if (ntype[0] != NBR_NONE) S[m * G::ROW] -= cfac * Gp[0 * G::M + m];
-			if (ntype[1] != NBR_NONE) S[m * G::ROW + N - 1] -= cfac * Gp[1 * G::M + m];
+			if (ntype[0] != NBR_NONE) S[m * G::ROW] -= gam[0];
+			if (ntype[1] != NBR_NONE) S[m * G::ROW + N - 1] -= gam[1];
 			__syncthreads();
 			if (D == 3) {
 				// y faces: entry m = x + N z
 				const int x = m % N, z = m / N;
-				if (ntype[2] != NBR_NONE) S[(z * N) * G::ROW + x] -= cfac * Gp[2 * G::M + m];
-				if (ntype[3] != NBR_NONE) S[(z * N + N - 1) * G::ROW + x] -= cfac * Gp[3 * G::M + m];
+				if (ntype[2] != NBR_NONE) S[(z * N) * G::ROW + x] -= gam[2];
+				if (ntype[3] != NBR_NONE) S[(z * N + N - 1) * G::ROW + x] -= gam[3];
 				__syncthreads();
 			}
 		}
@@ -335,9 +398,8 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
 			if (!ZERO_GUESS) {
-				const double *Gp = Gall + pp * G::S * G::M;
-				if (ntype[G::S - 2] != NBR_NONE) v[0] -= cfac * Gp[(G::S - 2) * G::M + m];
-				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= cfac * Gp[(G::S - 1) * G::M + m];
+				if (ntype[G::S - 2] != NBR_NONE) v[0] -= gam[G::S - 2];
+				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= gam[G::S - 1];
 			}
 			dst2_forward<N>(v, mg);
 #pragma unroll
@@ -382,7 +444,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 			const int step = (D == 2) ? G::ROW : N * G::ROW;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
-			__syncthreads(); // all reads of this buffer (and of Gall) are done: the next iteration may refill it
+			__syncthreads(); // all reads of this buffer are done: the next iteration may refill it
 			dst3_inverse<N>(v, mg);
 			if (valid) {
 				double *up = u + (size_t) p * G::NC + m;
@@ -429,7 +491,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 template <int D, int N, bool ZERO_GUESS> constexpr size_t smooth_smem_bytes()
 {
 	using G = Geo<D, N>;
-	return sizeof(double) * (size_t) (2 * G::PPB * G::SP + (ZERO_GUESS ? 0 : G::PPB * G::S * G::M));
+	return sizeof(double) * (size_t) (2 * G::PPB * G::SP);
 }
 
 // ---------------------------------------------------------------------------------------------
