@@ -230,6 +230,7 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------------
 // interface value gamma for entry m of side s of patch p, from the face buffer F.
@@ -286,6 +287,33 @@ __device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s,
 	}
 }
 
+// gamma of entry m on all sides at once.  The own-face and (first) neighbour-face loads of all sides
+// are issued back to back without control flow in between, so a patch costs two dependent memory
+// round trips (neighbour table, faces) instead of one per side; only refinement-boundary sides take
+// the slow path through iface_gamma.  a[s] returns the patch's own boundary value.
+template <int D, int N>
+__device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int m, const double *__restrict__ F,
+                                                int (&ty)[2 * D], double (&a)[2 * D], double (&gam)[2 * D])
+{
+	using G = Geo<D, N>;
+	double b[G::S];
+	int    q[G::S];
+#pragma unroll
+	for (int s = 0; s < G::S; s++) {
+		ty[s] = pm.nbr_type[s];
+		q[s]  = pm.nbr_idx[s][0];
+	}
+#pragma unroll
+	for (int s = 0; s < G::S; s++) a[s] = __ldg(F + ((size_t) p * G::S + s) * G::M + m);
+#pragma unroll
+	for (int s = 0; s < G::S; s++) b[s] = __ldg(F + ((size_t) (ty[s] == NBR_NONE ? p : q[s]) * G::S + (s ^ 1)) * G::M + m);
+#pragma unroll
+	for (int s = 0; s < G::S; s++) {
+		gam[s] = 0.5 * a[s] + 0.5 * b[s];
+		if (ty[s] > NBR_NORMAL) gam[s] = iface_gamma<D, N>(pm, p, s, m, F);
+	}
+}
+
 // cell index inside a patch of face entry m on side s (Vector.h:153-177: the slice drops axis s/2
 // and keeps the remaining axes in order)
 template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, int (&c)[3])
@@ -302,6 +330,32 @@ template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, 
 		else if (ax == 1) c[0] = i, c[1] = pos, c[2] = j;
 		else c[0] = i, c[1] = j, c[2] = pos;
 	}
+}
+
+// L2 prefetch of everything iface_gamma will read for patch p (own faces and the neighbours' opposite
+// faces), one 128-byte line per call slot; the M threads of a patch share the work.  Issued one
+// persistent-loop iteration ahead so that the demand loads of the next iteration hit L2.
+template <int D, int N>
+__device__ __forceinline__ void prefetch_faces_l2(const PatchMeta *__restrict__ meta, int p, int m, const double *__restrict__ F)
+{
+	using G              = Geo<D, N>;
+	constexpr int LPF    = (G::M * 8 + 127) / 128; // lines per face
+	constexpr int ITEMS  = G::S * (1 + G::Q) * LPF;
+	const PatchMeta &pm  = meta[p];
+	for (int i = m; i < ITEMS; i += G::M) {
+		const int line = i % LPF, j = (i / LPF) % (1 + G::Q), s = i / (LPF * (1 + G::Q));
+		const int t    = pm.nbr_type[s];
+		if (j == 0) {
+			prefetch_l2(F + ((size_t) p * G::S + s) * G::M + line * 16);
+		} else if (t != NBR_NONE && (j == 1 || t == NBR_FINE)) {
+			prefetch_l2(F + ((size_t) pm.nbr_idx[s][j - 1] * G::S + (s ^ 1)) * G::M + line * 16);
+		}
+	}
+}
+template <int D, int N> __device__ __forceinline__ void prefetch_patch_l2(const double *__restrict__ v, int p, int m)
+{
+	using G = Geo<D, N>;
+	for (int i = m * 16; i < G::NC; i += G::M * 16) prefetch_l2(v + (size_t) p * G::NC + i);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -366,10 +420,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 			h2                  = pm.h2;
 			if (!ZERO_GUESS) {
 				// entry m of every side is both produced and consumed by thread m: no staging needed
+				int    ty[G::S];
+				double own[G::S], gm[G::S];
+				gamma_all_sides<D, N>(pm, p, m, Fin, ty, own, gm);
 #pragma unroll
 				for (int s = 0; s < G::S; s++) {
-					ntype[s] = pm.nbr_type[s];
-					if (ntype[s] != NBR_NONE) gam[s] = cfac * iface_gamma<D, N>(pm, p, s, m, Fin);
+					ntype[s] = (int8_t) ty[s];
+					gam[s]   = cfac * gm[s];
 				}
 			}
 		}
@@ -507,128 +564,142 @@ template <int D, int N> __device__ __forceinline__ int gidx(int x, int y, int z)
 }
 
 template <int D, int N, int MODE>
-__global__ void __launch_bounds__(TGPU_THREADS)
+__global__ void __launch_bounds__(TGPU_THREADS, 2)
 apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ u, const double *__restrict__ f,
              const double *__restrict__ F, double *__restrict__ out, double *__restrict__ coarse)
 {
+	// Persistent CTAs over groups of PPB patches; u of the next group streams into the second
+	// ghosted shared-memory tile with cp.async while the current group is processed.
 	using G = Geo<D, N>;
 	extern __shared__ double smem[];
-	const int  t     = threadIdx.x;
-	const int  pb    = blockIdx.x * G::PPB;
-	const int  pp    = t / G::M;
-	const int  m     = t % G::M;
-	const int  p     = pb + pp;
-	const bool valid = p < P;
+	double *   Ubuf0 = smem;
+	double *   Ubuf1 = smem + G::PPB * G::GP;
+	const int  t    = threadIdx.x;
+	const int  pp   = t / G::M;
+	const int  m    = t % G::M;
+	const int  nblk = (P + G::PPB - 1) / G::PPB;
+	const int  x = m % N, y = (D == 2) ? 0 : m / N;
 
-	// ---- interior (coalesced) ----
-#pragma unroll
-	for (int k = 0; k < N; k++) {
-		const int    e  = t + TGPU_THREADS * k;
-		const int    lp = e / G::NC, c = e % G::NC;
-		const double val = (pb + lp < P) ? __ldg(u + (size_t) (pb + lp) * G::NC + c) : 0.0;
-		const int    x = c % N, y = (c / N) % N, z = (D == 2) ? 0 : c / (N * N);
-		smem[lp * G::GP + gidx<D, N>(x, y, z)] = val;
-	}
-	double *U = smem + pp * G::GP;
-	// ---- ghost layer ----
-	double inv_h2 = 0.0;
-	if (valid) {
-		const PatchMeta &pm = meta[p];
-		inv_h2              = pm.inv_h2;
-#pragma unroll
-		for (int s = 0; s < G::S; s++) {
-			const double a = __ldg(F + ((size_t) p * G::S + s) * G::M + m);
-			double       g;
-			if (pm.nbr_type[s] == NBR_NONE) g = ((pm.neumann >> s) & 1) ? a : -a;
-			else g = 2.0 * iface_gamma<D, N>(pm, p, s, m, F) - a;
-			int c[3];
-			face_cell<D, N>(s, m, c);
-			c[s >> 1] += (s & 1) ? 1 : -1;
-			U[gidx<D, N>(c[0], c[1], c[2])] = g;
-		}
-	}
-	__syncthreads();
-
-	// ---- stencil, marching along the last axis ----
-	const int x = m % N, y = (D == 2) ? 0 : m / N;
-	double    r[N];
-	{
-		double lo = (D == 2) ? U[gidx<D, N>(x, -1, 0)] : U[gidx<D, N>(x, y, -1)];
-		double ce = (D == 2) ? U[gidx<D, N>(x, 0, 0)] : U[gidx<D, N>(x, y, 0)];
+	auto prefetch = [&](int g, double *Udst) {
+		const int pb = g * G::PPB;
 #pragma unroll
 		for (int k = 0; k < N; k++) {
-			const double hi = (D == 2) ? U[gidx<D, N>(x, k + 1, 0)] : U[gidx<D, N>(x, y, k + 1)];
-			double       acc;
-			if (D == 2) {
-				acc = (U[gidx<D, N>(x - 1, k, 0)] - 2 * ce + U[gidx<D, N>(x + 1, k, 0)]) + (lo - 2 * ce + hi);
-			} else {
-				acc = (U[gidx<D, N>(x - 1, y, k)] - 2 * ce + U[gidx<D, N>(x + 1, y, k)])
-				      + (U[gidx<D, N>(x, y - 1, k)] - 2 * ce + U[gidx<D, N>(x, y + 1, k)]) + (lo - 2 * ce + hi);
+			const int  e  = t + TGPU_THREADS * k;
+			const int  lp = e / G::NC, c = e % G::NC;
+			const bool ok = pb + lp < P;
+			const int  cx = c % N, cy = (c / N) % N, cz = (D == 2) ? 0 : c / (N * N);
+			cp_async8(Udst + lp * G::GP + gidx<D, N>(cx, cy, cz), ok ? u + (size_t) (pb + lp) * G::NC + c : u, ok);
+		}
+	};
+
+	int g = blockIdx.x;
+	if (g < nblk) prefetch(g, Ubuf0);
+	cp_async_commit();
+
+	for (int it = 0; g < nblk; g += gridDim.x, it++) {
+		double *   U     = ((it & 1) ? Ubuf1 : Ubuf0) + pp * G::GP;
+		const int  p     = g * G::PPB + pp;
+		const bool valid = p < P;
+		if (g + (int) gridDim.x < nblk) {
+			prefetch(g + gridDim.x, (it & 1) ? Ubuf0 : Ubuf1);
+			const int pn = (g + gridDim.x) * G::PPB + pp;
+			if (pn < P) { // pull the next patch's f and faces into L2 now; they are demanded next iteration
+				if (MODE != 0) prefetch_patch_l2<D, N>(f, pn, m);
+				prefetch_faces_l2<D, N>(meta, pn, m, F);
 			}
-			r[k] = acc * inv_h2;
-			lo   = ce;
-			ce   = hi;
 		}
-	}
-	if (MODE == 0) {
+		cp_async_commit();
+
+		// right-hand side of this patch
+		double r[N];
+		if (MODE != 0) {
+#pragma unroll
+			for (int k = 0; k < N; k++) r[k] = valid ? __ldg(f + (size_t) p * G::NC + k * G::M + m) : 0.0;
+		}
+		// ---- ghost layer of the current tile (the cp.async above only writes interior cells) ----
+		double inv_h2 = 0.0;
+		int    orth   = -1;
+		int    parent = 0;
 		if (valid) {
-			double *op = out + (size_t) p * G::NC + m;
+			const PatchMeta &pm = meta[p];
+			inv_h2              = pm.inv_h2;
+			orth                = pm.orth_on_parent;
+			parent              = pm.parent_idx;
+			int    ty[G::S];
+			double own[G::S], gm[G::S];
+			gamma_all_sides<D, N>(pm, p, m, F, ty, own, gm);
 #pragma unroll
-			for (int k = 0; k < N; k++) op[k * G::M] = r[k];
+			for (int s = 0; s < G::S; s++) {
+				double gh;
+				if (ty[s] == NBR_NONE) gh = ((pm.neumann >> s) & 1) ? own[s] : -own[s];
+				else gh = 2.0 * gm[s] - own[s];
+				int c[3];
+				face_cell<D, N>(s, m, c);
+				c[s >> 1] += (s & 1) ? 1 : -1;
+				U[gidx<D, N>(c[0], c[1], c[2])] = gh;
+			}
 		}
-		return;
-	}
-	if (valid) {
-		const double *fp = f + (size_t) p * G::NC + m;
+		cp_async_wait<1>();
+		__syncthreads();
+
+		// ---- stencil, marching along the last axis ----
+		{
+			double lo = (D == 2) ? U[gidx<D, N>(x, -1, 0)] : U[gidx<D, N>(x, y, -1)];
+			double ce = (D == 2) ? U[gidx<D, N>(x, 0, 0)] : U[gidx<D, N>(x, y, 0)];
 #pragma unroll
-		for (int k = 0; k < N; k++) r[k] = __ldg(fp + k * G::M) - r[k];
-	}
-	if (MODE == 1) {
-		if (valid) {
-			double *op = out + (size_t) p * G::NC + m;
-#pragma unroll
-			for (int k = 0; k < N; k++) op[k * G::M] = r[k];
+			for (int k = 0; k < N; k++) {
+				const double hi = (D == 2) ? U[gidx<D, N>(x, k + 1, 0)] : U[gidx<D, N>(x, y, k + 1)];
+				double       acc;
+				if (D == 2) {
+					acc = (U[gidx<D, N>(x - 1, k, 0)] - 2 * ce + U[gidx<D, N>(x + 1, k, 0)]) + (lo - 2 * ce + hi);
+				} else {
+					acc = (U[gidx<D, N>(x - 1, y, k)] - 2 * ce + U[gidx<D, N>(x + 1, y, k)])
+					      + (U[gidx<D, N>(x, y - 1, k)] - 2 * ce + U[gidx<D, N>(x, y + 1, k)]) + (lo - 2 * ce + hi);
+				}
+				r[k] = (MODE == 0) ? acc * inv_h2 : r[k] - acc * inv_h2;
+				lo   = ce;
+				ce   = hi;
+			}
 		}
-		return;
-	}
-	// ---- MODE 2: restrict.  Stage r densely in smem (aliasing U), then average 2^D cells ----
-	__syncthreads();
-	double *R = smem; // [PPB][NC]
+		__syncthreads(); // all reads of this tile are done: the next iteration may refill it
+		if (MODE != 2) {
+			if (valid) {
+				double *op = out + (size_t) p * G::NC + m;
 #pragma unroll
-	for (int k = 0; k < N; k++) R[pp * G::NC + k * G::M + m] = r[k];
-	__syncthreads();
-	constexpr int H     = N / 2;
-	constexpr int CC    = G::NC >> D;      // coarse cells per patch
-	constexpr int ITEMS = G::PPB * G::NC;  // fine cells per block
-	// copy patches (present on both levels) move all NC cells; refined patches write CC averages.
-	for (int e = t; e < ITEMS; e += TGPU_THREADS) {
-		const int lp = e / G::NC, c = e % G::NC;
-		const int q  = pb + lp;
-		if (q >= P) continue;
-		const PatchMeta &qm   = meta[q];
-		const int        orth = qm.orth_on_parent;
-		double *         dst  = coarse + (size_t) qm.parent_idx * G::NC;
-		if (orth < 0) {
-			dst[c] = R[lp * G::NC + c];
-		} else if (c < CC) {
-			const int cx = c % H, cy = (c / H) % H, cz = (D == 2) ? 0 : c / (H * H);
-			double    acc = 0.0;
-			// reference accumulation order: x fastest, then y, then z (GMG/AvgRstr.h:95-102)
+				for (int k = 0; k < N; k++) op[k * G::M] = r[k];
+			}
+		} else {
+			// ---- restriction (GMG/AvgRstr.h:88-107) straight from registers: pairs along the last
+			// axis in-thread, then x (and y) partners through warp shuffles ----
+			constexpr int H = N / 2;
+			double        a[H];
 #pragma unroll
-			for (int dz = 0; dz < (D == 2 ? 1 : 2); dz++)
+			for (int j = 0; j < H; j++) {
+				a[j] = r[2 * j] / (1 << D) + r[2 * j + 1] / (1 << D);
+				a[j] += __shfl_xor_sync(0xffffffffu, a[j], 1);
+				if (D == 3) a[j] += __shfl_xor_sync(0xffffffffu, a[j], N);
+			}
+			if (valid) {
+				double *dst = coarse + (size_t) parent * G::NC;
+				if (orth < 0) { // patch present on both levels: copy
 #pragma unroll
-				for (int dy = 0; dy < 2; dy++)
+					for (int k = 0; k < N; k++) dst[k * G::M + m] = r[k];
+				} else if ((x & 1) == 0 && (y & 1) == 0) {
+					const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = ((orth >> (D - 1)) & 1) * H;
+					if (D == 2) {
 #pragma unroll
-					for (int dx = 0; dx < 2; dx++) {
-						const int fi = ((2 * cz + dz) * N + (2 * cy + dy)) * N + (2 * cx + dx);
-						acc += R[lp * G::NC + fi] / (1 << D);
+						for (int j = 0; j < H; j++) dst[(j + oy) * N + (x / 2 + ox)] = a[j];
+					} else {
+#pragma unroll
+						for (int j = 0; j < H; j++) dst[((j + oz) * N + (y / 2 + oy)) * N + (x / 2 + ox)] = a[j];
 					}
-			const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
-			dst[((cz + oz) * N + (cy + oy)) * N + (cx + ox)] = acc;
+				}
+			}
 		}
 	}
+	cp_async_wait<0>();
 }
-template <int D, int N> constexpr size_t apply_smem_bytes() { return sizeof(double) * (size_t) (Geo<D, N>::PPB * Geo<D, N>::GP); }
+template <int D, int N> constexpr size_t apply_smem_bytes() { return sizeof(double) * (size_t) (2 * Geo<D, N>::PPB * Geo<D, N>::GP); }
 
 // ---------------------------------------------------------------------------------------------
 // face buffer helpers

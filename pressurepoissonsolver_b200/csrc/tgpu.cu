@@ -730,7 +730,8 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : "residual_restrict"), l);
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
-		const int grid = (L.P + G::PPB - 1) / G::PPB;
+		const int nblk = (L.P + G::PPB - 1) / G::PPB;
+		const int grid = std::min(nblk, h->ctx->sm_count * 2);
 		const size_t sm = apply_smem_bytes<DD, NN>();
 		if (mode == 0) return launch(h->ctx, apply_kernel<DD, NN, 0>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
 		if (mode == 1) return launch(h->ctx, apply_kernel<DD, NN, 1>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);

@@ -60,12 +60,12 @@ def test_level_operators_vs_reference(gcase):
             h.prolong_add(l, uc, fine)
             assert np.array_equal(fine.download(), g["L%d_interp" % l])  # bit exact
             h.residual_restrict(l, f, u, c)
-            lv = None
-            # fused residual+restrict == restrict(f - A u) of the separate kernels, bit for bit
+            # fused residual+restrict == restrict(f - A u) of the separate kernels up to the order of
+            # the 2^D-term average (warp-shuffle tree instead of the reference's left fold)
             h.residual(l, f, u, out)
             c2 = h.new_vec(l + 1)
             h.restrict(l, out, c2)
-            assert np.array_equal(c.download(), c2.download())
+            assert rel_l2(c.download(), c2.download()) < 1e-15
         h.smooth(l, f, u)
         assert rel_l2(u.download(), g["L%d_smooth" % l]) < TOL
 
