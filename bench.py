@@ -178,7 +178,7 @@ def main():
         a[0] += 1
         a[1] += kms
     prof_total = sum(v[1] for v in agg.values())
-    smooth_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name == "smooth"]
+    smooth_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name in ("smooth", "smooth_prolong")]
     smooth0_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name == "smooth_zero_guess"]
     dom_ms = (smooth_ms[0] + smooth0_ms[0]) / 2 if smooth_ms and smooth0_ms else None
     peak, peak_src = measured_peaks()

@@ -37,7 +37,9 @@ struct __align__(16) PatchMeta {
 	int8_t  orth_on_coarse[6];
 	int8_t  pad_[2];
 	int32_t nbr_idx[6][4];
-	int32_t pad2_[3];
+	int32_t nbr_parent[6]; // parent_idx of nbr_idx[s][0] (normal neighbours; lets the post-smoother fold the
+	int8_t  nbr_orth[6];   // prolongation into its face reads without a dependent table lookup)
+	int8_t  pad2_[6];
 };
 
 constexpr int TGPU_THREADS = 256;
@@ -232,88 +234,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
-// ---------------------------------------------------------------------------------------------
-// interface value gamma for entry m of side s of patch p, from the face buffer F.
-// Weights: SURVEY App. A.2 (TriLinInterp.cpp:60-172, BilinearInterpolator.cpp:61-117);
-// which contributions meet on an interface: SchurInfo.h:141-150,253-259,363-370.
-// ---------------------------------------------------------------------------------------------
-template <int D, int N>
-__device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s, int m, const double *__restrict__ F)
-{
-	using G           = Geo<D, N>;
-	const double *own = F + ((size_t) p * G::S + s) * G::M;
-	const double  a   = own[m];
-	const int     t   = pm.nbr_type[s];
-	if (t == NBR_NORMAL) {
-		const double *nb = F + ((size_t) pm.nbr_idx[s][0] * G::S + (s ^ 1)) * G::M;
-		return 0.5 * a + 0.5 * nb[m];
-	}
-	if (t == NBR_COARSE) {
-		const int     orth = pm.orth_on_coarse[s];
-		const double *nb   = F + ((size_t) pm.nbr_idx[s][0] * G::S + (s ^ 1)) * G::M;
-		if (D == 2) {
-			const double f2f = 5.0 / 6 * a - 1.0 / 6 * own[m ^ 1];
-			return f2f + 2.0 / 6 * nb[(m + (orth & 1) * N) / 2];
-		} else {
-			const int    i = m % N, j = m / N;
-			const int    i0 = i & ~1, j0 = j & ~1;
-			const double b[4] = {own[j0 * N + i0], own[j0 * N + i0 + 1], own[(j0 + 1) * N + i0], own[(j0 + 1) * N + i0 + 1]};
-			const int    self = (i & 1) | ((j & 1) << 1);
-			double       acc  = 11 * a;
-#pragma unroll
-			for (int q = 0; q < 4; q++)
-				if (q != self) acc -= b[q];
-			const int ci = (i + (orth & 1) * N) / 2, cj = (j + ((orth >> 1) & 1) * N) / 2;
-			return acc / 12.0 + 4.0 * nb[cj * N + ci] / 12.0;
-		}
-	}
-	// NBR_FINE: I am the coarse side
-	if (D == 2) {
-		const int     q  = m >= N / 2;
-		const int     fi = 2 * (m % (N / 2));
-		const double *nb = F + ((size_t) pm.nbr_idx[s][q] * G::S + (s ^ 1)) * G::M;
-		return 1.0 / 3 * a + (1.0 / 3 * nb[fi] + 1.0 / 3 * nb[fi + 1]);
-	} else {
-		const int     i = m % N, j = m / N;
-		const int     q  = (i >= N / 2) | ((j >= N / 2) << 1);
-		const int     fi = 2 * (i % (N / 2)), fj = 2 * (j % (N / 2));
-		const double *nb = F + ((size_t) pm.nbr_idx[s][q] * G::S + (s ^ 1)) * G::M;
-		double        g  = 2.0 / 6.0 * a;
-		g += 1.0 / 6.0 * nb[fj * N + fi];
-		g += 1.0 / 6.0 * nb[fj * N + fi + 1];
-		g += 1.0 / 6.0 * nb[(fj + 1) * N + fi];
-		g += 1.0 / 6.0 * nb[(fj + 1) * N + fi + 1];
-		return g;
-	}
-}
-
-// gamma of entry m on all sides at once.  The own-face and (first) neighbour-face loads of all sides
-// are issued back to back without control flow in between, so a patch costs two dependent memory
-// round trips (neighbour table, faces) instead of one per side; only refinement-boundary sides take
-// the slow path through iface_gamma.  a[s] returns the patch's own boundary value.
-template <int D, int N>
-__device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int m, const double *__restrict__ F,
-                                                int (&ty)[2 * D], double (&a)[2 * D], double (&gam)[2 * D])
-{
-	using G = Geo<D, N>;
-	double b[G::S];
-	int    q[G::S];
-#pragma unroll
-	for (int s = 0; s < G::S; s++) {
-		ty[s] = pm.nbr_type[s];
-		q[s]  = pm.nbr_idx[s][0];
-	}
-#pragma unroll
-	for (int s = 0; s < G::S; s++) a[s] = __ldg(F + ((size_t) p * G::S + s) * G::M + m);
-#pragma unroll
-	for (int s = 0; s < G::S; s++) b[s] = __ldg(F + ((size_t) (ty[s] == NBR_NONE ? p : q[s]) * G::S + (s ^ 1)) * G::M + m);
-#pragma unroll
-	for (int s = 0; s < G::S; s++) {
-		gam[s] = 0.5 * a[s] + 0.5 * b[s];
-		if (ty[s] > NBR_NORMAL) gam[s] = iface_gamma<D, N>(pm, p, s, m, F);
-	}
-}
-
 // cell index inside a patch of face entry m on side s (Vector.h:153-177: the slice drops axis s/2
 // and keeps the remaining axes in order)
 template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, int (&c)[3])
@@ -329,6 +249,125 @@ template <int D, int N> __device__ __forceinline__ void face_cell(int s, int m, 
 		if (ax == 0) c[0] = pos, c[1] = i, c[2] = j;
 		else if (ax == 1) c[0] = i, c[1] = pos, c[2] = j;
 		else c[0] = i, c[1] = j, c[2] = pos;
+	}
+}
+
+// coarse cell that fine cell c of a patch with orthant `orth` on its parent lies in (DrctIntp.h:92-111)
+template <int D, int N> __device__ __forceinline__ int parent_cell(int orth, const int (&c)[3])
+{
+	if (orth < 0) return (c[2] * N + c[1]) * N + c[0];
+	const int cx = (c[0] + (orth & 1) * N) / 2, cy = (c[1] + ((orth >> 1) & 1) * N) / 2;
+	const int cz = (D == 2) ? 0 : (c[2] + ((orth >> 2) & 1) * N) / 2;
+	return (cz * N + cy) * N + cx;
+}
+// Accessor for "boundary value idx on side s of patch q".  Plain: the face buffer entry.  With a
+// coarse vector attached (post-smoothing right after the coarse-grid correction) the piecewise
+// constant prolongation of the correction, DrctIntp.h:92-111, is added on the fly, so the
+// prolonged fine vector is never materialised: F holds the faces of the pre-smoothed u.
+template <int D, int N, bool PROLONG> struct FaceVals {
+	using G = Geo<D, N>;
+	const double *__restrict__ F;
+	const double *__restrict__ uc;
+	const PatchMeta *__restrict__ meta;
+	__device__ __forceinline__ double get(int q, int par, int orth, int s, int idx) const
+	{
+		double v = __ldg(F + ((size_t) q * G::S + s) * G::M + idx);
+		if (PROLONG) {
+			int c[3];
+			face_cell<D, N>(s, idx, c);
+			v += __ldg(uc + (size_t) par * G::NC + parent_cell<D, N>(orth, c));
+		}
+		return v;
+	}
+	// slow-path variant: looks the parent of q up in the neighbour table
+	__device__ __forceinline__ double get(int q, int s, int idx) const
+	{
+		int par = 0, orth = -1;
+		if (PROLONG) {
+			par  = meta[q].parent_idx;
+			orth = meta[q].orth_on_parent;
+		}
+		return get(q, par, orth, s, idx);
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
+// interface value gamma for entry m of side s of patch p (general version, all neighbour types).
+// Weights: SURVEY App. A.2 (TriLinInterp.cpp:60-172, BilinearInterpolator.cpp:61-117);
+// which contributions meet on an interface: SchurInfo.h:141-150,253-259,363-370.
+// ---------------------------------------------------------------------------------------------
+template <int D, int N, bool PROLONG>
+__device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s, int m, const FaceVals<D, N, PROLONG> &fv)
+{
+	const int    po = pm.parent_idx, oo = pm.orth_on_parent;
+	const double a  = fv.get(p, po, oo, s, m);
+	const int    t  = pm.nbr_type[s];
+	if (t == NBR_NORMAL) return 0.5 * a + 0.5 * fv.get(pm.nbr_idx[s][0], s ^ 1, m);
+	if (t == NBR_COARSE) {
+		const int orth = pm.orth_on_coarse[s];
+		const int nb   = pm.nbr_idx[s][0];
+		if (D == 2) {
+			const double f2f = 5.0 / 6 * a - 1.0 / 6 * fv.get(p, po, oo, s, m ^ 1);
+			return f2f + 2.0 / 6 * fv.get(nb, s ^ 1, (m + (orth & 1) * N) / 2);
+		} else {
+			const int    i = m % N, j = m / N;
+			const int    i0 = i & ~1, j0 = j & ~1;
+			const int    self = (i & 1) | ((j & 1) << 1);
+			double       acc  = 11 * a;
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+				if (q != self) acc -= fv.get(p, po, oo, s, (j0 + (q >> 1)) * N + i0 + (q & 1));
+			const int ci = (i + (orth & 1) * N) / 2, cj = (j + ((orth >> 1) & 1) * N) / 2;
+			return acc / 12.0 + 4.0 * fv.get(nb, s ^ 1, cj * N + ci) / 12.0;
+		}
+	}
+	// NBR_FINE: I am the coarse side
+	if (D == 2) {
+		const int q  = m >= N / 2;
+		const int fi = 2 * (m % (N / 2));
+		const int nb = pm.nbr_idx[s][q];
+		return 1.0 / 3 * a + (1.0 / 3 * fv.get(nb, s ^ 1, fi) + 1.0 / 3 * fv.get(nb, s ^ 1, fi + 1));
+	} else {
+		const int i = m % N, j = m / N;
+		const int q  = (i >= N / 2) | ((j >= N / 2) << 1);
+		const int fi = 2 * (i % (N / 2)), fj = 2 * (j % (N / 2));
+		const int nb = pm.nbr_idx[s][q];
+		double    g  = 2.0 / 6.0 * a;
+		g += 1.0 / 6.0 * fv.get(nb, s ^ 1, fj * N + fi);
+		g += 1.0 / 6.0 * fv.get(nb, s ^ 1, fj * N + fi + 1);
+		g += 1.0 / 6.0 * fv.get(nb, s ^ 1, (fj + 1) * N + fi);
+		g += 1.0 / 6.0 * fv.get(nb, s ^ 1, (fj + 1) * N + fi + 1);
+		return g;
+	}
+}
+
+// gamma of entry m on all sides at once.  The own-face and (first) neighbour-face loads of all sides
+// are issued back to back without control flow in between, so a patch costs two dependent memory
+// round trips (neighbour table, faces) instead of one per side; only refinement-boundary sides take
+// the slow path through iface_gamma.  a[s] returns the patch's own boundary value.
+template <int D, int N, bool PROLONG>
+__device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int m, const FaceVals<D, N, PROLONG> &fv,
+                                                int (&ty)[2 * D], double (&a)[2 * D], double (&gam)[2 * D])
+{
+	using G = Geo<D, N>;
+	double b[G::S];
+	int    q[G::S], qp[G::S], qo[G::S];
+	const int po = pm.parent_idx, oo = pm.orth_on_parent;
+#pragma unroll
+	for (int s = 0; s < G::S; s++) {
+		ty[s] = pm.nbr_type[s];
+		q[s]  = ty[s] == NBR_NONE ? p : pm.nbr_idx[s][0];
+		qp[s] = ty[s] == NBR_NORMAL ? pm.nbr_parent[s] : po; // any valid index keeps the load harmless
+		qo[s] = ty[s] == NBR_NORMAL ? pm.nbr_orth[s] : oo;
+	}
+#pragma unroll
+	for (int s = 0; s < G::S; s++) a[s] = fv.get(p, po, oo, s, m);
+#pragma unroll
+	for (int s = 0; s < G::S; s++) b[s] = fv.get(q[s], qp[s], qo[s], s ^ 1, m);
+#pragma unroll
+	for (int s = 0; s < G::S; s++) {
+		gam[s] = 0.5 * a[s] + 0.5 * b[s];
+		if (ty[s] > NBR_NORMAL) gam[s] = iface_gamma<D, N, PROLONG>(pm, p, s, m, fv);
 	}
 }
 
@@ -363,13 +402,15 @@ template <int D, int N> __device__ __forceinline__ void prefetch_patch_l2(const 
 // per patch, all in shared memory / registers.  256 threads handle PPB = 256 / N^(D-1) patches.
 //   ZERO_GUESS: gamma == 0 (first sweep of a cycle, GMG/Cycle.h:118 u->set(0)), F_in is not read.
 //   EMIT:       also write the new boundary-cell slices to F_out.
+//   PROLONG:    face values are F_in + (P u_coarse) on the boundary cells (see FaceVals).
 // eig[k_x * M + (k_y + N k_z)] = (2/N)^D / sum_axes(-4 sin^2((k_a+1) pi / 2N))   (FftwPatchSolver.h:152-170,
 // DftPatchSolver.h:214); transposed so that the x-pencil threads of a warp read it coalesced
 // ---------------------------------------------------------------------------------------------
-template <int D, int N, bool ZERO_GUESS, bool EMIT>
+template <int D, int N, bool ZERO_GUESS, bool EMIT, bool PROLONG>
 __global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
 smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ f, double *__restrict__ u,
-              const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig)
+              const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
+              const double *__restrict__ uc)
 {
 	// Persistent CTAs: each loops over groups of PPB patches (group g = blockIdx.x + k gridDim.x).
 	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
@@ -407,7 +448,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 		const int  p     = g * G::PPB + pp;
 		const bool valid = p < P;
 		// the other buffer was last read in the previous iteration, before its closing barrier
-		if (g + (int) gridDim.x < nblk) prefetch(g + gridDim.x, (it & 1) ? Sbuf0 : Sbuf1);
+		if (g + (int) gridDim.x < nblk) {
+			prefetch(g + gridDim.x, (it & 1) ? Sbuf0 : Sbuf1);
+			if (!ZERO_GUESS) { // pull the faces the next group's gamma needs into L2 one iteration ahead
+				const int pn = (g + gridDim.x) * G::PPB + pp;
+				if (pn < P) prefetch_faces_l2<D, N>(meta, pn, m, Fin);
+			}
+		}
 		cp_async_commit();
 
 		double *S = Sall + pp * G::SP;
@@ -422,7 +469,8 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 				// entry m of every side is both produced and consumed by thread m: no staging needed
 				int    ty[G::S];
 				double own[G::S], gm[G::S];
-				gamma_all_sides<D, N>(pm, p, m, Fin, ty, own, gm);
+				const FaceVals<D, N, PROLONG> fvals{Fin, uc, meta};
+				gamma_all_sides<D, N, PROLONG>(pm, p, m, fvals, ty, own, gm);
 #pragma unroll
 				for (int s = 0; s < G::S; s++) {
 					ntype[s] = (int8_t) ty[s];
@@ -627,7 +675,8 @@ apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict
 			parent              = pm.parent_idx;
 			int    ty[G::S];
 			double own[G::S], gm[G::S];
-			gamma_all_sides<D, N>(pm, p, m, F, ty, own, gm);
+			const FaceVals<D, N, false> fvals{F, nullptr, meta};
+			gamma_all_sides<D, N, false>(pm, p, m, fvals, ty, own, gm);
 #pragma unroll
 			for (int s = 0; s < G::S; s++) {
 				double gh;
@@ -716,14 +765,6 @@ __global__ void extract_faces_kernel(int P, const double *__restrict__ u, double
 		face_cell<D, N>(s, m, c);
 		F[i] = __ldg(u + p * G::NC + (c[2] * N + c[1]) * N + c[0]);
 	}
-}
-// coarse cell that fine cell c of a patch with orthant `orth` on its parent lies in (DrctIntp.h:92-111)
-template <int D, int N> __device__ __forceinline__ int parent_cell(int orth, const int (&c)[3])
-{
-	if (orth < 0) return (c[2] * N + c[1]) * N + c[0];
-	const int cx = (c[0] + (orth & 1) * N) / 2, cy = (c[1] + ((orth >> 1) & 1) * N) / 2;
-	const int cz = (D == 2) ? 0 : (c[2] + ((orth >> 2) & 1) * N) / 2;
-	return (cz * N + cy) * N + cx;
 }
 // F_fine += (P u_coarse) restricted to the boundary cells: all the post-smoother ever reads of the
 // prolonged correction (SchurHelper.h:319-331 only uses u through its face slices).

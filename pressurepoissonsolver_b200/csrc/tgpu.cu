@@ -185,14 +185,13 @@ static bool supported_dn(int D, int N)
 
 template <int D, int N> static int set_smem_attrs()
 {
-	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                        (int) smooth_smem_bytes<D, N, true>()));
-	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                        (int) smooth_smem_bytes<D, N, true>()));
-	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                        (int) smooth_smem_bytes<D, N, false>()));
-	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                        (int) smooth_smem_bytes<D, N, false>()));
+	const int sb = (int) smooth_smem_bytes<D, N, true>();
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
@@ -465,6 +464,8 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 			for (int s = 0; s < 6; s++) {
 				pm.nbr_type[s]       = NBR_NONE;
 				pm.orth_on_coarse[s] = -1;
+				pm.nbr_parent[s]     = 0;
+				pm.nbr_orth[s]       = -1;
 				for (int q = 0; q < 4; q++) pm.nbr_idx[s][q] = -1;
 			}
 			for (int s = 0; s < S; s++) {
@@ -478,6 +479,8 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 					if (j < 0 || j >= d.npatch) return fail(TGPU_ERR_ARG, "nbr_idx out of range");
 					pm.nbr_idx[s][q] = j;
 				}
+				if (d.parent_idx) pm.nbr_parent[s] = d.parent_idx[pm.nbr_idx[s][0]];
+				if (d.orth_on_parent) pm.nbr_orth[s] = d.orth_on_parent[pm.nbr_idx[s][0]];
 				if (t == NBR_COARSE) {
 					const int o = d.orth_on_coarse[(size_t) p * S + s];
 					if (o < 0 || o >= Q) return fail(TGPU_ERR_ARG, "orth_on_coarse out of range");
@@ -738,22 +741,27 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 		return launch(h->ctx, apply_kernel<DD, NN, 2>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
 	});
 }
-// zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout
-static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout)
+// zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout;
+// uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation)
+static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout,
+                    const double *uc = nullptr)
 {
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
-	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : "smooth", l);
+	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : (uc ? "smooth_prolong" : "smooth"), l);
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
 		const int nblk = (L.P + G::PPB - 1) / G::PPB;
-		const int grid = std::min(nblk, h->ctx->sm_count * smooth_min_blocks<NN>());
+		const dim3 grid(std::min(nblk, h->ctx->sm_count * smooth_min_blocks<NN>())), block(TGPU_THREADS);
+		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = h->eig;
-		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, true>(), meta, L.P, f, u, Fin, Fout, eig);
-		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, true>(), meta, L.P, f, u, Fin, Fout, eig);
-		if (!zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, false>(), meta, L.P, f, u, Fin, Fout, eig);
-		return launch(h->ctx, smooth_kernel<DD, NN, false, false>, dim3(grid), dim3(TGPU_THREADS), smooth_smem_bytes<DD, NN, false>(), meta, L.P, f, u, Fin, Fout, eig);
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
 	});
 }
 static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)
@@ -907,7 +915,7 @@ static int generic_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const doub
 }
 // Fused schedule for V cycles with >= 1 pre and post sweep.  Per level visit:
 //   smooth(zero guess) -> u, faces | residual+restrict -> f_coarse | (coarser) |
-//   faces += P u_coarse on boundary cells only | smooth(f, faces) -> u
+//   smooth(f, faces + P u_coarse on the boundary cells) -> u
 // Identical arithmetic to the generic schedule except that dead stores (the interior of the
 // prolonged u, the fine residual vector, the zero fill of u) are never materialised.
 static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces)
@@ -930,10 +938,10 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	}
 	TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
-	TRY(k_prolong_faces(h, l, C.u, Fcur));
 	for (int i = 0; i < o.post_sweeps; i++) {
 		const bool emit = (i + 1 < o.post_sweeps) || want_faces;
-		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt));
+		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
+		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr));
 		std::swap(Fcur, Falt);
 	}
 	(void) want_faces;
