@@ -40,6 +40,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+APP = os.path.join(ROOT, "apps", "steady")
+
+
+def build_app(force=False):
+    """C++ host program against the mirrored plugin surface (include/tgpu_plugin.hpp)."""
+    src = os.path.join(ROOT, "apps", "steady.cpp")
+    deps = [src, os.path.join(ROOT, "include", "tgpu_plugin.hpp"), os.path.join(ROOT, "include", "tgpu.h"), LIB]
+    if not force and os.path.exists(APP) and all(os.path.getmtime(d) <= os.path.getmtime(APP) for d in deps):
+        return APP
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++14", "-I", os.path.join(ROOT, "include"), src, "-o", APP,
+           "-L", HERE, "-ltgpu", "-Wl,-rpath," + HERE]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("g++ failed building apps/steady")
+    return APP
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_app(force="--force" in sys.argv)
     print(LIB)
