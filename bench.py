@@ -26,6 +26,8 @@ CONFIGS = {
     "B": (3, "4uni.bin", 1, 16, "config B: apps/3d/steady GMG, uniform octree 4uni.bin --divide 1, 4096 patches of 16^3 (16,777,216 cells), 5 levels, trig RHS"),
     "A": (2, "2d2uni.bin", 6, 32, "config A: apps/2d/steady2d GMG, uniform quadtree 2d2uni.bin --divide 6, 16384 patches of 32^2 (16,777,216 cells), 8 levels, trig RHS"),
     "C": (3, "2refine.bin", 3, 16, "config C: apps/3d/steady GMG, refined octree 2refine.bin --divide 3, 7680 patches of 16^3 (31,457,280 cells), 6 levels, trig RHS"),
+    "B4": (3, "4uni.bin", 1, 16, "weak-scaling point for 4 GPUs: 4uni.bin --divide 1 with the lower half (z < 0.5) refined once more, 18,432 patches of 16^3 (75,497,472 cells), 6 levels, trig RHS"),
+    "B8": (3, "4uni.bin", 2, 16, "weak-scaling point for 8 GPUs: uniform octree 4uni.bin --divide 2, 32,768 patches of 16^3 (134,217,728 cells), 6 levels, trig RHS"),
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
@@ -126,16 +128,29 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    ctx = pps.Context(local_rank)
+    cfg = args.config
     if world > 1:
+        # torch.distributed (gloo) is plumbing only: NCCL id broadcast, barrier, max-over-ranks of the device time.
+        # The data path (halo faces, coarse right-hand side, norms) goes through the library's own NCCL communicator.
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")
+        ids = [pps.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+        if args.config == "B":  # weak scaling: ~4096 patches of 16^3 per GPU (see CONFIGS)
+            cfg = {2: "C", 4: "B4", 8: "B8"}.get(world, "B8")
 
-    D, mesh_file, divide, n, desc = CONFIGS[args.config]
-    ctx = pps.Context(local_rank)
+    D, mesh_file, divide, n, desc = CONFIGS[cfg]
     mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
-    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+    if cfg == "B4":
+        mesh.refine_box((0.0, 0.0, 0.0), (1.0, 1.0, 0.5))
+    if world > 1:
+        part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=32)
+        h = pps.Hierarchy.from_partition(ctx, part)
+    else:
+        h = pps.Hierarchy.from_mesh(ctx, mesh, n)
     cells = h.ncells(0)
     level_cells = [h.ncells(l) for l in range(h.nlevels)]
     f, u = h.new_vec(0), h.new_vec(0)
@@ -156,15 +171,18 @@ def main():
         h.vcycle(f, u, opts)
     ms = ctx.timer_stop()
     launches = ctx.kernel_launches() - l0
+    total_cells = cells
     if dist is not None:
         import torch
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        c = torch.tensor([cells], dtype=torch.int64)
+        dist.all_reduce(c)
+        total_cells = int(c.item())
     sampler.stop_flag = True
     sampler.join()
     ms_per_step = ms / args.steps
-    total_cells = cells * world  # replicas: every rank runs the same single-GPU problem (multi-GPU sharding: see DESIGN.md)
     value = total_cells / (ms_per_step * 1e-3)
 
     # ---- per-kernel profile of the same steps (CUDA events around every launch, graph bypassed) ----
@@ -208,8 +226,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": desc, "cycle": "V(1,1), 1 coarse sweep, all levels down to the root patch", "cells": cells,
                    "levels": level_cells, "l2": "inputs larger than L2 (f and u are %.0f MB each, L2 is 126 MB)" % (cells * 8 / 1e6),
-                   "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
-        "roofline": {"bound": "hbm", "kernel": "smooth_kernel (block-Jacobi DST patch solve) on the finest level",
+                   "parallelism": "1 GPU" if world == 1 else "%d GPUs: patches split along a Morton curve, NCCL halo-face exchange; %d cells on rank 0, %d in total" % (world, cells, total_cells)},
+        "roofline": {"bound": "hbm", "kernel": "smooth_kernel (block-Jacobi DST patch solve) on the finest level (rank 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": None, "peak_source": peak_src, "ms_per_launch": dom_ms,
                      "algorithmic_bytes_per_launch": SMOOTH_BYTES_PER_CELL * cells, "share_of_step": smooth_share,

@@ -90,6 +90,7 @@ int tgpu_profile_end(tgpu_ctx *ctx, int *n, const TgpuProfileEntry **entries);
 int tgpu_mesh_load(const char *path, int D, tgpu_mesh **mesh);
 int tgpu_mesh_uniform(int D, int num_levels, tgpu_mesh **mesh); /* unit domain, root = level 1 */
 int tgpu_mesh_refine_leaves(tgpu_mesh *mesh);
+int tgpu_mesh_refine_box(tgpu_mesh *mesh, const double *lo, const double *hi); /* refine leaves with centre in [lo, hi) */
 int tgpu_mesh_destroy(tgpu_mesh *mesh);
 int tgpu_mesh_info(const tgpu_mesh *mesh, int *D, int *num_levels, int *num_nodes);
 /* Extract every level (finest first) for n cells per patch side.  The returned descriptors stay
@@ -149,6 +150,27 @@ int tgpu_bicgstab(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_vec *f, tg
                   int *iterations, double *rel_residual);
 /* host-buffer convenience (the e2e path): f_host -> device, one cycle, u -> u_host */
 int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_pinned, double *u_pinned);
+
+/* ---- multi-GPU (one process per GPU): Morton partition of the patches + NCCL halo exchange ----
+ * Replaces the reference's Zoltan partition / migration (ThundereggDomGen.h:223-648), the interface
+ * VecScatters (SchurHelper.h:123-150,274-276), InterLevelComm's scatters (GMG/InterLevelComm.h:151-188)
+ * and the MPI_Allreduce in the norms (Vector.h:294,306,319).
+ * Levels with at least nranks*min_patches_per_rank patches are distributed (owned patches + halo face
+ * slots, parents live with their children); coarser levels are replicated on every rank. */
+typedef struct tgpu_part tgpu_part;
+int tgpu_mesh_partition(tgpu_mesh *mesh, int n, int rank, int nranks, int min_patches_per_rank, tgpu_part **part);
+int tgpu_part_destroy(tgpu_part *part);
+int tgpu_part_info(const tgpu_part *part, int *nlevels, int *ndistributed);
+/* local tables of one level (owned patches first, then halo slots) and the owned/halo -> global maps */
+int tgpu_part_level(const tgpu_part *part, int level, TgpuLevelDesc *local_desc, int32_t *n_owned, int32_t *n_halo,
+                    const int32_t **owned_global, const int32_t **halo_global, const int32_t **halo_owner, int32_t *npeers);
+/* k-th peer of a level: faces to send (local patch, side) and halo faces to receive (slot, side), both in the
+ * order the two ranks agree on */
+int tgpu_part_peer(const tgpu_part *part, int level, int k, int32_t *peer, int32_t *nsend, const int32_t **send_patch,
+                   const int32_t **send_side, int32_t *nrecv, const int32_t **recv_slot, const int32_t **recv_side);
+int tgpu_comm_unique_id(void *id128);                                              /* ncclGetUniqueId (128 bytes) */
+int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nranks);       /* ncclCommInitRank */
+int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part *part, tgpu_hier **h);
 
 /* ---- manufactured problem (apps/3d/steady.cpp:253-265, apps/2d/steady.cpp:314-316,
  *      apps/shared/Init.cpp:152-245,305-361): f with Dirichlet data folded in, exact solution ---- */

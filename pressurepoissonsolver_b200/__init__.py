@@ -65,7 +65,7 @@ class CycleOpts(C.Structure):
 ABI_SYMBOLS = [
     "tgpu_last_error", "tgpu_version", "tgpu_init", "tgpu_finalize", "tgpu_set_stream", "tgpu_sync",
     "tgpu_kernel_launches", "tgpu_timer_start", "tgpu_timer_stop", "tgpu_profile_begin", "tgpu_profile_end", "tgpu_mesh_load", "tgpu_mesh_uniform",
-    "tgpu_mesh_refine_leaves", "tgpu_mesh_destroy", "tgpu_mesh_info", "tgpu_mesh_extract_levels",
+    "tgpu_mesh_refine_leaves", "tgpu_mesh_refine_box", "tgpu_mesh_destroy", "tgpu_mesh_info", "tgpu_mesh_extract_levels",
     "tgpu_mesh_level_ids", "tgpu_hierarchy_create", "tgpu_hierarchy_destroy", "tgpu_hierarchy_info",
     "tgpu_level_npatch", "tgpu_vec_create", "tgpu_vec_destroy", "tgpu_vec_upload", "tgpu_vec_download",
     "tgpu_vec_upload_async", "tgpu_vec_download_async", "tgpu_vec_device_ptr", "tgpu_host_alloc", "tgpu_host_free",
@@ -74,7 +74,8 @@ ABI_SYMBOLS = [
     "tgpu_vec_scale_then_add_scaled2", "tgpu_vec_two_norm", "tgpu_vec_inf_norm", "tgpu_vec_dot", "tgpu_apply",
     "tgpu_residual", "tgpu_smooth", "tgpu_smooth_jacobi", "tgpu_restrict", "tgpu_prolong_add",
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
-    "tgpu_init_trig_rhs",
+    "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer",
+    "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -87,6 +88,7 @@ for _name, _args in {
     "tgpu_profile_begin": [_vp], "tgpu_profile_end": [_vp, C.POINTER(C.c_int), C.POINTER(C.POINTER(ProfileEntry))],
     "tgpu_mesh_load": [C.c_char_p, C.c_int, C.POINTER(_vp)], "tgpu_mesh_uniform": [C.c_int, C.c_int, C.POINTER(_vp)],
     "tgpu_mesh_refine_leaves": [_vp], "tgpu_mesh_destroy": [_vp],
+    "tgpu_mesh_refine_box": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tgpu_mesh_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "tgpu_mesh_extract_levels": [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(LevelDesc))],
     "tgpu_mesh_level_ids": [_vp, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
@@ -117,6 +119,16 @@ for _name, _args in {
                       C.POINTER(C.c_double)],
     "tgpu_vcycle_host": [_vp, C.POINTER(CycleOpts), _vp, _vp],
     "tgpu_init_trig_rhs": [_vp, _vp, _vp],
+    "tgpu_mesh_partition": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)], "tgpu_part_destroy": [_vp],
+    "tgpu_part_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "tgpu_part_level": [_vp, C.c_int, C.POINTER(LevelDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                        C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
+                        C.POINTER(C.c_int32)],
+    "tgpu_part_peer": [_vp, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)),
+                       C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)),
+                       C.POINTER(C.POINTER(C.c_int32))],
+    "tgpu_comm_unique_id": [_vp], "tgpu_comm_init": [_vp, _vp, C.c_int, C.c_int],
+    "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
 }.items():
     getattr(lib, _name).argtypes = _args
     getattr(lib, _name).restype = C.c_int
@@ -150,6 +162,9 @@ class Context:
         ms = C.c_double()
         check(lib.tgpu_timer_stop(self._p, C.byref(ms)))
         return ms.value
+
+    def comm_init(self, unique_id, rank, nranks):
+        check(lib.tgpu_comm_init(self._p, C.c_char_p(unique_id), rank, nranks))
 
     def profile_begin(self):
         check(lib.tgpu_profile_begin(self._p))
@@ -191,6 +206,11 @@ class Mesh:
             check(lib.tgpu_mesh_refine_leaves(self._p))
         return self
 
+    def refine_box(self, lo, hi):
+        a, b = (C.c_double * 3)(*lo), (C.c_double * 3)(*hi)
+        check(lib.tgpu_mesh_refine_box(self._p, a, b))
+        return self
+
     def info(self):
         D, nl, nn = C.c_int(), C.c_int(), C.c_int()
         check(lib.tgpu_mesh_info(self._p, C.byref(D), C.byref(nl), C.byref(nn)))
@@ -228,6 +248,56 @@ class Mesh:
         if self._p:
             lib.tgpu_mesh_destroy(self._p)
             self._p = _vp()
+
+
+def _desc_arrays(d, D):
+    S, Q, P = 2 * D, 1 << (D - 1), d.npatch
+    arr = lambda ptr, shape, dt: np.ctypeslib.as_array(ptr, shape=shape).astype(dt).copy()  # noqa: E731
+    return dict(npatch=P, spacings=arr(d.spacing, (P, D), np.float64), starts=arr(d.starts, (P, D), np.float64),
+                neumann=arr(d.neumann_bits, (P,), np.int32), nbr_type=arr(d.nbr_type, (P, S), np.int32),
+                nbr_idx=arr(d.nbr_idx, (P, S, Q), np.int32), orth_on_coarse=arr(d.orth_on_coarse, (P, S), np.int32),
+                parent_idx=arr(d.parent_idx, (P,), np.int32), orth_on_parent=arr(d.orth_on_parent, (P,), np.int32))
+
+
+class Partition:
+    """Patches of every level split over `nranks` GPUs + the halo-exchange plan of rank `rank`."""
+
+    def __init__(self, mesh, n, rank, nranks, min_patches_per_rank=8):
+        self._p = _vp()
+        self.D = mesh.info()[0]
+        self.n, self.rank, self.nranks = n, rank, nranks
+        check(lib.tgpu_mesh_partition(mesh._p, n, rank, nranks, min_patches_per_rank, C.byref(self._p)))
+        a, b = C.c_int(), C.c_int()
+        check(lib.tgpu_part_info(self._p, C.byref(a), C.byref(b)))
+        self.nlevels, self.ndist = a.value, b.value
+
+    def level(self, l):
+        d = LevelDesc()
+        no, nh, npe = C.c_int32(), C.c_int32(), C.c_int32()
+        og, hg, ho = (C.POINTER(C.c_int32)() for _ in range(3))
+        check(lib.tgpu_part_level(self._p, l, C.byref(d), C.byref(no), C.byref(nh), C.byref(og), C.byref(hg), C.byref(ho), C.byref(npe)))
+        out = _desc_arrays(d, self.D)
+        as_np = lambda ptr, n: np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.int32)  # noqa: E731
+        out.update(n_owned=no.value, n_halo=nh.value, owned_global=as_np(og, no.value), halo_global=as_np(hg, nh.value),
+                   halo_owner=as_np(ho, nh.value), peers=[])
+        for k in range(npe.value):
+            peer, ns, nr = C.c_int32(), C.c_int32(), C.c_int32()
+            sp, ss, rs, rd = (C.POINTER(C.c_int32)() for _ in range(4))
+            check(lib.tgpu_part_peer(self._p, l, k, C.byref(peer), C.byref(ns), C.byref(sp), C.byref(ss), C.byref(nr), C.byref(rs), C.byref(rd)))
+            out["peers"].append(dict(peer=peer.value, send_patch=as_np(sp, ns.value), send_side=as_np(ss, ns.value),
+                                     recv_slot=as_np(rs, nr.value), recv_side=as_np(rd, nr.value)))
+        return out
+
+    def close(self):
+        if self._p:
+            lib.tgpu_part_destroy(self._p)
+            self._p = _vp()
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib.tgpu_comm_unique_id(buf))
+    return buf.raw
 
 
 class Vec:
@@ -315,6 +385,14 @@ class Hierarchy:
     def from_mesh(cls, ctx, mesh, n):
         nl, descs = mesh.extract_levels(n)
         return cls(ctx, mesh.info()[0], n, nl, descs)
+
+    @classmethod
+    def from_partition(cls, ctx, part):
+        self = cls.__new__(cls)
+        self.ctx, self.D, self.n, self.nlevels = ctx, part.D, part.n, part.nlevels
+        self._p = _vp()
+        check(lib.tgpu_hierarchy_create_distributed(ctx._p, part._p, C.byref(self._p)))
+        return self
 
     def npatch(self, level):
         a, b = C.c_int64(), C.c_int64()

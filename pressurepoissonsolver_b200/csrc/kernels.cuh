@@ -272,7 +272,7 @@ template <int D, int N, bool PROLONG> struct FaceVals {
 	__device__ __forceinline__ double get(int q, int par, int orth, int s, int idx) const
 	{
 		double v = __ldg(F + ((size_t) q * G::S + s) * G::M + idx);
-		if (PROLONG) {
+		if (PROLONG && par >= 0) { // par < 0: halo slot whose face already arrived with the correction added
 			int c[3];
 			face_cell<D, N>(s, idx, c);
 			v += __ldg(uc + (size_t) par * G::NC + parent_cell<D, N>(orth, c));
@@ -849,6 +849,41 @@ __global__ void jacobi_update_kernel(const PatchMeta *__restrict__ meta, int P, 
 				diag += (pm.nbr_type[2 * a + 1] == NBR_NONE) ? (((pm.neumann >> (2 * a + 1)) & 1) ? 1.0 : -1.0) : 0.0;
 		}
 		u[i] += omega * r[i] / (diag * pm.inv_h2);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU halo exchange: gather the faces a peer needs into a contiguous send buffer (optionally
+// with the prolonged coarse correction added, see FaceVals) / scatter received faces into halo slots
+// ---------------------------------------------------------------------------------------------
+template <int D, int N, bool PROLONG>
+__global__ void pack_faces_kernel(const PatchMeta *__restrict__ meta, int nfaces, const int32_t *__restrict__ patch,
+                                  const int32_t *__restrict__ side, const double *__restrict__ F, const double *__restrict__ uc,
+                                  double *__restrict__ buf)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) nfaces * G::M;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int m = (int) (i % G::M), k = (int) (i / G::M);
+		const int p = patch[k], s = side[k];
+		double    v = F[((size_t) p * G::S + s) * G::M + m];
+		if (PROLONG) {
+			int c[3];
+			face_cell<D, N>(s, m, c);
+			v += __ldg(uc + (size_t) meta[p].parent_idx * G::NC + parent_cell<D, N>(meta[p].orth_on_parent, c));
+		}
+		buf[i] = v;
+	}
+}
+template <int D, int N>
+__global__ void unpack_faces_kernel(int nfaces, const int32_t *__restrict__ slot, const int32_t *__restrict__ side,
+                                    const double *__restrict__ buf, double *__restrict__ F)
+{
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) nfaces * G::M;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int m = (int) (i % G::M), k = (int) (i / G::M);
+		F[((size_t) slot[k] * G::S + side[k]) * G::M + m] = buf[i];
 	}
 }
 

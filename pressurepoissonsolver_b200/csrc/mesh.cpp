@@ -107,6 +107,25 @@ void Mesh::refineLeaves()
 	num_levels++;
 }
 
+void Mesh::refineBox(const double *lo, const double *hi)
+{
+	std::vector<std::pair<int, int>> leaves;
+	int                              deepest = 0;
+	for (const MeshNode &n : nodes) {
+		if (n.id < 0 || n.hasChildren()) continue;
+		bool in = true;
+		for (int a = 0; a < D; a++) {
+			const double c = n.starts[a] + 0.5 * n.lengths[a];
+			in             = in && c >= lo[a] && c < hi[a];
+		}
+		if (in) leaves.push_back({n.level, n.id}), deepest = std::max(deepest, n.level);
+	}
+	std::sort(leaves.begin(), leaves.end());
+	nodes.reserve(nodes.size() + leaves.size() * (size_t) (1 << D));
+	for (auto &p : leaves) refineNode(p.second);
+	if (!leaves.empty()) num_levels = std::max(num_levels, deepest + 1);
+}
+
 // OctTree.h:180-213 + Node(parent, orthant) OctNode.h:78-90
 void Mesh::refineNode(int id)
 {
@@ -275,5 +294,193 @@ std::vector<HostLevel> Mesh::extractLevels(int n) const
 		}
 	}
 	return out;
+}
+} // namespace tgpu
+
+// ---------------------------------------------------------------------------------------------
+// partition + halo plan
+// ---------------------------------------------------------------------------------------------
+namespace tgpu
+{
+static uint64_t mortonKey(const double *starts, int D)
+{
+	uint64_t key = 0;
+	uint32_t c[3] = {0, 0, 0};
+	for (int a = 0; a < D; a++) {
+		double s = starts[a];
+		if (s < 0) s = 0;
+		if (s >= 1) s = 0.999999999;
+		c[a] = (uint32_t) (s * (double) (1u << 20));
+	}
+	for (int b = 19; b >= 0; b--)
+		for (int a = D - 1; a >= 0; a--) key = (key << 1) | ((c[a] >> b) & 1u);
+	return key;
+}
+
+Partition partitionLevels(const std::vector<HostLevel> &global, int D, int n, int rank, int nranks, int min_patches_per_rank)
+{
+	if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("partition: bad rank / nranks");
+	const int L = (int) global.size(), S = 2 * D, Q = 1 << (D - 1);
+	Partition part;
+	part.D = D, part.n = n, part.rank = rank, part.nranks = nranks;
+	// distributed levels = the finest levels that have enough patches for every rank
+	int ndist = 0;
+	if (nranks > 1)
+		while (ndist < L && global[ndist].npatch >= (int64_t) nranks * std::max(1, min_patches_per_rank)) ndist++;
+	part.ndist = ndist;
+	part.owner.resize(ndist);
+	if (ndist > 0) {
+		// weights: finest-level descendants of every patch of the coarsest distributed level
+		std::vector<std::vector<int64_t>> w(ndist);
+		w[0].assign(global[0].npatch, 1);
+		for (int l = 0; l + 1 < ndist; l++) {
+			w[l + 1].assign(global[l + 1].npatch, 0);
+			for (int p = 0; p < global[l].npatch; p++) w[l + 1][global[l].parent_idx[p]] += w[l][p];
+		}
+		const int            top = ndist - 1;
+		const HostLevel &    T   = global[top];
+		std::vector<int32_t> order(T.npatch);
+		for (int p = 0; p < T.npatch; p++) order[p] = p;
+		std::vector<uint64_t> key(T.npatch);
+		for (int p = 0; p < T.npatch; p++) key[p] = mortonKey(&T.starts[(size_t) p * D], D);
+		std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+		int64_t total = 0;
+		for (int64_t x : w[top]) total += x;
+		part.owner[top].assign(T.npatch, 0);
+		// contiguous Morton ranges of ~equal weight; every rank gets at least one patch
+		int64_t acc = 0;
+		int     r = 0, have = 0;
+		for (int i = 0; i < T.npatch; i++) {
+			const int32_t p    = order[i];
+			part.owner[top][p] = r;
+			acc += w[top][p];
+			have++;
+			const bool quota_met   = acc * nranks >= (int64_t) (r + 1) * total;
+			const bool must_advance = (T.npatch - i - 1) <= (nranks - r - 1);
+			if (r < nranks - 1 && have >= 1 && (quota_met || must_advance)) r++, have = 0;
+		}
+		for (int l = top - 1; l >= 0; l--) {
+			part.owner[l].resize(global[l].npatch);
+			for (int p = 0; p < global[l].npatch; p++) part.owner[l][p] = part.owner[l + 1][global[l].parent_idx[p]];
+		}
+	}
+	part.levels.resize(L);
+	std::vector<int32_t> local_of_global_next; // local index of level l+1 patches on this rank (distributed) or identity
+	for (int l = L - 1; l >= 0; l--) {
+		PartLevel &      PL = part.levels[l];
+		const HostLevel &GL = global[l];
+		std::vector<int32_t> local_of_global(GL.npatch, -1);
+		if (l >= ndist) {
+			PL.distributed = false;
+			PL.local       = GL;
+			PL.n_owned     = GL.npatch;
+			PL.owned_global.resize(GL.npatch);
+			for (int p = 0; p < GL.npatch; p++) PL.owned_global[p] = p, local_of_global[p] = p;
+			local_of_global_next = local_of_global;
+			continue;
+		}
+		PL.distributed                 = true;
+		const std::vector<int32_t> &ow = part.owner[l];
+		for (int p = 0; p < GL.npatch; p++)
+			if (ow[p] == rank) {
+				local_of_global[p] = (int32_t) PL.owned_global.size();
+				PL.owned_global.push_back(p);
+			}
+		PL.n_owned = (int32_t) PL.owned_global.size();
+		// halo = off-rank neighbours of owned patches, in global order
+		std::vector<char> is_halo(GL.npatch, 0);
+		for (int32_t p : PL.owned_global)
+			for (int s = 0; s < S; s++)
+				for (int q = 0; q < Q; q++) {
+					const int32_t j = GL.nbr_idx[((size_t) p * S + s) * Q + q];
+					if (j >= 0 && ow[j] != rank) is_halo[j] = 1;
+				}
+		for (int p = 0; p < GL.npatch; p++)
+			if (is_halo[p]) {
+				local_of_global[p] = PL.n_owned + (int32_t) PL.halo_global.size();
+				PL.halo_global.push_back(p);
+				PL.halo_owner.push_back(ow[p]);
+			}
+		PL.n_halo = (int32_t) PL.halo_global.size();
+		// remapped local tables
+		HostLevel &LL = PL.local;
+		const int  P  = PL.n_owned + PL.n_halo;
+		LL.npatch     = P;
+		LL.spacing.resize((size_t) P * D);
+		LL.starts.resize((size_t) P * D);
+		LL.neumann.assign(P, 0);
+		LL.nbr_type.assign((size_t) P * S, TGPU_NBR_NONE);
+		LL.orth_on_coarse.assign((size_t) P * S, -1);
+		LL.orth_on_parent.assign(P, -1);
+		LL.nbr_idx.assign((size_t) P * S * Q, -1);
+		LL.parent_idx.assign(P, -1);
+		LL.ids.resize(P);
+		LL.parent_ids.resize(P);
+		LL.refine_levels.resize(P);
+		for (int k = 0; k < P; k++) {
+			const int32_t gp = k < PL.n_owned ? PL.owned_global[k] : PL.halo_global[k - PL.n_owned];
+			for (int a = 0; a < D; a++) {
+				LL.spacing[(size_t) k * D + a] = GL.spacing[(size_t) gp * D + a];
+				LL.starts[(size_t) k * D + a]  = GL.starts[(size_t) gp * D + a];
+			}
+			LL.ids[k]           = GL.ids[gp];
+			LL.parent_ids[k]    = GL.parent_ids[gp];
+			LL.refine_levels[k] = GL.refine_levels[gp];
+			if (k >= PL.n_owned) continue; // halo slots carry faces only: no neighbours, no parent
+			LL.neumann[k]        = GL.neumann[gp];
+			LL.orth_on_parent[k] = GL.orth_on_parent[gp];
+			if (l + 1 < L) {
+				const int32_t pl = local_of_global_next[GL.parent_idx[gp]];
+				if (pl < 0) throw std::runtime_error("partition: parent of an owned patch is not local");
+				LL.parent_idx[k] = pl;
+			}
+			for (int s = 0; s < S; s++) {
+				LL.nbr_type[(size_t) k * S + s]       = GL.nbr_type[(size_t) gp * S + s];
+				LL.orth_on_coarse[(size_t) k * S + s] = GL.orth_on_coarse[(size_t) gp * S + s];
+				for (int q = 0; q < Q; q++) {
+					const int32_t j = GL.nbr_idx[((size_t) gp * S + s) * Q + q];
+					if (j >= 0) LL.nbr_idx[((size_t) k * S + s) * Q + q] = local_of_global[j];
+				}
+			}
+		}
+		// exchange plan: peer q needs face (N, s^1) of my patch N whenever one of q's patches has N on side s
+		struct Need {
+			int32_t patch, side;
+			bool    operator<(const Need &o) const { return patch != o.patch ? patch < o.patch : side < o.side; }
+			bool    operator==(const Need &o) const { return patch == o.patch && side == o.side; }
+		};
+		std::vector<std::vector<Need>> send(nranks), recv(nranks);
+		for (int p = 0; p < GL.npatch; p++)
+			for (int s = 0; s < S; s++)
+				for (int q = 0; q < Q; q++) {
+					const int32_t j = GL.nbr_idx[((size_t) p * S + s) * Q + q];
+					if (j < 0 || ow[j] == ow[p]) continue;
+					if (ow[p] == rank) recv[ow[j]].push_back({j, s ^ 1}); // I read face s^1 of j (owned by ow[j])
+					if (ow[j] == rank) send[ow[p]].push_back({j, s ^ 1}); // ow[p] reads face s^1 of my patch j
+				}
+		for (int r = 0; r < nranks; r++) {
+			if (r == rank) continue;
+			auto uniq = [](std::vector<Need> &v) {
+				std::sort(v.begin(), v.end());
+				v.erase(std::unique(v.begin(), v.end()), v.end());
+			};
+			uniq(send[r]);
+			uniq(recv[r]);
+			if (send[r].empty() && recv[r].empty()) continue;
+			PeerExchange px;
+			px.peer = r;
+			for (const Need &x : send[r]) {
+				px.send_patch.push_back(local_of_global[x.patch]);
+				px.send_side.push_back(x.side);
+			}
+			for (const Need &x : recv[r]) {
+				px.recv_slot.push_back(local_of_global[x.patch]);
+				px.recv_side.push_back(x.side);
+			}
+			PL.peers.push_back(std::move(px));
+		}
+		local_of_global_next = local_of_global;
+	}
+	return part;
 }
 } // namespace tgpu

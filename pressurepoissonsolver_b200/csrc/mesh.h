@@ -45,6 +45,8 @@ class Mesh
 	static Mesh load(const std::string &path, int D);
 	static Mesh uniform(int D, int num_levels);
 	void        refineLeaves();
+	// refine every leaf whose centre lies in [lo, hi) (used to build weak-scaling meshes; the caller keeps 2:1 balance)
+	void        refineBox(const double *lo, const double *hi);
 	int         numNodes() const;
 
 	// finest first; same patch order as the reference's local_index
@@ -58,4 +60,38 @@ class Mesh
 
 // Orthant<D>::getValuesOnSide (src/Thunderegg/Side.h:346-362)
 void orthantsOnSide(int D, int side, int out[4]);
+} // namespace tgpu
+
+// ---------------------------------------------------------------------------------------------
+// Patch partition across the GPUs of one node + halo-exchange plan (replaces the reference's
+// Zoltan PHG partition + PatchInfo migration, ThundereggDomGen.h:223-648, and the per-level
+// VecScatter set-up of SchurHelper.h:195-280).
+//
+// Levels 0 .. ndist-1 are distributed: the coarsest distributed level is cut into `nranks`
+// contiguous ranges along a Morton (Z-order) curve, weighted by the number of finest-level
+// descendants; finer patches live where their parent lives, so restriction and prolongation
+// between distributed levels are local.  Levels ndist .. are replicated on every rank (their
+// right-hand side is assembled by an all-reduce).  A rank's local level = owned patches followed
+// by halo slots for every off-rank neighbour; only face slices are exchanged.
+namespace tgpu
+{
+struct PeerExchange {
+	int                  peer = -1;
+	std::vector<int32_t> send_patch, send_side; // local owned patch index, side whose face the peer needs
+	std::vector<int32_t> recv_slot, recv_side;  // local halo slot index (>= n_owned), side
+};
+struct PartLevel {
+	bool                      distributed = false;
+	HostLevel                 local;        // remapped tables: npatch = n_owned + n_halo (replicated: the global level)
+	int32_t                   n_owned = 0, n_halo = 0;
+	std::vector<int32_t>      owned_global; // global patch index of each owned patch
+	std::vector<int32_t>      halo_global, halo_owner;
+	std::vector<PeerExchange> peers;
+};
+struct Partition {
+	int                    D = 3, n = 0, rank = 0, nranks = 1, ndist = 0;
+	std::vector<PartLevel> levels;
+	std::vector<std::vector<int32_t>> owner; // [level][global patch] for distributed levels
+};
+Partition partitionLevels(const std::vector<HostLevel> &global, int D, int n, int rank, int nranks, int min_patches_per_rank);
 } // namespace tgpu

@@ -2,6 +2,8 @@
 // Host-side structure: context (stream, scratch), hierarchy (device neighbour tables, per-level
 // work vectors and face buffers, eigenvalue table), vectors, cycle driver with CUDA-graph replay.
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -54,6 +56,56 @@ extern "C" const char *tgpu_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *tgpu_version(void) { return "tgpu 0.1 (sm_100a, fp64)"; }
 
 // ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time
+// ------------------------------------------------------------------------------------------
+namespace
+{
+struct NcclApi {
+	void *lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId *)                                                              = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int)                                       = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t)                                                                  = nullptr;
+	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                = nullptr;
+	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                      = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)()                                                                             = nullptr;
+	ncclResult_t (*GroupEnd)()                                                                               = nullptr;
+	const char *(*GetErrorString)(ncclResult_t)                                                              = nullptr;
+};
+NcclApi g_nccl;
+int     load_nccl()
+{
+	if (g_nccl.lib) return TGPU_OK;
+	const char *names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char *nm : names) {
+		g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+		if (g_nccl.lib) break;
+	}
+	if (!g_nccl.lib) return fail(TGPU_ERR_COMM, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+#define NCCL_SYM(field, name)                                                                      \
+	*(void **) (&g_nccl.field) = dlsym(g_nccl.lib, name);                                          \
+	if (!g_nccl.field) return fail(TGPU_ERR_COMM, std::string("libnccl is missing symbol ") + name);
+	NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+	NCCL_SYM(CommInitRank, "ncclCommInitRank")
+	NCCL_SYM(CommDestroy, "ncclCommDestroy")
+	NCCL_SYM(Send, "ncclSend")
+	NCCL_SYM(Recv, "ncclRecv")
+	NCCL_SYM(AllReduce, "ncclAllReduce")
+	NCCL_SYM(GroupStart, "ncclGroupStart")
+	NCCL_SYM(GroupEnd, "ncclGroupEnd")
+	NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+	return TGPU_OK;
+}
+} // namespace
+#define NC(call)                                                                                         \
+	do {                                                                                                 \
+		ncclResult_t r_ = (call);                                                                        \
+		if (r_ != ncclSuccess) return fail(TGPU_ERR_COMM, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+	} while (0)
+
+
+// ------------------------------------------------------------------------------------------
 // objects
 // ------------------------------------------------------------------------------------------
 struct tgpu_ctx {
@@ -68,6 +120,10 @@ struct tgpu_ctx {
 	int64_t      launches  = 0;
 	bool         capturing = false;
 	int64_t      captured  = 0;
+	// multi-GPU
+	ncclComm_t comm   = nullptr;
+	int        rank   = 0;
+	int        nranks = 1;
 	// per-launch profiling
 	bool                          profiling = false;
 	const char *                  tag_name  = "kernel";
@@ -98,8 +154,23 @@ struct tgpu_mesh {
 	std::vector<TgpuLevelDesc> descs;
 };
 
+struct tgpu_part {
+	Partition                  part;
+	std::vector<TgpuLevelDesc> descs;
+};
+
+struct PeerDev {
+	int    peer = -1;
+	size_t send_off = 0, send_n = 0, recv_off = 0, recv_n = 0; // in faces
+};
 struct LevelDev {
-	int        P      = 0;
+	int        P      = 0; // owned patches (kernel loop bound, vector length)
+	int        slots  = 0; // owned + halo face slots
+	bool       distributed = false;
+	std::vector<PeerDev> peers;
+	int32_t *  send_patch = nullptr, *send_side = nullptr, *recv_slot = nullptr, *recv_side = nullptr;
+	double *   sendbuf = nullptr, *recvbuf = nullptr;
+	size_t     nsend = 0, nrecv = 0;
 	size_t     ncells = 0, nface = 0;
 	PatchMeta *meta    = nullptr;
 	double *   starts  = nullptr;
@@ -270,6 +341,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *ctx)
 	if (!ctx) return TGPU_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
 	cudaFree(ctx->d_partial);
 	cudaFree(ctx->d_result);
 	cudaFreeHost(ctx->h_result);
@@ -374,6 +446,14 @@ extern "C" int tgpu_mesh_refine_leaves(tgpu_mesh *m)
 	return TGPU_OK;
 	API_END
 }
+extern "C" int tgpu_mesh_refine_box(tgpu_mesh *m, const double *lo, const double *hi)
+{
+	API_BEGIN
+	if (!m || !lo || !hi) return fail(TGPU_ERR_ARG, "null argument");
+	m->mesh.refineBox(lo, hi);
+	return TGPU_OK;
+	API_END
+}
 extern "C" int tgpu_mesh_destroy(tgpu_mesh *m)
 {
 	delete m;
@@ -420,7 +500,10 @@ template <typename T> static int dev_upload(T **dst, const T *src, size_t count)
 	return TGPU_OK;
 }
 
-extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLevelDesc *levels, tgpu_hier **out)
+// n_owned == nullptr: every patch of every level is owned (single GPU).  Otherwise level l has n_owned[l]
+// owned patches followed by halo face slots (multi-GPU, see tgpu_hierarchy_create_distributed).
+static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLevelDesc *levels, const int32_t *n_owned,
+                                 tgpu_hier **out)
 {
 	API_BEGIN
 	if (!ctx || !levels || !out || nlevels < 1) return fail(TGPU_ERR_ARG, "tgpu_hierarchy_create: bad argument");
@@ -439,9 +522,11 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 		const TgpuLevelDesc &d = levels[l];
 		if (d.npatch < 1) return fail(TGPU_ERR_ARG, "level without patches");
 		LevelDev L;
-		L.P      = d.npatch;
-		L.ncells = (size_t) d.npatch * NC;
+		L.P      = n_owned ? n_owned[l] : d.npatch;
+		L.slots  = d.npatch;
+		L.ncells = (size_t) L.P * NC;
 		L.nface  = (size_t) d.npatch * S * M;
+		if (L.P < 0 || L.P > d.npatch) return fail(TGPU_ERR_ARG, "owned patch count out of range");
 		std::vector<PatchMeta> meta(d.npatch);
 		const int              Pc = (l + 1 < nlevels) ? levels[l + 1].npatch : 0;
 		for (int p = 0; p < d.npatch; p++) {
@@ -457,7 +542,7 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 			if (pm.neumann) L.has_neumann = true;
 			pm.parent_idx     = d.parent_idx ? d.parent_idx[p] : -1;
 			pm.orth_on_parent = d.orth_on_parent ? d.orth_on_parent[p] : -1;
-			if (l + 1 < nlevels) {
+			if (l + 1 < nlevels && p < L.P) {
 				if (pm.parent_idx < 0 || pm.parent_idx >= Pc) return fail(TGPU_ERR_ARG, "parent_idx out of range");
 				if (pm.orth_on_parent >= (1 << D)) return fail(TGPU_ERR_ARG, "orth_on_parent out of range");
 			}
@@ -517,6 +602,145 @@ extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, c
 	return TGPU_OK;
 	API_END
 }
+extern "C" int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLevelDesc *levels, tgpu_hier **out)
+{
+	return hierarchy_create_impl(ctx, D, n, nlevels, levels, nullptr, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: partition ABI, NCCL (resolved at run time with dlopen so that libtgpu.so itself has
+// no link-time NCCL dependency), distributed hierarchy
+// ------------------------------------------------------------------------------------------
+extern "C" int tgpu_mesh_partition(tgpu_mesh *m, int n, int rank, int nranks, int min_patches_per_rank, tgpu_part **out)
+{
+	API_BEGIN
+	if (!m || !out) return fail(TGPU_ERR_ARG, "null argument");
+	if (n < 2 || (n & 1)) return fail(TGPU_ERR_ARG, "n must be even and >= 2");
+	std::unique_ptr<tgpu_part> p(new tgpu_part());
+	std::vector<HostLevel>     global = m->mesh.extractLevels(n);
+	p->part                           = partitionLevels(global, m->mesh.D, n, rank, nranks, min_patches_per_rank);
+	for (const PartLevel &L : p->part.levels) p->descs.push_back(L.local.desc());
+	*out = p.release();
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_part_destroy(tgpu_part *p)
+{
+	delete p;
+	return TGPU_OK;
+}
+extern "C" int tgpu_part_info(const tgpu_part *p, int *nlevels, int *ndist)
+{
+	if (!p) return fail(TGPU_ERR_ARG, "null partition");
+	if (nlevels) *nlevels = (int) p->part.levels.size();
+	if (ndist) *ndist = p->part.ndist;
+	return TGPU_OK;
+}
+extern "C" int tgpu_part_level(const tgpu_part *p, int level, TgpuLevelDesc *desc, int32_t *n_owned, int32_t *n_halo,
+                               const int32_t **owned_global, const int32_t **halo_global, const int32_t **halo_owner, int32_t *npeers)
+{
+	if (!p || level < 0 || level >= (int) p->part.levels.size()) return fail(TGPU_ERR_ARG, "bad level");
+	const PartLevel &L = p->part.levels[level];
+	if (desc) *desc = p->descs[level];
+	if (n_owned) *n_owned = L.n_owned;
+	if (n_halo) *n_halo = L.n_halo;
+	if (owned_global) *owned_global = L.owned_global.data();
+	if (halo_global) *halo_global = L.halo_global.data();
+	if (halo_owner) *halo_owner = L.halo_owner.data();
+	if (npeers) *npeers = (int32_t) L.peers.size();
+	return TGPU_OK;
+}
+extern "C" int tgpu_part_peer(const tgpu_part *p, int level, int k, int32_t *peer, int32_t *nsend, const int32_t **send_patch,
+                              const int32_t **send_side, int32_t *nrecv, const int32_t **recv_slot, const int32_t **recv_side)
+{
+	if (!p || level < 0 || level >= (int) p->part.levels.size()) return fail(TGPU_ERR_ARG, "bad level");
+	const PartLevel &L = p->part.levels[level];
+	if (k < 0 || k >= (int) L.peers.size()) return fail(TGPU_ERR_ARG, "bad peer index");
+	const PeerExchange &x = L.peers[k];
+	if (peer) *peer = x.peer;
+	if (nsend) *nsend = (int32_t) x.send_patch.size();
+	if (send_patch) *send_patch = x.send_patch.data();
+	if (send_side) *send_side = x.send_side.data();
+	if (nrecv) *nrecv = (int32_t) x.recv_slot.size();
+	if (recv_slot) *recv_slot = x.recv_slot.data();
+	if (recv_side) *recv_side = x.recv_side.data();
+	return TGPU_OK;
+}
+
+extern "C" int tgpu_comm_unique_id(void *id128)
+{
+	API_BEGIN
+	if (!id128) return fail(TGPU_ERR_ARG, "null argument");
+	TRY(load_nccl());
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+	ncclUniqueId id;
+	NC(g_nccl.GetUniqueId(&id));
+	memcpy(id128, &id, sizeof(id));
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nranks)
+{
+	API_BEGIN
+	if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(TGPU_ERR_ARG, "tgpu_comm_init: bad argument");
+	TRY(load_nccl());
+	CU(cudaSetDevice(ctx->device));
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	NC(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+	ctx->rank   = rank;
+	ctx->nranks = nranks;
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part *part, tgpu_hier **out)
+{
+	API_BEGIN
+	if (!ctx || !part || !out) return fail(TGPU_ERR_ARG, "null argument");
+	const Partition &pt = part->part;
+	if (pt.nranks > 1 && (!ctx->comm || ctx->nranks != pt.nranks || ctx->rank != pt.rank))
+		return fail(TGPU_ERR_ARG, "tgpu_hierarchy_create_distributed: call tgpu_comm_init with the partition's rank/nranks first");
+	std::vector<int32_t> owned;
+	for (const PartLevel &L : pt.levels) owned.push_back(L.n_owned);
+	tgpu_hier *h = nullptr;
+	TRY(hierarchy_create_impl(ctx, pt.D, pt.n, (int) pt.levels.size(), part->descs.data(), owned.data(), &h));
+	size_t M = 1;
+	for (int i = 0; i < pt.D - 1; i++) M *= pt.n;
+	for (size_t l = 0; l < pt.levels.size(); l++) {
+		const PartLevel &PL = pt.levels[l];
+		LevelDev &       L  = h->levels[l];
+		L.distributed       = PL.distributed;
+		std::vector<int32_t> sp, ss, rs, rsd;
+		for (const PeerExchange &x : PL.peers) {
+			PeerDev pd;
+			pd.peer     = x.peer;
+			pd.send_off = sp.size(), pd.send_n = x.send_patch.size();
+			pd.recv_off = rs.size(), pd.recv_n = x.recv_slot.size();
+			sp.insert(sp.end(), x.send_patch.begin(), x.send_patch.end());
+			ss.insert(ss.end(), x.send_side.begin(), x.send_side.end());
+			rs.insert(rs.end(), x.recv_slot.begin(), x.recv_slot.end());
+			rsd.insert(rsd.end(), x.recv_side.begin(), x.recv_side.end());
+			L.peers.push_back(pd);
+		}
+		L.nsend = sp.size(), L.nrecv = rs.size();
+		if (L.nsend) {
+			TRY(dev_upload(&L.send_patch, sp.data(), sp.size()));
+			TRY(dev_upload(&L.send_side, ss.data(), ss.size()));
+			CU(cudaMalloc(&L.sendbuf, L.nsend * M * sizeof(double)));
+		}
+		if (L.nrecv) {
+			TRY(dev_upload(&L.recv_slot, rs.data(), rs.size()));
+			TRY(dev_upload(&L.recv_side, rsd.data(), rsd.size()));
+			CU(cudaMalloc(&L.recvbuf, L.nrecv * M * sizeof(double)));
+		}
+		// halo slots must never hold NaN garbage before the first exchange
+		CU(cudaMemset(L.Fa, 0, L.nface * sizeof(double)));
+		CU(cudaMemset(L.Fb, 0, L.nface * sizeof(double)));
+	}
+	*out = h;
+	return TGPU_OK;
+	API_END
+}
 
 static void free_graphs(tgpu_hier *h)
 {
@@ -539,6 +763,12 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.spacing);
 		cudaFree(L.Fa);
 		cudaFree(L.Fb);
+		cudaFree(L.send_patch);
+		cudaFree(L.send_side);
+		cudaFree(L.recv_slot);
+		cudaFree(L.recv_side);
+		cudaFree(L.sendbuf);
+		cudaFree(L.recvbuf);
 		cudaFree(L.u);
 		cudaFree(L.f);
 		cudaFree(L.r);
@@ -688,6 +918,8 @@ template <int OP> static int reduce(const tgpu_vec *a, const tgpu_vec *b, double
 	Tag       tg(ctx, "reduce", a->level);
 	TRY(launch(ctx, reduce_stage1<OP>, dim3(nb), dim3(256), 0, a->n, (const double *) a->d, (const double *) b->d, ctx->d_partial));
 	TRY(launch(ctx, reduce_stage2<OP>, dim3(1), dim3(256), 0, nb, (const double *) ctx->d_partial, ctx->d_result));
+	if (ctx->nranks > 1 && a->h->levels[a->level].distributed)
+		NC(g_nccl.AllReduce(ctx->d_result, ctx->d_result, 1, ncclDouble, OP == 0 ? ncclSum : ncclMax, ctx->comm, ctx->stream));
 	CU(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	*result = ctx->h_result[0];
@@ -787,6 +1019,48 @@ static int k_set(tgpu_hier *h, double *v, size_t n, double alpha)
 	return launch(h->ctx, blas1_kernel<B_SET>, dim3(grid_for(h->ctx, n)), dim3(256), 0, n, v, (const double *) nullptr, (const double *) nullptr, alpha, 0.0, 0.0);
 }
 
+// halo exchange of one distributed level: pack the faces every peer needs, grouped ncclSend/ncclRecv,
+// scatter what arrived into the halo slots of F.  uc != nullptr sends F + (P uc) on the boundary cells
+// (the receiver must not add the correction again: halo slots have no parent, see FaceVals).
+static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
+{
+	LevelDev &L   = h->levels[l];
+	tgpu_ctx *ctx = h->ctx;
+	if (!L.distributed || ctx->nranks == 1 || (L.nsend == 0 && L.nrecv == 0)) return TGPU_OK;
+	size_t M = 1;
+	for (int i = 0; i < h->D - 1; i++) M *= h->N;
+	Tag tg(ctx, "halo_exchange", l);
+	if (L.nsend) {
+		DISPATCH_DN(h->D, h->N, {
+			if (uc) TRY(launch(ctx, pack_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const double *) F, uc, L.sendbuf));
+			else TRY(launch(ctx, pack_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const double *) F, uc, L.sendbuf));
+		});
+	}
+	NC(g_nccl.GroupStart());
+	for (const PeerDev &pd : L.peers) {
+		if (pd.send_n) NC(g_nccl.Send(L.sendbuf + pd.send_off * M, pd.send_n * M, ncclDouble, pd.peer, ctx->comm, ctx->stream));
+		if (pd.recv_n) NC(g_nccl.Recv(L.recvbuf + pd.recv_off * M, pd.recv_n * M, ncclDouble, pd.peer, ctx->comm, ctx->stream));
+	}
+	NC(g_nccl.GroupEnd());
+	if (L.nrecv) {
+		DISPATCH_DN(h->D, h->N, TRY(launch(ctx, unpack_faces_kernel<DD, NN>, dim3(grid_for(ctx, L.nrecv * M)), dim3(256), 0, (int) L.nrecv, (const int32_t *) L.recv_slot, (const int32_t *) L.recv_side, (const double *) L.recvbuf, F)));
+	}
+	return TGPU_OK;
+}
+// sum a replicated level vector over the ranks (every cell is written by exactly one rank, the others hold 0)
+static int k_allreduce_sum(tgpu_hier *h, double *v, size_t n)
+{
+	tgpu_ctx *ctx = h->ctx;
+	if (ctx->nranks == 1) return TGPU_OK;
+	NC(g_nccl.AllReduce(v, v, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+	return TGPU_OK;
+}
+// true if level l is distributed and level l + 1 is replicated (the restriction crosses the boundary)
+static bool crosses_replication(const tgpu_hier *h, int l)
+{
+	return h->ctx->nranks > 1 && l + 1 < (int) h->levels.size() && h->levels[l].distributed && !h->levels[l + 1].distributed;
+}
+
 extern "C" int tgpu_apply(tgpu_hier *h, int level, const tgpu_vec *u, tgpu_vec *out)
 {
 	API_BEGIN
@@ -794,6 +1068,7 @@ extern "C" int tgpu_apply(tgpu_hier *h, int level, const tgpu_vec *u, tgpu_vec *
 	TRY(check_level_vec(h, level, out, "tgpu_apply"));
 	if (u == out) return fail(TGPU_ERR_ARG, "tgpu_apply: in-place apply is not supported");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
 	return k_apply(h, level, 0, u->d, nullptr, h->levels[level].Fa, out->d, nullptr);
 	API_END
 }
@@ -805,6 +1080,7 @@ extern "C" int tgpu_residual(tgpu_hier *h, int level, const tgpu_vec *f, const t
 	TRY(check_level_vec(h, level, r, "tgpu_residual"));
 	if (u == r) return fail(TGPU_ERR_ARG, "tgpu_residual: r must not alias u");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
 	return k_apply(h, level, 1, u->d, f->d, h->levels[level].Fa, r->d, nullptr);
 	API_END
 }
@@ -815,6 +1091,7 @@ extern "C" int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec 
 	TRY(check_level_vec(h, level, u, "tgpu_smooth"));
 	if (f == u) return fail(TGPU_ERR_ARG, "tgpu_smooth: f must not alias u");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
+	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
 	return k_smooth(h, level, false, false, f->d, u->d, h->levels[level].Fa, nullptr);
 	API_END
 }
@@ -834,6 +1111,7 @@ extern "C" int tgpu_smooth_jacobi(tgpu_hier *h, int level, const tgpu_vec *f, tg
 	TRY(ensure_work(h, level, true));
 	LevelDev &L = h->levels[level];
 	TRY(k_extract_faces(h, level, u->d, L.Fa));
+	TRY(k_exchange(h, level, L.Fa, nullptr));
 	TRY(k_apply(h, level, 1, u->d, f->d, L.Fa, L.r, nullptr));
 	DISPATCH_DN(h->D, h->N, return launch(h->ctx, jacobi_update_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, u->d, omega));
 	API_END
@@ -843,6 +1121,11 @@ extern "C" int tgpu_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *fine,
 	API_BEGIN
 	TRY(check_level_vec(h, fine_level, fine, "tgpu_restrict"));
 	TRY(check_level_vec(h, fine_level + 1, coarse, "tgpu_restrict"));
+	if (crosses_replication(h, fine_level)) {
+		TRY(k_set(h, coarse->d, coarse->n, 0.0));
+		TRY(k_restrict(h, fine_level, fine->d, coarse->d));
+		return k_allreduce_sum(h, coarse->d, coarse->n);
+	}
 	return k_restrict(h, fine_level, fine->d, coarse->d);
 	API_END
 }
@@ -861,7 +1144,11 @@ extern "C" int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_v
 	TRY(check_level_vec(h, fine_level, u, "tgpu_residual_restrict"));
 	TRY(check_level_vec(h, fine_level + 1, coarse_f, "tgpu_residual_restrict"));
 	TRY(k_extract_faces(h, fine_level, u->d, h->levels[fine_level].Fa));
-	return k_apply(h, fine_level, 2, u->d, f->d, h->levels[fine_level].Fa, nullptr, coarse_f->d);
+	TRY(k_exchange(h, fine_level, h->levels[fine_level].Fa, nullptr));
+	if (crosses_replication(h, fine_level)) TRY(k_set(h, coarse_f->d, coarse_f->n, 0.0));
+	TRY(k_apply(h, fine_level, 2, u->d, f->d, h->levels[fine_level].Fa, nullptr, coarse_f->d));
+	if (crosses_replication(h, fine_level)) TRY(k_allreduce_sum(h, coarse_f->d, coarse_f->n));
+	return TGPU_OK;
 	API_END
 }
 
@@ -882,15 +1169,20 @@ extern "C" int tgpu_cycle_opts_default(TgpuCycleOpts *o)
 static int generic_smooth(tgpu_hier *h, int l, const double *f, double *u)
 {
 	TRY(k_extract_faces(h, l, u, h->levels[l].Fa));
+	TRY(k_exchange(h, l, h->levels[l].Fa, nullptr));
 	return k_smooth(h, l, false, false, f, u, h->levels[l].Fa, nullptr);
 }
 static int generic_prep_coarser(tgpu_hier *h, int l, const double *f, const double *u)
 {
 	LevelDev &L = h->levels[l], &C = h->levels[l + 1];
 	TRY(k_extract_faces(h, l, u, L.Fa));
+	TRY(k_exchange(h, l, L.Fa, nullptr));
 	TRY(k_apply(h, l, 1, u, f, L.Fa, L.r, nullptr)); // r = A u; r = -r + f
 	TRY(k_set(h, C.u, C.ncells, 0.0));               // new_u (zero-initialised Vec)
-	return k_restrict(h, l, L.r, C.f);               // new_f = R r
+	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
+	TRY(k_restrict(h, l, L.r, C.f));                 // new_f = R r
+	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
+	return TGPU_OK;
 }
 static int generic_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u)
 {
@@ -926,6 +1218,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	if (l == last) {
 		for (int i = 0; i < o.coarse_sweeps; i++) {
 			const bool emit = (i + 1 < o.coarse_sweeps);
+			if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt));
 			if (i > 0 && emit) std::swap(Fcur, Falt);
 		}
@@ -933,14 +1226,20 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	}
 	LevelDev &C = h->levels[l + 1];
 	for (int i = 0; i < o.pre_sweeps; i++) {
+		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt));
 		if (i > 0) std::swap(Fcur, Falt);
 	}
+	TRY(k_exchange(h, l, Fcur, nullptr)); // faces of the pre-smoothed u -> neighbours on other GPUs
+	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
 	TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
+	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
+	TRY(k_exchange(h, l, Fcur, C.u)); // same faces + prolonged correction (owned faces add it on the fly)
 	for (int i = 0; i < o.post_sweeps; i++) {
 		const bool emit = (i + 1 < o.post_sweeps) || want_faces;
 		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
+		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr));
 		std::swap(Fcur, Falt);
 	}
@@ -968,7 +1267,7 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 		TRY(need_smoother(h, (int) l));
 		TRY(ensure_work(h, (int) l, true));
 	}
-	if (!o.use_graph || ctx->profiling) return run_cycle(h, o, f, u);
+	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u);
 	for (GraphEntry &g : h->graphs)
 		if (g.f == f && g.u == u && same_opts(g.opts, o)) {
 			CU(cudaGraphLaunch(g.exec, ctx->stream));

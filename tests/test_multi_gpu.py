@@ -1,0 +1,88 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): one process per GPU, patches
+partitioned along the Morton curve, NCCL halo exchange.  The gathered distributed V-cycle / BiCGStab
+results must equal the reference golden vectors and the single-GPU path."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import MESHES, ROOT, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret):
+    sys.path.insert(0, ROOT)
+    import time
+    import pressurepoissonsolver_b200 as pps
+    ctx = pps.Context(rank)
+    if rank == 0:
+        uid = pps.comm_unique_id()
+        with open(idfile + ".tmp", "wb") as fh:
+            fh.write(uid)
+        os.rename(idfile + ".tmp", idfile)
+    else:
+        while not os.path.exists(idfile):
+            time.sleep(0.05)
+        uid = open(idfile, "rb").read()
+    ctx.comm_init(uid, rank, world)
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
+    part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=2)
+    h = pps.Hierarchy.from_partition(ctx, part)
+    pl = part.level(0)
+    nc = n ** D
+    fg = np.asarray(f_global).reshape(-1, nc)
+    f, u, r = h.new_vec(0, fg[pl["owned_global"]]), h.new_vec(0), h.new_vec(0)
+    out = {"owned": pl["owned_global"], "ndist": part.ndist}
+    h.vcycle(f, u)
+    out["vcycle"] = u.download().reshape(-1, nc)
+    out["fnorm"] = f.two_norm()
+    h.apply(0, f, r)
+    out["apply"] = r.download().reshape(-1, nc)
+    x = h.new_vec(0)
+    its, rel = h.bicgstab(f, x, tol=1e-12, max_it=100)
+    out["its"], out["x"] = its, x.download().reshape(-1, nc)
+    ret[rank] = out
+    h.close()
+    ctx.close()
+
+
+def run_distributed(world, mesh_file, D, n, divide, f_global):
+    import tempfile
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    ret = mpc.Manager().dict()
+    with tempfile.TemporaryDirectory() as tmp:
+        idfile = os.path.join(tmp, "nccl_id")
+        procs = [mpc.Process(target=_worker, args=(r, world, idfile, mesh_file, D, n, divide, f_global, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+    nc = n ** D
+    P = sum(len(ret[r]["owned"]) for r in range(world))
+    gather = lambda key: np.concatenate([ret[r][key] for r in range(world)])[np.argsort(np.concatenate([ret[r]["owned"] for r in range(world)]))]  # noqa: E731
+    return ret, gather, P * nc
+
+
+@pytest.mark.parametrize("name", ["3d_2refine_d1_n4", "3d_multi_refine_n4", "2d_multi_refine_8_n4", "3d_2refine_n8"])
+def test_distributed_cycle_matches_reference(name):
+    world = min(_ngpu(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    g = load_golden(name)
+    ret, gather, ncells = run_distributed(world, str(g["mesh"]), int(g["D"]), int(g["n"]), int(g["divide"]), g["rhs_f"])
+    assert ret[0]["ndist"] >= 1
+    assert ncells == g["rhs_f"].size
+    assert rel_l2(gather("vcycle"), g["vcycle"]) < 1e-12
+    assert abs(ret[0]["fnorm"] / np.linalg.norm(g["rhs_f"]) - 1) < 1e-13
+    assert ret[0]["its"] == int(g["bicgstab_info"][0])
+    assert rel_l2(gather("x"), g["bicgstab_u"]) < 1e-10
