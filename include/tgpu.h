@@ -168,6 +168,8 @@ int tgpu_part_level(const tgpu_part *part, int level, TgpuLevelDesc *local_desc,
  * order the two ranks agree on */
 int tgpu_part_peer(const tgpu_part *part, int level, int k, int32_t *peer, int32_t *nsend, const int32_t **send_patch,
                    const int32_t **send_side, int32_t *nrecv, const int32_t **recv_slot, const int32_t **recv_side);
+/* owned patches [0, n_interior) have no off-rank neighbour (their sweep overlaps the halo exchange) */
+int tgpu_part_level_interior(const tgpu_part *part, int level, int32_t *n_interior);
 int tgpu_comm_unique_id(void *id128);                                              /* ncclGetUniqueId (128 bytes) */
 int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nranks);       /* ncclCommInitRank */
 int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part *part, tgpu_hier **h);

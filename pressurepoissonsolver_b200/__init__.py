@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "tgpu_vec_scale_then_add_scaled2", "tgpu_vec_two_norm", "tgpu_vec_inf_norm", "tgpu_vec_dot", "tgpu_apply",
     "tgpu_residual", "tgpu_smooth", "tgpu_smooth_jacobi", "tgpu_restrict", "tgpu_prolong_add",
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
-    "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer",
+    "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
 ]
 
@@ -127,6 +127,7 @@ for _name, _args in {
     "tgpu_part_peer": [_vp, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)),
                        C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)),
                        C.POINTER(C.POINTER(C.c_int32))],
+    "tgpu_part_level_interior": [_vp, C.c_int, C.POINTER(C.c_int32)],
     "tgpu_comm_unique_id": [_vp], "tgpu_comm_init": [_vp, _vp, C.c_int, C.c_int],
     "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
 }.items():
@@ -278,7 +279,9 @@ class Partition:
         check(lib.tgpu_part_level(self._p, l, C.byref(d), C.byref(no), C.byref(nh), C.byref(og), C.byref(hg), C.byref(ho), C.byref(npe)))
         out = _desc_arrays(d, self.D)
         as_np = lambda ptr, n: np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.int32)  # noqa: E731
-        out.update(n_owned=no.value, n_halo=nh.value, owned_global=as_np(og, no.value), halo_global=as_np(hg, nh.value),
+        ni = C.c_int32()
+        check(lib.tgpu_part_level_interior(self._p, l, C.byref(ni)))
+        out.update(n_interior=ni.value, n_owned=no.value, n_halo=nh.value, owned_global=as_np(og, no.value), halo_global=as_np(hg, nh.value),
                    halo_owner=as_np(ho, nh.value), peers=[])
         for k in range(npe.value):
             peer, ns, nr = C.c_int32(), C.c_int32(), C.c_int32()

@@ -408,10 +408,11 @@ template <int D, int N> __device__ __forceinline__ void prefetch_patch_l2(const 
 // ---------------------------------------------------------------------------------------------
 template <int D, int N, bool ZERO_GUESS, bool EMIT, bool PROLONG>
 __global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
-smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ f, double *__restrict__ u,
+smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
               const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
               const double *__restrict__ uc)
 {
+	// works on patches [p0, P) (multi-GPU: interior and boundary patches are separate launches)
 	// Persistent CTAs: each loops over groups of PPB patches (group g = blockIdx.x + k gridDim.x).
 	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
 	// cp.async while the current group is being solved (double buffering).
@@ -423,13 +424,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 	const int t    = threadIdx.x;
 	const int pp   = t / G::M;
 	const int m    = t % G::M;
-	const int nblk = (P + G::PPB - 1) / G::PPB;
+	const int nblk = (P - p0 + G::PPB - 1) / G::PPB;
 
 	Mags<N> mg;
 	mg.load();
 
 	auto prefetch = [&](int g, double *Sdst) {
-		const int pb = g * G::PPB;
+		const int pb = p0 + g * G::PPB;
 #pragma unroll
 		for (int k = 0; k < N; k++) {
 			const int  e  = t + TGPU_THREADS * k;
@@ -445,13 +446,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restric
 
 	for (int it = 0; g < nblk; g += gridDim.x, it++) {
 		double *   Sall  = (it & 1) ? Sbuf1 : Sbuf0;
-		const int  p     = g * G::PPB + pp;
+		const int  p     = p0 + g * G::PPB + pp;
 		const bool valid = p < P;
 		// the other buffer was last read in the previous iteration, before its closing barrier
 		if (g + (int) gridDim.x < nblk) {
 			prefetch(g + gridDim.x, (it & 1) ? Sbuf0 : Sbuf1);
 			if (!ZERO_GUESS) { // pull the faces the next group's gamma needs into L2 one iteration ahead
-				const int pn = (g + gridDim.x) * G::PPB + pp;
+				const int pn = p0 + (g + gridDim.x) * G::PPB + pp;
 				if (pn < P) prefetch_faces_l2<D, N>(meta, pn, m, Fin);
 			}
 		}
@@ -613,7 +614,7 @@ template <int D, int N> __device__ __forceinline__ int gidx(int x, int y, int z)
 
 template <int D, int N, int MODE>
 __global__ void __launch_bounds__(TGPU_THREADS, 2)
-apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ u, const double *__restrict__ f,
+apply_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ u, const double *__restrict__ f,
              const double *__restrict__ F, double *__restrict__ out, double *__restrict__ coarse)
 {
 	// Persistent CTAs over groups of PPB patches; u of the next group streams into the second
@@ -625,11 +626,11 @@ apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict
 	const int  t    = threadIdx.x;
 	const int  pp   = t / G::M;
 	const int  m    = t % G::M;
-	const int  nblk = (P + G::PPB - 1) / G::PPB;
+	const int  nblk = (P - p0 + G::PPB - 1) / G::PPB;
 	const int  x = m % N, y = (D == 2) ? 0 : m / N;
 
 	auto prefetch = [&](int g, double *Udst) {
-		const int pb = g * G::PPB;
+		const int pb = p0 + g * G::PPB;
 #pragma unroll
 		for (int k = 0; k < N; k++) {
 			const int  e  = t + TGPU_THREADS * k;
@@ -646,11 +647,11 @@ apply_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict
 
 	for (int it = 0; g < nblk; g += gridDim.x, it++) {
 		double *   U     = ((it & 1) ? Ubuf1 : Ubuf0) + pp * G::GP;
-		const int  p     = g * G::PPB + pp;
+		const int  p     = p0 + g * G::PPB + pp;
 		const bool valid = p < P;
 		if (g + (int) gridDim.x < nblk) {
 			prefetch(g + gridDim.x, (it & 1) ? Ubuf0 : Ubuf1);
-			const int pn = (g + gridDim.x) * G::PPB + pp;
+			const int pn = p0 + (g + gridDim.x) * G::PPB + pp;
 			if (pn < P) { // pull the next patch's f and faces into L2 now; they are demanded next iteration
 				if (MODE != 0) prefetch_patch_l2<D, N>(f, pn, m);
 				prefetch_faces_l2<D, N>(meta, pn, m, F);

@@ -330,11 +330,13 @@ Partition partitionLevels(const std::vector<HostLevel> &global, int D, int n, in
 	part.ndist = ndist;
 	part.owner.resize(ndist);
 	if (ndist > 0) {
-		// weights: finest-level descendants of every patch of the coarsest distributed level
+		// weights: patches visited per cycle below (and including) each patch of the coarsest distributed
+		// level, summed over ALL distributed levels - a coarse leaf that persists through k levels is
+		// smoothed k times, so it weighs k
 		std::vector<std::vector<int64_t>> w(ndist);
 		w[0].assign(global[0].npatch, 1);
 		for (int l = 0; l + 1 < ndist; l++) {
-			w[l + 1].assign(global[l + 1].npatch, 0);
+			w[l + 1].assign(global[l + 1].npatch, 1);
 			for (int p = 0; p < global[l].npatch; p++) w[l + 1][global[l].parent_idx[p]] += w[l][p];
 		}
 		const int            top = ndist - 1;
@@ -374,6 +376,7 @@ Partition partitionLevels(const std::vector<HostLevel> &global, int D, int n, in
 			PL.distributed = false;
 			PL.local       = GL;
 			PL.n_owned     = GL.npatch;
+			PL.n_interior  = GL.npatch;
 			PL.owned_global.resize(GL.npatch);
 			for (int p = 0; p < GL.npatch; p++) PL.owned_global[p] = p, local_of_global[p] = p;
 			local_of_global_next = local_of_global;
@@ -381,11 +384,23 @@ Partition partitionLevels(const std::vector<HostLevel> &global, int D, int n, in
 		}
 		PL.distributed                 = true;
 		const std::vector<int32_t> &ow = part.owner[l];
-		for (int p = 0; p < GL.npatch; p++)
-			if (ow[p] == rank) {
-				local_of_global[p] = (int32_t) PL.owned_global.size();
-				PL.owned_global.push_back(p);
-			}
+		// owned patches: interior ones (no off-rank neighbour) first, then the boundary ones, so that the
+		// interior sweep can run while the halo exchange is in flight
+		std::vector<int32_t> interior, boundary;
+		for (int p = 0; p < GL.npatch; p++) {
+			if (ow[p] != rank) continue;
+			bool bnd = false;
+			for (int s = 0; s < S && !bnd; s++)
+				for (int q = 0; q < Q; q++) {
+					const int32_t j = GL.nbr_idx[((size_t) p * S + s) * Q + q];
+					if (j >= 0 && ow[j] != rank) bnd = true;
+				}
+			(bnd ? boundary : interior).push_back(p);
+		}
+		PL.n_interior = (int32_t) interior.size();
+		PL.owned_global = interior;
+		PL.owned_global.insert(PL.owned_global.end(), boundary.begin(), boundary.end());
+		for (size_t k = 0; k < PL.owned_global.size(); k++) local_of_global[PL.owned_global[k]] = (int32_t) k;
 		PL.n_owned = (int32_t) PL.owned_global.size();
 		// halo = off-rank neighbours of owned patches, in global order
 		std::vector<char> is_halo(GL.npatch, 0);

@@ -84,6 +84,7 @@ struct PartLevel {
 	bool                      distributed = false;
 	HostLevel                 local;        // remapped tables: npatch = n_owned + n_halo (replicated: the global level)
 	int32_t                   n_owned = 0, n_halo = 0;
+	int32_t                   n_interior = 0; // owned patches [0, n_interior) have no off-rank neighbour
 	std::vector<int32_t>      owned_global; // global patch index of each owned patch
 	std::vector<int32_t>      halo_global, halo_owner;
 	std::vector<PeerExchange> peers;

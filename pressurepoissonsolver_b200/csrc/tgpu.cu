@@ -121,9 +121,10 @@ struct tgpu_ctx {
 	bool         capturing = false;
 	int64_t      captured  = 0;
 	// multi-GPU
-	ncclComm_t comm   = nullptr;
-	int        rank   = 0;
-	int        nranks = 1;
+	ncclComm_t   comm        = nullptr;
+	int          rank        = 0;
+	int          nranks      = 1;
+	cudaStream_t comm_stream = nullptr; // halo exchanges run here, concurrently with interior sweeps
 	// per-launch profiling
 	bool                          profiling = false;
 	const char *                  tag_name  = "kernel";
@@ -167,6 +168,8 @@ struct LevelDev {
 	int        P      = 0; // owned patches (kernel loop bound, vector length)
 	int        slots  = 0; // owned + halo face slots
 	bool       distributed = false;
+	int        n_interior  = 0;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; // fork/join points of the overlapped exchange
 	std::vector<PeerDev> peers;
 	int32_t *  send_patch = nullptr, *send_side = nullptr, *recv_slot = nullptr, *recv_side = nullptr;
 	double *   sendbuf = nullptr, *recvbuf = nullptr;
@@ -230,6 +233,25 @@ static int launch(tgpu_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block
 	else ctx->launches++;
 	return TGPU_OK;
 }
+// brackets non-kernel stream work (NCCL calls) with profiling events
+struct ProfSpan {
+	tgpu_ctx *ctx;
+	ProfSpan(tgpu_ctx *c, const char *name, int level) : ctx(c)
+	{
+		if (!c->profiling) return;
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0);
+		cudaEventCreate(&e1);
+		cudaEventRecord(e0, c->stream);
+		c->prof_events.push_back(e0);
+		c->prof_events.push_back(e1);
+		c->prof_entries.push_back(TgpuProfileEntry{name, level, 0.f});
+	}
+	~ProfSpan()
+	{
+		if (ctx->profiling) cudaEventRecord(ctx->prof_events.back(), ctx->stream);
+	}
+};
 static int grid_for(tgpu_ctx *ctx, size_t n, int block = 256, int per_sm = 8)
 {
 	size_t want = (n + block - 1) / block;
@@ -342,6 +364,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+	if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
 	cudaFree(ctx->d_partial);
 	cudaFree(ctx->d_result);
 	cudaFreeHost(ctx->h_result);
@@ -650,6 +673,12 @@ extern "C" int tgpu_part_level(const tgpu_part *p, int level, TgpuLevelDesc *des
 	if (npeers) *npeers = (int32_t) L.peers.size();
 	return TGPU_OK;
 }
+extern "C" int tgpu_part_level_interior(const tgpu_part *p, int level, int32_t *n_interior)
+{
+	if (!p || !n_interior || level < 0 || level >= (int) p->part.levels.size()) return fail(TGPU_ERR_ARG, "bad argument");
+	*n_interior = p->part.levels[level].n_interior;
+	return TGPU_OK;
+}
 extern "C" int tgpu_part_peer(const tgpu_part *p, int level, int k, int32_t *peer, int32_t *nsend, const int32_t **send_patch,
                               const int32_t **send_side, int32_t *nrecv, const int32_t **recv_slot, const int32_t **recv_side)
 {
@@ -688,6 +717,7 @@ extern "C" int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nr
 	ncclUniqueId id;
 	memcpy(&id, id128, sizeof(id));
 	NC(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
+	if (!ctx->comm_stream) CU(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
 	ctx->rank   = rank;
 	ctx->nranks = nranks;
 	return TGPU_OK;
@@ -710,6 +740,8 @@ extern "C" int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part 
 		const PartLevel &PL = pt.levels[l];
 		LevelDev &       L  = h->levels[l];
 		L.distributed       = PL.distributed;
+		L.n_interior        = PL.n_interior;
+		for (int e = 0; e < 4; e++) CU(cudaEventCreateWithFlags(&L.ev[e], cudaEventDisableTiming));
 		std::vector<int32_t> sp, ss, rs, rsd;
 		for (const PeerExchange &x : PL.peers) {
 			PeerDev pd;
@@ -763,6 +795,8 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.spacing);
 		cudaFree(L.Fa);
 		cudaFree(L.Fb);
+		for (int e = 0; e < 4; e++)
+			if (L.ev[e]) cudaEventDestroy(L.ev[e]);
 		cudaFree(L.send_patch);
 		cudaFree(L.send_side);
 		cudaFree(L.recv_slot);
@@ -959,41 +993,46 @@ static int k_extract_faces(tgpu_hier *h, int l, const double *u, double *F)
 	DISPATCH_DN(h->D, h->N, return launch(h->ctx, extract_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, L.P, u, F));
 }
 // mode 0: out = A u; 1: out = f - A u; 2: coarse = R (f - A u).  F must hold the faces of u.
-static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double *f, const double *F, double *out, double *coarse)
+static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double *f, const double *F, double *out, double *coarse,
+                   int p0 = 0, int p1 = -1)
 {
 	LevelDev &L = h->levels[l];
+	if (p1 < 0) p1 = L.P;
+	if (p1 <= p0) return TGPU_OK;
 	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : "residual_restrict"), l);
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
-		const int nblk = (L.P + G::PPB - 1) / G::PPB;
+		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
 		const int grid = std::min(nblk, h->ctx->sm_count * 2);
 		const size_t sm = apply_smem_bytes<DD, NN>();
-		if (mode == 0) return launch(h->ctx, apply_kernel<DD, NN, 0>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
-		if (mode == 1) return launch(h->ctx, apply_kernel<DD, NN, 1>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
-		return launch(h->ctx, apply_kernel<DD, NN, 2>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, L.P, u, f, F, out, coarse);
+		if (mode == 0) return launch(h->ctx, apply_kernel<DD, NN, 0>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse);
+		if (mode == 1) return launch(h->ctx, apply_kernel<DD, NN, 1>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse);
+		return launch(h->ctx, apply_kernel<DD, NN, 2>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse);
 	});
 }
 // zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout;
 // uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation)
 static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout,
-                    const double *uc = nullptr)
+                    const double *uc = nullptr, int p0 = 0, int p1 = -1)
 {
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
+	if (p1 < 0) p1 = L.P;
+	if (p1 <= p0) return TGPU_OK;
 	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : (uc ? "smooth_prolong" : "smooth"), l);
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
-		const int nblk = (L.P + G::PPB - 1) / G::PPB;
+		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
 		const dim3 grid(std::min(nblk, h->ctx->sm_count * smooth_min_blocks<NN>())), block(TGPU_THREADS);
 		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = h->eig;
-		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
-		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
-		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
-		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
-		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
-		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, L.P, f, u, Fin, Fout, eig, uc);
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
 	});
 }
 static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)
@@ -1036,12 +1075,15 @@ static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
 			else TRY(launch(ctx, pack_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const double *) F, uc, L.sendbuf));
 		});
 	}
+	{
+	ProfSpan span(ctx, "nccl_sendrecv", l);
 	NC(g_nccl.GroupStart());
 	for (const PeerDev &pd : L.peers) {
 		if (pd.send_n) NC(g_nccl.Send(L.sendbuf + pd.send_off * M, pd.send_n * M, ncclDouble, pd.peer, ctx->comm, ctx->stream));
 		if (pd.recv_n) NC(g_nccl.Recv(L.recvbuf + pd.recv_off * M, pd.recv_n * M, ncclDouble, pd.peer, ctx->comm, ctx->stream));
 	}
 	NC(g_nccl.GroupEnd());
+	}
 	if (L.nrecv) {
 		DISPATCH_DN(h->D, h->N, TRY(launch(ctx, unpack_faces_kernel<DD, NN>, dim3(grid_for(ctx, L.nrecv * M)), dim3(256), 0, (int) L.nrecv, (const int32_t *) L.recv_slot, (const int32_t *) L.recv_side, (const double *) L.recvbuf, F)));
 	}
@@ -1052,6 +1094,7 @@ static int k_allreduce_sum(tgpu_hier *h, double *v, size_t n)
 {
 	tgpu_ctx *ctx = h->ctx;
 	if (ctx->nranks == 1) return TGPU_OK;
+	ProfSpan span(ctx, "nccl_allreduce", -1);
 	NC(g_nccl.AllReduce(v, v, n, ncclDouble, ncclSum, ctx->comm, ctx->stream));
 	return TGPU_OK;
 }
@@ -1205,6 +1248,21 @@ static int generic_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const doub
 	}
 	return TGPU_OK;
 }
+// fork: the comm stream waits for everything queued on the main stream so far, runs the exchange, and
+// records `done`; the main stream carries on with patches that need no halo data and waits on `done` later.
+static int exchange_async(tgpu_hier *h, int l, double *F, const double *uc, cudaEvent_t fork, cudaEvent_t done)
+{
+	tgpu_ctx *   ctx  = h->ctx;
+	cudaStream_t main = ctx->stream;
+	CU(cudaEventRecord(fork, main));
+	CU(cudaStreamWaitEvent(ctx->comm_stream, fork, 0));
+	ctx->stream = ctx->comm_stream;
+	int rc      = k_exchange(h, l, F, uc);
+	ctx->stream = main;
+	TRY(rc);
+	CU(cudaEventRecord(done, ctx->comm_stream));
+	return TGPU_OK;
+}
 // Fused schedule for V cycles with >= 1 pre and post sweep.  Per level visit:
 //   smooth(zero guess) -> u, faces | residual+restrict -> f_coarse | (coarser) |
 //   smooth(f, faces + P u_coarse on the boundary cells) -> u
@@ -1230,16 +1288,30 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt));
 		if (i > 0) std::swap(Fcur, Falt);
 	}
-	TRY(k_exchange(h, l, Fcur, nullptr)); // faces of the pre-smoothed u -> neighbours on other GPUs
+	const bool overlap = L.distributed && h->ctx->nranks > 1 && (L.nsend || L.nrecv);
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
-	TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
+	if (overlap) {
+		// faces of the pre-smoothed u travel on the comm stream while the interior patches are swept
+		TRY(exchange_async(h, l, Fcur, nullptr, L.ev[0], L.ev[1]));
+		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, 0, L.n_interior));
+		CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[1], 0));
+		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, L.n_interior, L.P));
+	} else {
+		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
+	}
 	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
-	TRY(k_exchange(h, l, Fcur, C.u)); // same faces + prolonged correction (owned faces add it on the fly)
+	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
+	if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
 	for (int i = 0; i < o.post_sweeps; i++) {
 		const bool emit = (i + 1 < o.post_sweeps) || want_faces;
 		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
+		if (i == 0 && overlap) {
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior));
+			CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[3], 0));
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, L.n_interior, L.P));
+		} else
 		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr));
 		std::swap(Fcur, Falt);
 	}
