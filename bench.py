@@ -28,6 +28,7 @@ CONFIGS = {
     "C": (3, "2refine.bin", 3, 16, "config C: apps/3d/steady GMG, refined octree 2refine.bin --divide 3, 7680 patches of 16^3 (31,457,280 cells), 6 levels, trig RHS"),
     "B4": (3, "4uni.bin", 1, 16, "weak-scaling point for 4 GPUs: 4uni.bin --divide 1 with the lower half (z < 0.5) refined once more, 18,432 patches of 16^3 (75,497,472 cells), 6 levels, trig RHS"),
     "B8": (3, "4uni.bin", 2, 16, "weak-scaling point for 8 GPUs: uniform octree 4uni.bin --divide 2, 32,768 patches of 16^3 (134,217,728 cells), 6 levels, trig RHS"),
+    "D16": (3, "4uni.bin", 3, 16, "config D mesh with 16^3 patches: uniform octree 4uni.bin --divide 3, 262,144 patches of 16^3 (1,073,741,824 cells), 7 levels, trig RHS"),
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
@@ -141,9 +142,9 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
         if args.config == "B":
-            # N > 1: the 8x larger uniform octree (a uniform octree only grows in steps of 8): 134 M cells shared by
-            # the N GPUs = strong scaling among N = 2, 4, 8; at N = 8 each GPU holds exactly the N = 1 workload
-            cfg = "B8"
+            # N > 1: the >= 1 B-cell 3D uniform octree of BASELINE config D (with 16^3 patches), shared by the N GPUs:
+            # strong scaling among N = 2, 4, 8 (N = 1 stays on config B as the contract asks)
+            cfg = os.environ.get("BENCH_MULTI_CONFIG", "D16")
 
     D, mesh_file, divide, n, desc = CONFIGS[cfg]
     mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
@@ -226,11 +227,15 @@ def main():
     e2e_ms = ctx.timer_stop() / e2e_steps
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     e2e_ms = max(e2e_ms, e2e_wall_ms)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
     assert np.isfinite(up.array).all()
 
     line = {
         "metric": "fp64 GMG V-cycle DOF/s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world in (1, 8) else "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": desc, "cycle": "V(1,1), 1 coarse sweep, all levels down to the root patch", "cells": cells,
                    "levels": level_cells, "l2": "inputs larger than L2 (f and u are %.0f MB each, L2 is 126 MB)" % (cells * 8 / 1e6),
@@ -241,7 +246,7 @@ def main():
                      "algorithmic_bytes_per_launch": SMOOTH_BYTES_PER_CELL * cells, "share_of_step": smooth_share,
                      "vcycle_algorithmic_gbs": cycle_gbs, "vcycle_frac": cycle_gbs / peak,
                      "vcycle_bytes_per_dof": cycle_bytes / cells},
-        "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": cells * 8, "d2h_bytes_per_step": cells * 8,
+        "e2e": {"value": total_cells / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": cells * 8, "d2h_bytes_per_step": cells * 8,
                 "ms_per_step": e2e_ms, "api": "tgpu_vcycle_host (pinned host f -> device, V-cycle, u -> pinned host)"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
