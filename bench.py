@@ -206,7 +206,7 @@ def main():
         a[1] += kms
     prof_total = sum(v[1] for v in agg.values())
     smooth_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name in ("smooth", "smooth_prolong")]
-    smooth0_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name == "smooth_zero_guess"]
+    smooth0_ms = [v[1] / v[0] for (name, lvl), v in agg.items() if lvl == 0 and name in ("smooth_zero_guess", "smooth_zero_guess_faces")]
     dom_ms = (smooth_ms[0] + smooth0_ms[0]) / 2 if smooth_ms and smooth0_ms else None
     peak, peak_src = measured_peaks()
     achieved = SMOOTH_BYTES_PER_CELL * cells / (dom_ms * 1e-3) / 1e9 if dom_ms else None

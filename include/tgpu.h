@@ -58,7 +58,8 @@ typedef struct TgpuCycleOpts {
 	int32_t mid_sweeps;    /* default 1 (W cycle) */
 	int32_t coarse_sweeps; /* default 1 */
 	int32_t cycle_type;    /* 0 = V, 1 = W */
-	int32_t fused;         /* 1 (default) = fused kernel schedule, 0 = API-granular sequence as GMG/Cycle.h */
+	int32_t fused;         /* 1 (default) = fused kernel schedule (face-only residual), 2 = fused schedule with the residual
+	                          evaluated from u and f, 0 = API-granular sequence as GMG/Cycle.h */
 	int32_t use_graph;     /* 1 (default) = replay the cycle as a CUDA graph */
 } TgpuCycleOpts;
 
@@ -106,6 +107,9 @@ int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLe
 int tgpu_hierarchy_destroy(tgpu_hier *h);
 int tgpu_hierarchy_info(const tgpu_hier *h, int *D, int *n, int *nlevels);
 int tgpu_level_npatch(const tgpu_hier *h, int level, int64_t *npatch, int64_t *ncells);
+/* test hook: on != 0 routes every smoother launch through the size-generic kernel even where a
+ * specialised one exists (D = 3, n = 16), so that the two can be compared */
+int tgpu_hierarchy_force_generic_kernels(tgpu_hier *h, int on);
 
 /* ---- vectors ---- */
 int tgpu_vec_create(tgpu_hier *h, int level, tgpu_vec **v); /* zero-initialised like a new PETSc Vec */

@@ -76,6 +76,7 @@ ABI_SYMBOLS = [
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
     "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
+    "tgpu_hierarchy_force_generic_kernels",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -130,6 +131,7 @@ for _name, _args in {
     "tgpu_part_level_interior": [_vp, C.c_int, C.POINTER(C.c_int32)],
     "tgpu_comm_unique_id": [_vp], "tgpu_comm_init": [_vp, _vp, C.c_int, C.c_int],
     "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
+    "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int],
 }.items():
     getattr(lib, _name).argtypes = _args
     getattr(lib, _name).restype = C.c_int
@@ -396,6 +398,9 @@ class Hierarchy:
         self._p = _vp()
         check(lib.tgpu_hierarchy_create_distributed(ctx._p, part._p, C.byref(self._p)))
         return self
+
+    def force_generic_kernels(self, on=True):
+        check(lib.tgpu_hierarchy_force_generic_kernels(self._p, 1 if on else 0))
 
     def npatch(self, level):
         a, b = C.c_int64(), C.c_int64()

@@ -264,15 +264,22 @@ template <int D, int N> __device__ __forceinline__ int parent_cell(int orth, con
 // coarse vector attached (post-smoothing right after the coarse-grid correction) the piecewise
 // constant prolongation of the correction, DrctIntp.h:92-111, is added on the fly, so the
 // prolonged fine vector is never materialised: F holds the faces of the pre-smoothed u.
-template <int D, int N, bool PROLONG> struct FaceVals {
+enum { FV_PLAIN = 0, FV_PROLONG = 1, FV_DIFF = 2, FV_NEG = 3 };
+// FV_DIFF: F2 - F (old minus new boundary values) and FV_NEG: -F; gamma is linear in the boundary
+// values, so these give gamma(u_old) - gamma(u_new) directly (face-supported residual, see
+// face_residual_restrict_kernel).
+template <int D, int N, int MODE> struct FaceVals {
 	using G = Geo<D, N>;
 	const double *__restrict__ F;
-	const double *__restrict__ uc;
+	const double *__restrict__ uc; // FV_PROLONG: coarse vector; FV_DIFF: the old face buffer F2
 	const PatchMeta *__restrict__ meta;
 	__device__ __forceinline__ double get(int q, int par, int orth, int s, int idx) const
 	{
-		double v = __ldg(F + ((size_t) q * G::S + s) * G::M + idx);
-		if (PROLONG && par >= 0) { // par < 0: halo slot whose face already arrived with the correction added
+		const size_t o = ((size_t) q * G::S + s) * G::M + idx;
+		double       v = __ldg(F + o);
+		if (MODE == FV_NEG) v = -v;
+		if (MODE == FV_DIFF) v = __ldg(uc + o) - v;
+		if (MODE == FV_PROLONG && par >= 0) { // par < 0: halo slot whose face already arrived with the correction added
 			int c[3];
 			face_cell<D, N>(s, idx, c);
 			v += __ldg(uc + (size_t) par * G::NC + parent_cell<D, N>(orth, c));
@@ -283,7 +290,7 @@ template <int D, int N, bool PROLONG> struct FaceVals {
 	__device__ __forceinline__ double get(int q, int s, int idx) const
 	{
 		int par = 0, orth = -1;
-		if (PROLONG) {
+		if (MODE == FV_PROLONG) {
 			par  = meta[q].parent_idx;
 			orth = meta[q].orth_on_parent;
 		}
@@ -296,8 +303,8 @@ template <int D, int N, bool PROLONG> struct FaceVals {
 // Weights: SURVEY App. A.2 (TriLinInterp.cpp:60-172, BilinearInterpolator.cpp:61-117);
 // which contributions meet on an interface: SchurInfo.h:141-150,253-259,363-370.
 // ---------------------------------------------------------------------------------------------
-template <int D, int N, bool PROLONG>
-__device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s, int m, const FaceVals<D, N, PROLONG> &fv)
+template <int D, int N, int MODE>
+__device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s, int m, const FaceVals<D, N, MODE> &fv)
 {
 	const int    po = pm.parent_idx, oo = pm.orth_on_parent;
 	const double a  = fv.get(p, po, oo, s, m);
@@ -345,8 +352,8 @@ __device__ __forceinline__ double iface_gamma(const PatchMeta &pm, int p, int s,
 // are issued back to back without control flow in between, so a patch costs two dependent memory
 // round trips (neighbour table, faces) instead of one per side; only refinement-boundary sides take
 // the slow path through iface_gamma.  a[s] returns the patch's own boundary value.
-template <int D, int N, bool PROLONG>
-__device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int m, const FaceVals<D, N, PROLONG> &fv,
+template <int D, int N, int MODE>
+__device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int m, const FaceVals<D, N, MODE> &fv,
                                                 int (&ty)[2 * D], double (&a)[2 * D], double (&gam)[2 * D])
 {
 	using G = Geo<D, N>;
@@ -367,7 +374,7 @@ __device__ __forceinline__ void gamma_all_sides(const PatchMeta &pm, int p, int 
 #pragma unroll
 	for (int s = 0; s < G::S; s++) {
 		gam[s] = 0.5 * a[s] + 0.5 * b[s];
-		if (ty[s] > NBR_NORMAL) gam[s] = iface_gamma<D, N, PROLONG>(pm, p, s, m, fv);
+		if (ty[s] > NBR_NORMAL) gam[s] = iface_gamma<D, N, MODE>(pm, p, s, m, fv);
 	}
 }
 
@@ -470,8 +477,8 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				// entry m of every side is both produced and consumed by thread m: no staging needed
 				int    ty[G::S];
 				double own[G::S], gm[G::S];
-				const FaceVals<D, N, PROLONG> fvals{Fin, uc, meta};
-				gamma_all_sides<D, N, PROLONG>(pm, p, m, fvals, ty, own, gm);
+				const FaceVals<D, N, PROLONG ? FV_PROLONG : FV_PLAIN> fvals{Fin, uc, meta};
+				gamma_all_sides(pm, p, m, fvals, ty, own, gm);
 #pragma unroll
 				for (int s = 0; s < G::S; s++) {
 					ntype[s] = (int8_t) ty[s];
@@ -676,8 +683,8 @@ apply_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__
 			parent              = pm.parent_idx;
 			int    ty[G::S];
 			double own[G::S], gm[G::S];
-			const FaceVals<D, N, false> fvals{F, nullptr, meta};
-			gamma_all_sides<D, N, false>(pm, p, m, fvals, ty, own, gm);
+			const FaceVals<D, N, FV_PLAIN> fvals{F, nullptr, meta};
+			gamma_all_sides(pm, p, m, fvals, ty, own, gm);
 #pragma unroll
 			for (int s = 0; s < G::S; s++) {
 				double gh;
@@ -750,6 +757,101 @@ apply_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__
 	cp_async_wait<0>();
 }
 template <int D, int N> constexpr size_t apply_smem_bytes() { return sizeof(double) * (size_t) (2 * Geo<D, N>::PPB * Geo<D, N>::GP); }
+
+// ---------------------------------------------------------------------------------------------
+// Residual + restriction right after a block-Jacobi sweep, from face data alone.
+// The sweep solves A_p u_new = f - (2/h^2) E^T gamma(u_old) exactly on every patch
+// (SchurHelper.h:319-331) and the composite operator is (A u)_p = A_p u_p + (2/h^2) E^T gamma(u)
+// (StarPatchOp.h:46-64 with the interface values of SURVEY App. A.2), hence
+//     r = f - A u_new = (2/h^2) E^T (gamma(u_old) - gamma(u_new)):
+// zero away from the patch boundary cells and a function of the boundary-cell slices only.  The
+// kernel evaluates it from the face buffers (DIFF = false: u_old = 0, first sweep of a cycle) and
+// applies AvgRstr (GMG/AvgRstr.h:88-107) on the fly, coarse = R r.  Neither u nor f is read and no
+// fine residual is written; the only difference to GMG/Cycle.h:59-66 is the rounding noise of the patch
+// solve (~1e-16 relative) that the reference's r carries in the patch interiors.
+// ---------------------------------------------------------------------------------------------
+template <int D, int N, bool DIFF>
+__global__ void __launch_bounds__(TGPU_THREADS)
+face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
+                              const double *__restrict__ Fold, double *__restrict__ coarse)
+{
+	using G         = Geo<D, N>;
+	constexpr int H = N / 2;
+	__shared__ double R[G::PPB][G::S][G::M];
+	const int t = threadIdx.x, pp = t / G::M, m = t % G::M;
+	const int nblk = (P - p0 + G::PPB - 1) / G::PPB;
+	for (int g = blockIdx.x; g < nblk; g += gridDim.x) {
+		const int  p     = p0 + g * G::PPB + pp;
+		const bool valid = p < P;
+		int        orth = -1, parent = 0;
+		if (valid) {
+			const PatchMeta &pm = meta[p];
+			orth                = pm.orth_on_parent;
+			parent              = pm.parent_idx;
+			const double cfac   = 2.0 * pm.inv_h2;
+			int          ty[G::S];
+			double       own[G::S], gm[G::S];
+			const FaceVals<D, N, DIFF ? FV_DIFF : FV_NEG> fv{Fnew, Fold, meta};
+			gamma_all_sides(pm, p, m, fv, ty, own, gm);
+#pragma unroll
+			for (int s = 0; s < G::S; s++) R[pp][s][m] = (ty[s] == NBR_NONE) ? 0.0 : cfac * gm[s];
+		}
+		__syncthreads();
+		if (valid) {
+			double *dst                = coarse + (size_t) parent * G::NC;
+			const double(*Rp)[G::M]    = R[pp];
+			if (orth < 0) { // patch present on both levels: coarse = r (dense, zero in the interior)
+				const int x = m % N, y = (D == 2) ? 0 : m / N;
+#pragma unroll 4
+				for (int k = 0; k < N; k++) {
+					double v = 0.0;
+					if (D == 2) {
+						if (x == 0) v += Rp[0][k];
+						if (x == N - 1) v += Rp[1][k];
+						if (k == 0) v += Rp[2][x];
+						if (k == N - 1) v += Rp[3][x];
+					} else {
+						if (x == 0) v += Rp[0][y + N * k];
+						if (x == N - 1) v += Rp[1][y + N * k];
+						if (y == 0) v += Rp[2][x + N * k];
+						if (y == N - 1) v += Rp[3][x + N * k];
+						if (k == 0) v += Rp[4][m];
+						if (k == N - 1) v += Rp[5][m];
+					}
+					dst[k * G::M + m] = v;
+				}
+			} else {
+				const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
+				constexpr int CC = G::NC >> D; // coarse cells under this fine patch
+				for (int c = m; c < CC; c += G::M) {
+					const int X = c % H, Y = (c / H) % H, Z = (D == 2) ? 0 : c / (H * H);
+					double    v = 0.0;
+					if (D == 2) {
+						auto blk = [&](int s, int I) { return (Rp[s][2 * I] + Rp[s][2 * I + 1]) / 4.0; };
+						if (X == 0) v += blk(0, Y);
+						if (X == H - 1) v += blk(1, Y);
+						if (Y == 0) v += blk(2, X);
+						if (Y == H - 1) v += blk(3, X);
+						dst[(Y + oy) * N + (X + ox)] = v;
+					} else {
+						auto blk = [&](int s, int I, int J) {
+							const double *q = &Rp[s][2 * I + N * 2 * J];
+							return ((q[0] + q[1]) + (q[N] + q[N + 1])) / 8.0;
+						};
+						if (X == 0) v += blk(0, Y, Z);
+						if (X == H - 1) v += blk(1, Y, Z);
+						if (Y == 0) v += blk(2, X, Z);
+						if (Y == H - 1) v += blk(3, X, Z);
+						if (Z == 0) v += blk(4, X, Y);
+						if (Z == H - 1) v += blk(5, X, Y);
+						dst[((Z + oz) * N + (Y + oy)) * N + (X + ox)] = v;
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
 
 // ---------------------------------------------------------------------------------------------
 // face buffer helpers
@@ -1006,3 +1108,4 @@ __global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, cons
 	}
 }
 } // namespace tgpu
+#include "smooth3d16.cuh"

@@ -199,6 +199,7 @@ struct tgpu_hier {
 	std::vector<GraphEntry> graphs;
 	std::vector<tgpu_vec *> krylov_ws;
 	tgpu_vec *            host_f = nullptr, *host_u = nullptr;
+	bool                  generic_kernels = false; // test hook: force the size-generic smoother
 };
 
 struct tgpu_vec {
@@ -276,6 +277,24 @@ static bool supported_dn(int D, int N)
 	return (D == 2 && (N == 4 || N == 8 || N == 16 || N == 32)) || (D == 3 && (N == 4 || N == 8 || N == 16));
 }
 
+template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d16()
+{
+	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes()));
+	return TGPU_OK;
+}
+static int set_smem_attrs_3d16()
+{
+	TRY((set_smem_attr_3d16<true, true, false, true>()));
+	TRY((set_smem_attr_3d16<true, false, false, true>()));
+	TRY((set_smem_attr_3d16<true, true, false, false>()));
+	TRY((set_smem_attr_3d16<false, true, false, true>()));
+	TRY((set_smem_attr_3d16<false, false, false, true>()));
+	TRY((set_smem_attr_3d16<false, true, false, false>()));
+	TRY((set_smem_attr_3d16<false, true, true, true>()));
+	TRY((set_smem_attr_3d16<false, false, true, true>()));
+	TRY((set_smem_attr_3d16<false, true, true, false>()));
+	return TGPU_OK;
+}
 template <int D, int N> static int set_smem_attrs()
 {
 	const int sb = (int) smooth_smem_bytes<D, N, true>();
@@ -285,6 +304,7 @@ template <int D, int N> static int set_smem_attrs()
 	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
 	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
 	CU(cudaFuncSetAttribute(smooth_kernel<D, N, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+	if (D == 3 && N == 16) TRY(set_smem_attrs_3d16());
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
@@ -819,6 +839,13 @@ extern "C" int tgpu_hierarchy_info(const tgpu_hier *h, int *D, int *n, int *nlev
 	if (nlevels) *nlevels = (int) h->levels.size();
 	return TGPU_OK;
 }
+extern "C" int tgpu_hierarchy_force_generic_kernels(tgpu_hier *h, int on)
+{
+	if (!h) return fail(TGPU_ERR_ARG, "null argument");
+	h->generic_kernels = on != 0;
+	free_graphs(h);
+	return TGPU_OK;
+}
 extern "C" int tgpu_level_npatch(const tgpu_hier *h, int level, int64_t *npatch, int64_t *ncells)
 {
 	if (!h || level < 0 || level >= (int) h->levels.size()) return fail(TGPU_ERR_ARG, "bad level");
@@ -1011,15 +1038,42 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 	});
 }
 // zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout;
-// uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation)
+// uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation);
+// write_u = false (needs emit): only the faces of the new u are wanted (the generic kernel still writes u)
+template <bool Z, bool E, bool PR, bool W>
+static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
+                             const double *uc)
+{
+	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(TGPU_THREADS);
+	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
+	              Fout, (const double *) h->eig, uc);
+}
 static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout,
-                    const double *uc = nullptr, int p0 = 0, int p1 = -1)
+                    const double *uc = nullptr, int p0 = 0, int p1 = -1, bool write_u = true)
 {
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return TGPU_OK;
-	Tag tg(h->ctx, zero_guess ? "smooth_zero_guess" : (uc ? "smooth_prolong" : "smooth"), l);
+	if (!emit) write_u = true;
+	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
+	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
+	       l);
+	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
+		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+		switch (key) {
+		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 8 | 1: return launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 8 | 4: return launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 4 | 1: return launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 1: return launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 4: return launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 4 | 2 | 1: return launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 2 | 1: return launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
+		}
+	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
@@ -1033,6 +1087,22 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
 		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
 		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+	});
+}
+// coarse = R (f - A u) for a u that a block-Jacobi sweep has just produced: needs only the faces of the new
+// (Fnew) and, unless the sweep started from zero (Fold == nullptr), the previous (Fold) iterate
+static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, const double *Fold, double *coarse, int p0 = 0, int p1 = -1)
+{
+	LevelDev &L = h->levels[l];
+	if (p1 < 0) p1 = L.P;
+	if (p1 <= p0) return TGPU_OK;
+	Tag tg(h->ctx, "face_residual_restrict", l);
+	DISPATCH_DN(h->D, h->N, {
+		using G        = Geo<DD, NN>;
+		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
+		const dim3 grid(std::min(nblk, h->ctx->sm_count * 8)), block(TGPU_THREADS);
+		if (Fold) return launch(h->ctx, face_residual_restrict_kernel<DD, NN, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		return launch(h->ctx, face_residual_restrict_kernel<DD, NN, false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
 	});
 }
 static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)
@@ -1264,10 +1334,14 @@ static int exchange_async(tgpu_hier *h, int l, double *F, const double *uc, cuda
 	return TGPU_OK;
 }
 // Fused schedule for V cycles with >= 1 pre and post sweep.  Per level visit:
-//   smooth(zero guess) -> u, faces | residual+restrict -> f_coarse | (coarser) |
+//   smooth(zero guess) -> faces | residual+restrict from the faces -> f_coarse | (coarser) |
 //   smooth(f, faces + P u_coarse on the boundary cells) -> u
-// Identical arithmetic to the generic schedule except that dead stores (the interior of the
-// prolonged u, the fine residual vector, the zero fill of u) are never materialised.
+// A block-Jacobi sweep depends on the previous iterate only through its boundary-cell slices
+// (SchurHelper.h:319-331), and right after a sweep the residual is (2/h^2) E^T (gamma(u_old) - gamma(u_new))
+// (see face_residual_restrict_kernel).  So, compared with the generic schedule, the dead stores are never
+// materialised: the zero fill of u, the pre-smoothed u itself, the fine residual vector and the interior
+// of the prolonged u; only the last sweep of a level visit writes u.  opts.fused = 2 keeps the PR-1 form
+// of the middle step (residual evaluated from u and f by apply_kernel<2>) for cross-checking.
 static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces)
 {
 	const int last = (int) h->levels.size() - 1;
@@ -1277,45 +1351,52 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		for (int i = 0; i < o.coarse_sweeps; i++) {
 			const bool emit = (i + 1 < o.coarse_sweeps);
 			if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
-			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt));
+			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !emit));
 			if (i > 0 && emit) std::swap(Fcur, Falt);
 		}
 		return TGPU_OK;
 	}
-	LevelDev &C = h->levels[l + 1];
+	const bool from_faces = (o.fused != 2);
+	LevelDev & C          = h->levels[l + 1];
 	for (int i = 0; i < o.pre_sweeps; i++) {
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
-		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt));
+		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !from_faces));
 		if (i > 0) std::swap(Fcur, Falt);
 	}
-	const bool overlap = L.distributed && h->ctx->nranks > 1 && (L.nsend || L.nrecv);
+	// Fcur: faces of the pre-smoothed u; Falt: faces of the iterate before the last pre-sweep (if pre_sweeps > 1)
+	const double *Fold    = o.pre_sweeps > 1 ? Falt : nullptr;
+	const bool    overlap = L.distributed && h->ctx->nranks > 1 && (L.nsend || L.nrecv);
+	auto residual_restrict = [&](int p0, int p1) {
+		if (from_faces) return k_face_residual_restrict(h, l, Fcur, Fold, C.f, p0, p1);
+		return k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, p0, p1);
+	};
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
 	if (overlap) {
 		// faces of the pre-smoothed u travel on the comm stream while the interior patches are swept
 		TRY(exchange_async(h, l, Fcur, nullptr, L.ev[0], L.ev[1]));
-		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, 0, L.n_interior));
+		TRY(residual_restrict(0, L.n_interior));
 		CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[1], 0));
-		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, L.n_interior, L.P));
+		TRY(residual_restrict(L.n_interior, L.P));
 	} else {
-		TRY(k_apply(h, l, 2, u, f, Fcur, nullptr, C.f));
+		TRY(residual_restrict(0, L.P));
 	}
 	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
 	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
 	if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
 	for (int i = 0; i < o.post_sweeps; i++) {
-		const bool emit = (i + 1 < o.post_sweeps) || want_faces;
+		const bool lastsweep = (i + 1 == o.post_sweeps);
+		const bool emit      = !lastsweep || want_faces;
 		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		if (i == 0 && overlap) {
-			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior));
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior, lastsweep));
 			CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[3], 0));
-			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, L.n_interior, L.P));
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, L.n_interior, L.P, lastsweep));
 		} else
-		TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr));
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr, 0, -1, lastsweep));
 		std::swap(Fcur, Falt);
 	}
-	(void) want_faces;
 	return TGPU_OK;
 }
 static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u)

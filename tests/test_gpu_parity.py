@@ -70,7 +70,7 @@ def test_level_operators_vs_reference(gcase):
         assert rel_l2(u.download(), g["L%d_smooth" % l]) < TOL
 
 
-@pytest.mark.parametrize("fused,graph", [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize("fused,graph", [(1, 1), (1, 0), (2, 1), (2, 0), (0, 1), (0, 0)])
 def test_vcycle_vs_reference(gcase, fused, graph):
     g, h = gcase
     f = h.new_vec(0, g["rhs_f"])
@@ -139,12 +139,47 @@ def test_vs_oracle_seeded(ctx, mesh_file, D, n, divide):
     h.vcycle(f, u)
     assert rel_l2(u.download(), go.vcycle(levels, fn)) < TOL
     for opts in (dict(pre_sweeps=2, post_sweeps=2, coarse_sweeps=2), dict(pre_sweeps=2, post_sweeps=1, fused=0),
+                 dict(pre_sweeps=3, post_sweeps=2, coarse_sweeps=3, fused=2), dict(pre_sweeps=3, post_sweeps=3),
                  dict(cycle_type=1), dict(pre_sweeps=0, post_sweeps=2)):
         h.vcycle(f, u, pps.CycleOpts.default(**opts))
         if opts.get("cycle_type", 0) == 0:
             ref = go.vcycle(levels, fn, pre=opts.get("pre_sweeps", 1), post=opts.get("post_sweeps", 1),
                             coarse_sweeps=opts.get("coarse_sweeps", 1))
             assert rel_l2(u.download(), ref) < TOL, opts
+    h.close()
+    mesh.close()
+
+
+@pytest.mark.parametrize("mesh_file,divide", [("3uni.bin", 0), ("2refine.bin", 1), ("multi_refine.bin", 0)])
+def test_specialised_3d16_kernels_vs_generic(ctx, mesh_file, divide):
+    """D = 3, n = 16 has its own smoother kernel (smooth3d16.cuh); every variant of it must agree with
+    the size-generic kernel, and both with the oracle."""
+    h, mesh = build(ctx, mesh_file, 3, 16, divide)
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), 3, 16, divide)
+    rng = np.random.default_rng(99)
+    fn = rng.standard_normal(levels[0].shape)
+    un = rng.standard_normal(levels[0].shape)
+    f = h.new_vec(0, fn)
+    res = {}
+    for generic in (False, True):
+        h.force_generic_kernels(generic)
+        u = h.new_vec(0, un)
+        h.smooth(0, f, u)
+        res[generic, "smooth"] = u.download()
+        for name, opts in (("v11", {}), ("v22", dict(pre_sweeps=2, post_sweeps=2, coarse_sweeps=2)),
+                           ("v11_u", dict(fused=2)), ("v32_u", dict(pre_sweeps=3, post_sweeps=2, fused=2)),
+                           ("plain", dict(fused=0))):
+            h.vcycle(f, u, pps.CycleOpts.default(**opts))
+            res[generic, name] = u.download()
+    h.force_generic_kernels(False)
+    for key in ("smooth", "v11", "v22", "v11_u", "v32_u", "plain"):
+        assert rel_l2(res[False, key], res[True, key]) < 1e-13, key
+    assert rel_l2(res[False, "smooth"], go.smooth(levels[0], fn, un)) < TOL
+    assert rel_l2(res[False, "v11"], go.vcycle(levels, fn)) < TOL
+    assert rel_l2(res[False, "v11_u"], go.vcycle(levels, fn)) < TOL
+    assert rel_l2(res[False, "plain"], go.vcycle(levels, fn)) < TOL
+    assert rel_l2(res[False, "v22"], go.vcycle(levels, fn, pre=2, post=2, coarse_sweeps=2)) < TOL
+    assert rel_l2(res[False, "v32_u"], go.vcycle(levels, fn, pre=3, post=2)) < TOL
     h.close()
     mesh.close()
 
@@ -227,10 +262,11 @@ def test_full_size_properties(config_b):
     h.vcycle(f2, u2)
     u2.scale(0.5)
     assert np.array_equal(u.download(), u2.download())
-    # fused schedule == API-granular schedule
-    h.vcycle(f, u2, pps.CycleOpts.default(fused=0, use_graph=0))
-    u2.add_scaled(-1.0, u)
-    assert u2.two_norm() / u.two_norm() < 1e-13
+    # fused schedules == API-granular schedule
+    for fused in (0, 2):
+        h.vcycle(f, u2, pps.CycleOpts.default(fused=fused, use_graph=0))
+        u2.add_scaled(-1.0, u)
+        assert u2.two_norm() / u.two_norm() < 1e-13, fused
     # stationary iteration contracts like the reference does on uniform meshes (~0.1-0.2 per cycle)
     u.set(0.0)
     hist = []
