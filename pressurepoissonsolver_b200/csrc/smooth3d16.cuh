@@ -12,6 +12,12 @@
 //     leaving two CTA barriers around the y phase (+1 when gamma has to be subtracted first);
 //   * f streams in with 16-byte cp.async into the second buffer, completion tracked by an mbarrier
 //     (cp.async.mbarrier.arrive), so "the tile has landed" costs no CTA barrier;
+//   * the interface values gamma of the NEXT patch are gathered one side per transform: the four loads
+//     of a side (own face, neighbour face, and the coarse correction under both when the prolongation
+//     is fused in) are issued before a transform and combined after it, so their L2/HBM latency hides
+//     behind ~116 DFMAs instead of stalling the whole CTA at the top of an iteration; x- and y-face
+//     values are subtracted in place from the next tile (already landed), z-face values wait in
+//     two registers;
 //   * WRITE_U = false (sweeps whose u is only ever seen through its boundary slices: every sweep but
 //     the last of a level visit in the fused cycle): the last inverse transform is evaluated in full
 //     only for the 60 pencils on the patch boundary (warps 0-1); the other pencils compute just their
@@ -49,8 +55,84 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 	: "memory");
 }
 
+constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
 constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
 constexpr size_t smooth3d16_smem_bytes() { return sizeof(double) * 2 * S16_TILE; }
+
+// refinement-boundary sides are rare: keep their (large) code out of line
+template <bool PROLONG>
+__device__ __noinline__ double iface_gamma_slow16(const PatchMeta *__restrict__ meta, int p, int s, int m,
+                                                  const double *__restrict__ F, const double *__restrict__ uc)
+{
+	const FaceVals<3, 16, PROLONG ? FV_PROLONG : FV_PLAIN> fv{F, uc, meta};
+	return iface_gamma<3, 16, PROLONG ? FV_PROLONG : FV_PLAIN>(meta[p], p, s, m, fv);
+}
+// Gather descriptor of one patch side: everything that is uniform over the 256 face entries, resolved
+// once per patch by one thread, so that an entry's four loads are "base + per-thread constant offset":
+//   (2/h^2) gamma = c (0.5 (a0[t] + a1[o]) + 0.5 (b0[t] + wb b1[o])),  o = the entry's offset on the coarse plane
+// a0/b0: own / neighbour face slice (FaceVals), a1/b1: the parent patches' cells under them
+// (DrctIntp.h:92-111; only read when the prolongation is fused in), c = 0 on sides without a neighbour,
+// wb = 0 for halo faces that already carry the correction.  Sides that need the general code
+// (coarse/fine neighbours, parents of equal size) are flagged in `slow`.
+struct GDesc16 {
+	const double *a0, *b0, *a1, *b1;
+	double        c, wb;
+};
+struct GPatch16 {
+	GDesc16 d[6];
+	double  h2;
+	int     slow[6]; // side needs iface_gamma_slow16
+};
+template <bool PROLONG>
+__device__ __forceinline__ void make_gdesc16(const PatchMeta &pm, int p, int s, const double *__restrict__ F,
+                                             const double *__restrict__ uc, GPatch16 &out)
+{
+	GDesc16 &  d   = out.d[s];
+	const int  ty  = pm.nbr_type[s];
+	const int  ax  = s >> 1;
+	const int  st  = (ax == 0) ? 1 : (ax == 1 ? 16 : 256); // stride of the face-normal axis
+	bool       slow = ty > NBR_NORMAL;
+	d.a0 = d.b0 = F + ((size_t) p * 6 + s) * 256;
+	d.a1 = d.b1 = PROLONG ? uc : F;
+	d.c         = (ty == NBR_NONE) ? 0.0 : 2.0 * pm.inv_h2;
+	d.wb        = 1.0;
+	if (ty == NBR_NORMAL) {
+		d.b0 = F + ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 256;
+		if (PROLONG) {
+			const int o = pm.orth_on_parent, qp = pm.nbr_parent[s], qo = pm.nbr_orth[s];
+			if (o < 0 || (qp >= 0 && qo < 0)) slow = true;
+			d.a1 = uc + (size_t) pm.parent_idx * 4096 + 8 * ((o & 1) + 16 * ((o >> 1) & 1) + 256 * ((o >> 2) & 1)) + ((s & 1) ? 7 * st : 0);
+			if (qp >= 0) d.b1 = uc + (size_t) qp * 4096 + 8 * ((qo & 1) + 16 * ((qo >> 1) & 1) + 256 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 7 * st);
+			else d.b1 = d.a1, d.wb = 0.0;
+		}
+	}
+	if (slow) {
+		d.a0 = d.b0 = F + ((size_t) p * 6 + s) * 256; // harmless addresses; the value comes from iface_gamma_slow16
+		d.a1 = d.b1 = PROLONG ? uc : F;
+	}
+	out.slow[s] = slow;
+}
+template <bool PROLONG> struct SideGamma16 {
+	double a0, a1, b0, b1;
+	__device__ __forceinline__ void issue(const GDesc16 &d, int t, int off)
+	{
+		a0 = __ldg(d.a0 + t);
+		b0 = __ldg(d.b0 + t);
+		a1 = b1 = 0.0;
+		if (PROLONG) {
+			a1 = __ldg(d.a1 + off);
+			b1 = __ldg(d.b1 + off);
+		}
+	}
+	__device__ __forceinline__ double finish(const GPatch16 &gp, int s, const PatchMeta *__restrict__ meta, int p, int t,
+	                                         const double *__restrict__ F, const double *__restrict__ uc) const
+	{
+		const GDesc16 &d = gp.d[s];
+		double         g = d.c * (0.5 * (a0 + a1) + 0.5 * (b0 + d.wb * b1));
+		if (gp.slow[s]) g = d.c * iface_gamma_slow16<PROLONG>(meta, p, s, t, F, uc);
+		return g;
+	}
+};
 
 template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __launch_bounds__(TGPU_THREADS, 3)
@@ -63,8 +145,15 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
 	extern __shared__ __align__(16) double smem[];
 	__shared__ uint64_t                    mbar[2];
+	// neighbour-table entry of the patch after the next (staged with cp.async) and the gather descriptors
+	// of the current / next patch derived from it
+	constexpr int                   MW = (int) (sizeof(PatchMeta) / sizeof(double));
+	__shared__ __align__(16) double metaS[MW];
+	__shared__ GPatch16             GD[2];
 	const int t = threadIdx.x, lo = t & 15, hi = t >> 4;
 	const int npatch = P - p0;
+	// offset of entry t's cell on the parent's plane, per face-normal axis
+	const int off[3] = {(lo >> 1) * 16 + (hi >> 1) * 256, (lo >> 1) + (hi >> 1) * 256, (lo >> 1) + (hi >> 1) * 16};
 	if (t == 0) {
 		mbar_init(&mbar[0], TGPU_THREADS);
 		mbar_init(&mbar[1], TGPU_THREADS);
@@ -73,7 +162,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	Mags<N> mg;
 	mg.load();
 
-	auto prefetch = [&](int g, int b) {
+	// f of patch g -> tile b; with_meta: also the table entry of the patch after it -> metaS
+	auto prefetch = [&](int g, int b, bool with_meta) {
 		const double *src = f + (size_t) (p0 + g) * G::NC;
 		double *      dst = smem + b * S16_TILE;
 #pragma unroll
@@ -81,40 +171,66 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			const int c = t + TGPU_THREADS * i, row = c >> 3; // 16-byte chunk c of the patch, row = y + 16 z
 			cp_async16(dst + (row & 15) * ROW + (row >> 4) * PL + (c & 7) * 2, src + c * 2);
 		}
+		if (with_meta && t < MW && g + (int) gridDim.x < npatch)
+			cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + p0 + g + gridDim.x) + t, true);
 		cp_async_mbar_arrive(&mbar[b]);
+	};
+	// one thread per side (lane 31 of warps 0-5) resolves the descriptors of patch q into GD[slot]
+	auto describe = [&](const PatchMeta &pm, int q, int slot) {
+		if ((t & 31) == 31 && t < 6 * 32) make_gdesc16<PROLONG>(pm, q, t >> 5, Fin, uc, GD[slot]);
+		if (t == 6 * 32 + 31) GD[slot].h2 = pm.h2;
 	};
 
 	int g = blockIdx.x;
-	if (g < npatch) prefetch(g, 0);
-	for (int it = 0; g < npatch; g += gridDim.x, it++) {
-		const int        b      = it & 1;
-		double *         S      = smem + b * S16_TILE;
-		const int        p      = p0 + g;
-		const int        gn     = g + gridDim.x;
-		const PatchMeta &pm     = meta[p];
-		const double     h2     = pm.h2;
-		double           gam[6] = {0, 0, 0, 0, 0, 0}; // (2/h^2) gamma of entry t on each side (0: no neighbour)
-		if (!ZERO_GUESS) {
-			const double cfac = 2.0 * pm.inv_h2;
-			int          ty[G::S];
-			double       own[G::S], gm[G::S];
-			const FaceVals<3, N, PROLONG ? FV_PROLONG : FV_PLAIN> fvals{Fin, uc, meta};
-			gamma_all_sides(pm, p, t, fvals, ty, own, gm);
+	if (g >= npatch) return;
+	prefetch(g, 0, false);
+	double gz0 = 0.0, gz1 = 0.0; // (2/h^2) gamma of entry t on the two z faces of the current patch
+	SideGamma16<PROLONG> sg;
+	if (!ZERO_GUESS) {
+		// first patch of this CTA: nothing to hide the gathers behind
+		const int p = p0 + g;
+		describe(meta[p], p, 0);
+		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
+		__syncthreads();
+		double gx[4];
 #pragma unroll
-			for (int s = 0; s < G::S; s++) gam[s] = (ty[s] == NBR_NONE) ? 0.0 : cfac * gm[s];
+		for (int s = 0; s < 4; s++) {
+			sg.issue(GD[0].d[s], t, off[s >> 1]);
+			gx[s] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
 		}
-		mbar_wait(&mbar[b], (it >> 1) & 1); // every thread's cp.async of this tile has landed
-		if (!ZERO_GUESS) {
-			// x faces: entry t = (y, z) = (lo, hi).  The threads that touch the same edge cell through a
-			// y face, entry (x, z), share z and hence the warp: a warp-level sync orders the two updates.
-			double *r = S + lo * ROW + hi * PL;
-			r[0] -= gam[0];
-			r[N - 1] -= gam[1];
-			__syncwarp();
-			double *c = S + lo + hi * PL;
-			c[0] -= gam[2];
-			c[(N - 1) * ROW] -= gam[3];
+		sg.issue(GD[0].d[4], t, off[2]);
+		gz0 = sg.finish(GD[0], 4, meta, p, t, Fin, uc);
+		sg.issue(GD[0].d[5], t, off[2]);
+		gz1 = sg.finish(GD[0], 5, meta, p, t, Fin, uc);
+		mbar_wait(&mbar[0], 0);
+		// x faces: entry t = (y, z) = (lo, hi); y faces: entry t = (x, z) = (lo, hi); they share edge cells
+		double *r = smem + lo * ROW + hi * PL;
+		r[0] -= gx[0];
+		r[N - 1] -= gx[1];
+		__syncthreads();
+		double *c = smem + lo + hi * PL;
+		c[0] -= gx[2];
+		c[(N - 1) * ROW] -= gx[3];
+	}
+	for (int it = 0; g < npatch; g += gridDim.x, it++) {
+		const int       b    = it & 1;
+		double *        S    = smem + b * S16_TILE;
+		double *        Sn   = smem + (b ^ 1) * S16_TILE;
+		const int       p    = p0 + g;
+		const int       gn   = g + gridDim.x;
+		const bool      next = gn < npatch;
+		const int       pn   = p0 + gn;  // patch whose gamma is gathered during this iteration
+		const GPatch16 &gp   = GD[b ^ 1]; // its descriptors
+		double          h2;
+		if (ZERO_GUESS) {
+			h2 = meta[p].h2;
+			mbar_wait(&mbar[b], (it >> 1) & 1); // every thread's cp.async of this tile has landed
+		} else {
+			// boundary-cell updates of this tile (made during the previous iteration) and the descriptors
+			// become visible; every thread is past the previous iteration: the other tile may be refilled
 			__syncthreads();
+			h2 = GD[b].h2;
+			if (next) prefetch(gn, b ^ 1, true); // + the table entry of the patch after the next -> metaS
 		}
 		double v[N];
 		{ // z forward: pencil (x, y) = (lo, hi)
@@ -122,12 +238,14 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
 			if (!ZERO_GUESS) {
-				v[0] -= gam[4];
-				v[N - 1] -= gam[5];
+				v[0] -= gz0;
+				v[N - 1] -= gz1;
+				if (next) sg.issue(gp.d[4], t, off[2]);
 			}
 			dst2_forward<N>(v, mg);
 #pragma unroll
 			for (int k = 0; k < N; k++) q[k * PL] = v[k];
+			if (!ZERO_GUESS && next) gz0 = sg.finish(gp, 4, meta, pn, t, Fin, uc);
 		}
 		__syncwarp(); // rows (y, k_z) with y in {2w, 2w+1} were produced by this warp
 		double2 *rowp = reinterpret_cast<double2 *>(S + hi * ROW + lo * PL); // row (y, k_z) = (hi, lo)
@@ -138,29 +256,43 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
+			if (!ZERO_GUESS && next) sg.issue(gp.d[5], t, off[2]);
 			dst2_forward<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			if (!ZERO_GUESS && next) gz1 = sg.finish(gp, 5, meta, pn, t, Fin, uc);
 		}
 		__syncthreads();
-		// every thread is past the previous iteration: the other buffer may be refilled
-		if (gn < npatch) {
-			prefetch(gn, b ^ 1);
-			if (!ZERO_GUESS) prefetch_faces_l2<3, N>(meta, p0 + gn, t, Fin);
-		}
+		if (ZERO_GUESS && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
 		{ // y forward, eigenvalues, y inverse: pencil (k_x, k_z) = (lo, hi)
 			double *q = S + lo + hi * PL;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * ROW];
+			if (!ZERO_GUESS && next) sg.issue(gp.d[0], t, off[0]);
 			dst2_forward<N>(v, mg);
 			const double *er = eig + t; // eig[k_y * 256 + k_x + 16 k_z] (the table is symmetric in the axes)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
+			double gx0 = 0.0, gx1 = 0.0;
+			if (!ZERO_GUESS && next) {
+				gx0 = sg.finish(gp, 0, meta, pn, t, Fin, uc);
+				sg.issue(gp.d[1], t, off[0]);
+			}
 			dst3_inverse<N>(v, mg);
 #pragma unroll
 			for (int k = 0; k < N; k++) q[k * ROW] = v[k];
+			if (!ZERO_GUESS && next) {
+				gx1 = sg.finish(gp, 1, meta, pn, t, Fin, uc);
+				mbar_wait(&mbar[b ^ 1], ((it + 1) >> 1) & 1); // the next tile (and metaS) has landed
+				double *r = Sn + lo * ROW + hi * PL;           // x faces of the next patch: entry t = (y, z)
+				r[0] -= gx0;
+				r[N - 1] -= gx1;
+				// descriptors of the patch after the next; GD[b] was last read before this iteration's first barrier
+				if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + gridDim.x, b);
+			}
 		}
-		__syncthreads();
+		__syncthreads(); // (also orders the x-face updates of the next tile before its y-face updates)
+		double gy0 = 0.0;
 		{ // x inverse
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) {
@@ -168,15 +300,18 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
+			if (!ZERO_GUESS && next) sg.issue(gp.d[2], t, off[1]);
 			dst3_inverse<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			if (!ZERO_GUESS && next) gy0 = sg.finish(gp, 2, meta, pn, t, Fin, uc);
 		}
 		if (WRITE_U) {
 			__syncwarp();
 			double *q = S + lo + hi * ROW; // z inverse: pencil (x, y) = (lo, hi)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
+			if (!ZERO_GUESS && next) sg.issue(gp.d[3], t, off[1]);
 			dst3_inverse<N>(v, mg);
 			double *up = u + (size_t) p * G::NC + t;
 #pragma unroll
@@ -204,6 +339,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			}
 		} else {
 			__syncthreads();
+			if (!ZERO_GUESS && next) sg.issue(gp.d[3], t, off[1]);
 			// Only the boundary-cell slices of u are needed.  Warp 0: the x = 0 and x = 15 columns, warp 1:
 			// the y = 0 and y = 15 rows (+ 4 interior pencils): full inverse transform; warps 2-7: the other
 			// 192 interior pencils, z-face values only:
@@ -257,6 +393,12 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				Fp[4 * G::M + x + N * y] = E + O;
 				Fp[5 * G::M + x + N * y] = E - O;
 			}
+		}
+		if (!ZERO_GUESS && next) {
+			const double gy1 = sg.finish(gp, 3, meta, pn, t, Fin, uc);
+			double *     c   = Sn + lo + hi * PL; // y faces of the next patch: entry t = (x, z)
+			c[0] -= gy0;
+			c[(N - 1) * ROW] -= gy1;
 		}
 	}
 }

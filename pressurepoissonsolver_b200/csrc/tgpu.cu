@@ -1044,7 +1044,7 @@ template <bool Z, bool E, bool PR, bool W>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
                              const double *uc)
 {
-	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(TGPU_THREADS);
+	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(S16_BLOCK);
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
 	              Fout, (const double *) h->eig, uc);
 }
