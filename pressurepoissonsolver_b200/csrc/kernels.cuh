@@ -43,6 +43,12 @@ struct __align__(16) PatchMeta {
 };
 
 constexpr int TGPU_THREADS = 256;
+// Programmatic dependent launch: every kernel of the library starts with this pair.  launch_dependents
+// lets the next kernel of the stream be scheduled (its blocks become resident and run up to their own
+// wait) while this grid is still running; wait blocks until the grids this one depends on have
+// completed and flushed.  Both are no-ops for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 // resident smoother CTAs per SM the register budget is tuned for (N = 32 pencils need > 128 registers)
 #ifndef SMOOTH_BLOCKS_16
 #define SMOOTH_BLOCKS_16 3
@@ -424,6 +430,8 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
 	// cp.async while the current group is being solved (double buffering).
 	using G = Geo<D, N>;
+	pdl_launch_dependents();
+	pdl_wait();
 	extern __shared__ double smem[];
 	double *Sbuf0 = smem;                      // [PPB][SP]
 	double *Sbuf1 = smem + G::PPB * G::SP;     // [PPB][SP]
@@ -627,6 +635,8 @@ apply_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__
 	// Persistent CTAs over groups of PPB patches; u of the next group streams into the second
 	// ghosted shared-memory tile with cp.async while the current group is processed.
 	using G = Geo<D, N>;
+	pdl_launch_dependents();
+	pdl_wait();
 	extern __shared__ double smem[];
 	double *   Ubuf0 = smem;
 	double *   Ubuf1 = smem + G::PPB * G::GP;
@@ -776,6 +786,8 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
                               const double *__restrict__ Fold, double *__restrict__ coarse)
 {
 	using G         = Geo<D, N>;
+	pdl_launch_dependents();
+	pdl_wait();
 	constexpr int H = N / 2;
 	__shared__ double R[G::PPB][G::S][G::M];
 	const int t = threadIdx.x, pp = t / G::M, m = t % G::M;
@@ -859,6 +871,8 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
 template <int D, int N>
 __global__ void extract_faces_kernel(int P, const double *__restrict__ u, double *__restrict__ F)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) P * G::S * G::M;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -875,6 +889,8 @@ template <int D, int N>
 __global__ void prolong_faces_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ uc,
                                      double *__restrict__ F)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) P * G::S * G::M;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -890,6 +906,8 @@ template <int D, int N>
 __global__ void prolong_add_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ uc,
                                    double *__restrict__ uf)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) P * G::NC;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -905,6 +923,8 @@ template <int D, int N>
 __global__ void restrict_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ fine,
                                 double *__restrict__ coarse)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	constexpr int H    = N / 2;
 	constexpr int CC   = G::NC >> D;
@@ -938,6 +958,8 @@ template <int D, int N>
 __global__ void jacobi_update_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ r,
                                      double *__restrict__ u, double omega)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) P * G::NC;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -964,6 +986,8 @@ __global__ void pack_faces_kernel(const PatchMeta *__restrict__ meta, int nfaces
                                   const int32_t *__restrict__ side, const double *__restrict__ F, const double *__restrict__ uc,
                                   double *__restrict__ buf)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) nfaces * G::M;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -982,6 +1006,8 @@ template <int D, int N>
 __global__ void unpack_faces_kernel(int nfaces, const int32_t *__restrict__ slot, const int32_t *__restrict__ side,
                                     const double *__restrict__ buf, double *__restrict__ F)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) nfaces * G::M;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -998,6 +1024,8 @@ template <int OP>
 __global__ void blas1_kernel(size_t n, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ b,
                              double alpha, double beta, double gamma)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
 		if (OP == B_SET) v[i] = alpha;
 		else if (OP == B_SCALE) v[i] *= alpha;
@@ -1027,6 +1055,8 @@ __device__ __forceinline__ double warp_max(double x)
 template <int OP>
 __global__ void reduce_stage1(size_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ partial)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	double acc = 0.0;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
 		if (OP == 0) acc = fma(a[i], b[i], acc);
@@ -1044,6 +1074,8 @@ __global__ void reduce_stage1(size_t n, const double *__restrict__ a, const doub
 }
 template <int OP> __global__ void reduce_stage2(int nb, const double *__restrict__ partial, double *__restrict__ result)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	double acc = 0.0;
 	for (int i = threadIdx.x; i < nb; i += blockDim.x) {
 		if (OP == 0) acc += partial[i];
@@ -1078,6 +1110,8 @@ template <int D, int N>
 __global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ starts,
                                  const double *__restrict__ spacing, double *__restrict__ f, double *__restrict__ exact)
 {
+	pdl_launch_dependents();
+	pdl_wait();
 	using G            = Geo<D, N>;
 	const size_t total = (size_t) P * G::NC;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {

@@ -161,6 +161,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	__syncthreads();
 	Mags<N> mg;
 	mg.load();
+	pdl_launch_dependents();
+	pdl_wait();
 
 	// f of patch g -> tile b; with_meta: also the table entry of the patch after it -> metaS
 	auto prefetch = [&](int g, int b, bool with_meta) {

@@ -6,6 +6,7 @@
 #include <nccl.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -119,6 +120,8 @@ struct tgpu_ctx {
 	cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
 	int64_t      launches  = 0;
 	bool         capturing = false;
+	int          pdl       = 1;    // TGPU_PDL: 0 = off, 1 = between small grids only (default), 2 = always
+	bool         last_small = false;
 	int64_t      captured  = 0;
 	// multi-GPU
 	ncclComm_t   comm        = nullptr;
@@ -221,7 +224,23 @@ static int launch(tgpu_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block
 		cudaEventCreate(&e1);
 		cudaEventRecord(e0, ctx->stream);
 	}
-	kernel<<<grid, block, smem, ctx->stream>>>(args...);
+	cudaLaunchConfig_t  cfg = {};
+	cudaLaunchAttribute at[1];
+	cfg.gridDim          = grid;
+	cfg.blockDim         = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream           = ctx->stream;
+	// programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains
+	// (every kernel of the library begins with griddepcontrol.launch_dependents + griddepcontrol.wait)
+	at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs                                        = at;
+	// only between kernels that leave most of the GPU idle (the coarse levels): early-resident blocks of a
+	// dependent grid take shared memory and warp slots away from a predecessor that fills the machine
+	const bool small = (int) (grid.x * grid.y) <= ctx->sm_count;
+	cfg.numAttrs     = (ctx->pdl == 1 && small && ctx->last_small) || ctx->pdl == 2 ? 1 : 0;
+	ctx->last_small  = small;
+	cudaLaunchKernelEx(&cfg, kernel, args...);
 	if (ctx->profiling) {
 		cudaEventRecord(e1, ctx->stream);
 		ctx->prof_events.push_back(e0);
@@ -366,6 +385,7 @@ extern "C" int tgpu_init(int device, tgpu_ctx **out)
 	cudaDeviceProp prop;
 	CU(cudaGetDeviceProperties(&prop, device));
 	ctx->sm_count = prop.multiProcessorCount;
+	if (const char *e = getenv("TGPU_PDL")) ctx->pdl = atoi(e);
 	CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	ctx->own_stream = true;
 	CU(cudaMalloc(&ctx->d_partial, MAX_PARTIAL * sizeof(double)));
