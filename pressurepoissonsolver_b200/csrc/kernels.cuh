@@ -1017,6 +1017,86 @@ __global__ void unpack_faces_kernel(int nfaces, const int32_t *__restrict__ slot
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-to-peer halo exchange over NVLink (one process per GPU, peer buffers mapped with CUDA IPC):
+// push_faces_kernel stores the faces a neighbouring rank needs straight into the halo slots of that
+// rank's face buffer; p2p_signal_kernel / p2p_wait_kernel hand the data over with system-scope
+// release/acquire on per-peer generation counters.  Replaces pack + ncclSend/ncclRecv + unpack
+// (and with it the reference's interface VecScatters, SchurHelper.h:123-150).
+// ---------------------------------------------------------------------------------------------
+template <int D, int N, bool PROLONG>
+__global__ void push_faces_kernel(const PatchMeta *__restrict__ meta, int nfaces, const int32_t *__restrict__ patch,
+                                  const int32_t *__restrict__ side, const int32_t *__restrict__ peer_of,
+                                  const int32_t *__restrict__ ridx, const double *__restrict__ F, const double *__restrict__ uc,
+                                  double *const *__restrict__ peerF)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) nfaces * G::M;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int m = (int) (i % G::M), k = (int) (i / G::M);
+		const int p = patch[k], s = side[k];
+		double    v = F[((size_t) p * G::S + s) * G::M + m];
+		if (PROLONG) {
+			int c[3];
+			face_cell<D, N>(s, m, c);
+			v += __ldg(uc + (size_t) meta[p].parent_idx * G::NC + parent_cell<D, N>(meta[p].orth_on_parent, c));
+		}
+		peerF[peer_of[k]][(size_t) ridx[k] * G::M + m] = v;
+	}
+}
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+// generation = ++counter; every peer's flag (in the peer's memory) is set to it.  Runs after the kernels
+// whose stores it publishes (stream order), so their peer writes have been performed.
+__global__ void p2p_signal_kernel(uint64_t *const *__restrict__ remote_flags, int npeers, uint64_t *__restrict__ counter)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	const uint64_t v = *counter + 1;
+	__syncthreads();
+	if ((int) threadIdx.x < npeers) {
+		__threadfence_system();
+		st_release_sys(remote_flags[threadIdx.x], v);
+	}
+	if (threadIdx.x == 0) *counter = v;
+}
+// waits until every peer's flag has reached generation counter + 1 - lag, then counter += 1.
+// A peer that never arrives (crashed rank) trips the timeout instead of hanging the GPU: *err is set.
+__global__ void p2p_wait_kernel(const uint64_t *__restrict__ local_flags, const int32_t *__restrict__ peer_rank, int npeers,
+                                uint64_t *__restrict__ counter, int lag, int *__restrict__ err)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	const uint64_t expected = *counter + 1 - lag;
+	__syncthreads();
+	if ((int) threadIdx.x < npeers) {
+		const uint64_t *f = local_flags + peer_rank[threadIdx.x];
+		unsigned long long t0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		while (ld_acquire_sys(f) < expected) {
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > 20000000000ull) { // 20 s
+				atomicExch(err, 1);
+				break;
+			}
+			__nanosleep(200);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) *counter += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BLAS-1 (Vector.h:190-262) and reductions (Vector.h:283-321, warp-shuffle + block partials)
 // ---------------------------------------------------------------------------------------------
 enum Blas1Op { B_SET, B_SCALE, B_SHIFT, B_COPY, B_ADD, B_AXPY, B_AXPBY2, B_SCALE_ADD, B_SCALE_ADDS, B_SCALE_ADDS2 };

@@ -20,6 +20,7 @@
 
 using namespace tgpu;
 
+extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h);
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
@@ -69,6 +70,7 @@ struct NcclApi {
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                = nullptr;
 	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                      = nullptr;
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)            = nullptr;
 	ncclResult_t (*GroupStart)()                                                                             = nullptr;
 	ncclResult_t (*GroupEnd)()                                                                               = nullptr;
 	const char *(*GetErrorString)(ncclResult_t)                                                              = nullptr;
@@ -92,6 +94,7 @@ int     load_nccl()
 	NCCL_SYM(Send, "ncclSend")
 	NCCL_SYM(Recv, "ncclRecv")
 	NCCL_SYM(AllReduce, "ncclAllReduce")
+	NCCL_SYM(AllGather, "ncclAllGather")
 	NCCL_SYM(GroupStart, "ncclGroupStart")
 	NCCL_SYM(GroupEnd, "ncclGroupEnd")
 	NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -184,6 +187,13 @@ struct LevelDev {
 	double *   Fa = nullptr, *Fb = nullptr; // face buffers
 	double *   u = nullptr, *f = nullptr, *r = nullptr; // cycle work vectors (lazily allocated)
 	bool       has_neumann = false;
+	// peer-to-peer halo exchange: peers' face buffers and flags mapped with CUDA IPC (see setup_p2p)
+	bool       p2p = false;
+	int32_t *  send_peer = nullptr, *send_ridx = nullptr, *peer_rank = nullptr; // device: per send face / per peer
+	double **  peerFa = nullptr, **peerFb = nullptr;             // device [npeers]: the peers' Fa / Fb
+	uint64_t **peer_data_flag = nullptr, **peer_ack_flag = nullptr; // device [npeers]: my entry of the peers' flag rows
+	uint64_t * data_flags = nullptr, *ack_flags = nullptr;       // my flag rows [nranks] (in the arena, written by peers)
+	uint64_t * cnt = nullptr;                                    // generation counters: data sent / awaited, ack sent / awaited
 };
 
 struct GraphEntry {
@@ -203,6 +213,10 @@ struct tgpu_hier {
 	std::vector<tgpu_vec *> krylov_ws;
 	tgpu_vec *            host_f = nullptr, *host_u = nullptr;
 	bool                  generic_kernels = false; // test hook: force the size-generic smoother
+	// peer-to-peer arena: flag rows + the face buffers of the distributed levels, one IPC-exported allocation
+	void *                arena = nullptr;
+	std::vector<void *>   ipc_opened;
+	int *                 p2p_err = nullptr;
 };
 
 struct tgpu_vec {
@@ -763,6 +777,149 @@ extern "C" int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nr
 	return TGPU_OK;
 	API_END
 }
+
+// ------------------------------------------------------------------------------------------
+// peer-to-peer set-up: one IPC-exported arena per rank holds the flag rows and the face buffers of the
+// distributed levels; every rank maps the arenas of its neighbours and learns into which of their halo
+// slots each of its boundary faces goes.  NCCL is used here once, as the bootstrap transport.
+// ------------------------------------------------------------------------------------------
+struct P2PPack {
+	cudaIpcMemHandle_t handle;
+	uint64_t           base_off;           // arena - allocation base
+	uint64_t           flags_off;          // flag rows: [level][kind: data, ack][rank]
+	uint64_t           fa_off[16], fb_off[16];
+};
+static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
+static int alloc_base_of(void *ptr, void **base)
+{
+	typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+	void *                          fn = nullptr;
+	cudaDriverEntryPointQueryResult qr;
+	CU(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+	if (!fn || qr != cudaDriverEntryPointSuccess) return fail(TGPU_ERR_CUDA, "cuMemGetAddressRange is not available");
+	unsigned long long b  = 0;
+	size_t             sz = 0;
+	if (((fn_t) fn)(&b, &sz, (unsigned long long) (uintptr_t) ptr) != 0) return fail(TGPU_ERR_CUDA, "cuMemGetAddressRange failed");
+	*base = (void *) (uintptr_t) b;
+	return TGPU_OK;
+}
+static int setup_p2p(tgpu_hier *h, const Partition &pt)
+{
+	tgpu_ctx *ctx = h->ctx;
+	const int nl = (int) h->levels.size(), nr = ctx->nranks, me = ctx->rank;
+	if (nl > 16) return fail(TGPU_ERR_UNSUPPORTED, "peer-to-peer exchange supports at most 16 levels");
+	const int S = 2 * h->D;
+	size_t    M = 1;
+	for (int i = 0; i < h->D - 1; i++) M *= h->N;
+	// ---- arena layout ----
+	P2PPack mine;
+	memset(&mine, 0, sizeof(mine));
+	size_t off      = 0;
+	mine.flags_off  = off;
+	off += align256((size_t) nl * 2 * nr * sizeof(uint64_t));
+	for (int l = 0; l < nl; l++) {
+		LevelDev &L = h->levels[l];
+		if (!L.distributed || (L.nsend == 0 && L.nrecv == 0)) continue;
+		mine.fa_off[l] = off, off += align256(L.nface * sizeof(double));
+		mine.fb_off[l] = off, off += align256(L.nface * sizeof(double));
+	}
+	CU(cudaMalloc(&h->arena, off));
+	CU(cudaMemset(h->arena, 0, off));
+	void *base = nullptr;
+	TRY(alloc_base_of(h->arena, &base));
+	mine.base_off = (uint64_t) ((char *) h->arena - (char *) base);
+	CU(cudaIpcGetMemHandle(&mine.handle, base));
+	CU(cudaMalloc(&h->p2p_err, sizeof(int)));
+	CU(cudaMemset(h->p2p_err, 0, sizeof(int)));
+	// ---- all-gather the packs ----
+	std::vector<P2PPack> all(nr);
+	{
+		P2PPack *d_mine = nullptr, *d_all = nullptr;
+		CU(cudaMalloc(&d_mine, sizeof(P2PPack)));
+		CU(cudaMalloc(&d_all, sizeof(P2PPack) * nr));
+		CU(cudaMemcpy(d_mine, &mine, sizeof(P2PPack), cudaMemcpyHostToDevice));
+		NC(g_nccl.AllGather(d_mine, d_all, sizeof(P2PPack), ncclChar, ctx->comm, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		CU(cudaMemcpy(all.data(), d_all, sizeof(P2PPack) * nr, cudaMemcpyDeviceToHost));
+		cudaFree(d_mine);
+		cudaFree(d_all);
+	}
+	// ---- map the arenas of the ranks I exchange with ----
+	std::vector<char *> rarena(nr, nullptr);
+	rarena[me] = (char *) h->arena;
+	for (int l = 0; l < nl; l++)
+		for (const PeerDev &pd : h->levels[l].peers) {
+			if (rarena[pd.peer]) continue;
+			void *rb = nullptr;
+			CU(cudaIpcOpenMemHandle(&rb, all[pd.peer].handle, cudaIpcMemLazyEnablePeerAccess));
+			h->ipc_opened.push_back(rb);
+			rarena[pd.peer] = (char *) rb + all[pd.peer].base_off;
+		}
+	// ---- per level: move the face buffers into the arena, exchange the halo-slot numbering, build the tables ----
+	for (int l = 0; l < nl; l++) {
+		LevelDev &       L  = h->levels[l];
+		const PartLevel &PL = pt.levels[l];
+		if (!L.distributed || (L.nsend == 0 && L.nrecv == 0)) continue;
+		cudaFree(L.Fa);
+		cudaFree(L.Fb);
+		L.Fa         = (double *) ((char *) h->arena + mine.fa_off[l]);
+		L.Fb         = (double *) ((char *) h->arena + mine.fb_off[l]);
+		L.data_flags = (uint64_t *) ((char *) h->arena + mine.flags_off) + ((size_t) l * 2 + 0) * nr;
+		L.ack_flags  = (uint64_t *) ((char *) h->arena + mine.flags_off) + ((size_t) l * 2 + 1) * nr;
+		CU(cudaMalloc(&L.cnt, 4 * sizeof(uint64_t)));
+		CU(cudaMemset(L.cnt, 0, 4 * sizeof(uint64_t)));
+		const int np = (int) L.peers.size();
+		// my halo slots as the peers see them: they send (slot, side) lists in the agreed order
+		int32_t *d_rslot = nullptr;
+		CU(cudaMalloc(&d_rslot, std::max<size_t>(1, L.nsend) * sizeof(int32_t)));
+		NC(g_nccl.GroupStart());
+		for (const PeerDev &pd : L.peers) {
+			if (pd.recv_n) NC(g_nccl.Send(L.recv_slot + pd.recv_off, pd.recv_n, ncclInt32, pd.peer, ctx->comm, ctx->stream));
+			if (pd.send_n) NC(g_nccl.Recv(d_rslot + pd.send_off, pd.send_n, ncclInt32, pd.peer, ctx->comm, ctx->stream));
+		}
+		NC(g_nccl.GroupEnd());
+		CU(cudaStreamSynchronize(ctx->stream));
+		std::vector<int32_t> rslot(L.nsend), ridx(L.nsend), speer(L.nsend), prank(np);
+		if (L.nsend) CU(cudaMemcpy(rslot.data(), d_rslot, L.nsend * sizeof(int32_t), cudaMemcpyDeviceToHost));
+		cudaFree(d_rslot);
+		std::vector<double *>   pfa(np), pfb(np);
+		std::vector<uint64_t *> pdf(np), paf(np);
+		size_t                  k = 0;
+		for (int i = 0; i < np; i++) {
+			const PeerDev &     pd = L.peers[i];
+			const PeerExchange &x  = PL.peers[i];
+			prank[i]               = pd.peer;
+			char *ra               = rarena[pd.peer];
+			pfa[i]                 = (double *) (ra + all[pd.peer].fa_off[l]);
+			pfb[i]                 = (double *) (ra + all[pd.peer].fb_off[l]);
+			uint64_t *rflags       = (uint64_t *) (ra + all[pd.peer].flags_off);
+			pdf[i]                 = rflags + ((size_t) l * 2 + 0) * nr + me;
+			paf[i]                 = rflags + ((size_t) l * 2 + 1) * nr + me;
+			for (size_t j = 0; j < pd.send_n; j++, k++) {
+				speer[k] = i;
+				ridx[k]  = rslot[k] * S + x.send_side[j];
+			}
+		}
+		TRY(dev_upload(&L.send_peer, speer.data(), speer.size()));
+		TRY(dev_upload(&L.send_ridx, ridx.data(), ridx.size()));
+		TRY(dev_upload(&L.peer_rank, prank.data(), prank.size()));
+		TRY(dev_upload(&L.peerFa, pfa.data(), pfa.size()));
+		TRY(dev_upload(&L.peerFb, pfb.data(), pfb.size()));
+		TRY(dev_upload(&L.peer_data_flag, pdf.data(), pdf.size()));
+		TRY(dev_upload(&L.peer_ack_flag, paf.data(), paf.size()));
+		L.p2p = true;
+	}
+	// nobody may push before everybody has finished mapping
+	{
+		int *d = nullptr;
+		CU(cudaMalloc(&d, sizeof(int)));
+		CU(cudaMemset(d, 0, sizeof(int)));
+		NC(g_nccl.AllReduce(d, d, 1, ncclInt32, ncclSum, ctx->comm, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		cudaFree(d);
+	}
+	return TGPU_OK;
+}
 extern "C" int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part *part, tgpu_hier **out)
 {
 	API_BEGIN
@@ -809,6 +966,15 @@ extern "C" int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part 
 		CU(cudaMemset(L.Fa, 0, L.nface * sizeof(double)));
 		CU(cudaMemset(L.Fb, 0, L.nface * sizeof(double)));
 	}
+	// TGPU_P2P=0 keeps the NCCL send/recv exchange (pack, ncclSend/ncclRecv, unpack)
+	const char *e = getenv("TGPU_P2P");
+	if (pt.nranks > 1 && !(e && atoi(e) == 0)) {
+		int rc = setup_p2p(h, pt);
+		if (rc != TGPU_OK) {
+			tgpu_hierarchy_destroy(h);
+			return rc;
+		}
+	}
 	*out = h;
 	return TGPU_OK;
 	API_END
@@ -833,8 +999,18 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.meta);
 		cudaFree(L.starts);
 		cudaFree(L.spacing);
-		cudaFree(L.Fa);
-		cudaFree(L.Fb);
+		if (!L.p2p) { // otherwise they live in the arena
+			cudaFree(L.Fa);
+			cudaFree(L.Fb);
+		}
+		cudaFree(L.send_peer);
+		cudaFree(L.send_ridx);
+		cudaFree(L.peer_rank);
+		cudaFree(L.peerFa);
+		cudaFree(L.peerFb);
+		cudaFree(L.peer_data_flag);
+		cudaFree(L.peer_ack_flag);
+		cudaFree(L.cnt);
 		for (int e = 0; e < 4; e++)
 			if (L.ev[e]) cudaEventDestroy(L.ev[e]);
 		cudaFree(L.send_patch);
@@ -847,6 +1023,9 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.f);
 		cudaFree(L.r);
 	}
+	for (void *b : h->ipc_opened) cudaIpcCloseMemHandle(b);
+	cudaFree(h->arena);
+	cudaFree(h->p2p_err);
 	cudaFree(h->eig);
 	delete h;
 	return TGPU_OK;
@@ -1148,14 +1327,65 @@ static int k_set(tgpu_hier *h, double *v, size_t n, double alpha)
 	return launch(h->ctx, blas1_kernel<B_SET>, dim3(grid_for(h->ctx, n)), dim3(256), 0, n, v, (const double *) nullptr, (const double *) nullptr, alpha, 0.0, 0.0);
 }
 
-// halo exchange of one distributed level: pack the faces every peer needs, grouped ncclSend/ncclRecv,
-// scatter what arrived into the halo slots of F.  uc != nullptr sends F + (P uc) on the boundary cells
-// (the receiver must not add the correction again: halo slots have no parent, see FaceVals).
+// ---- peer-to-peer halo exchange (see kernels.cuh: push_faces_kernel, p2p_signal_kernel, p2p_wait_kernel) ----
+// Per level two generation counters per peer, both in the receiver's memory: DATA (my faces have landed in
+// your halo slots) and ACK (I have consumed the halo you pushed).  Generation g is pushed once every peer has
+// acknowledged g - 1, consumed after every peer's DATA has reached g, and acknowledged right after its
+// consumers were enqueued (k_exchange_done).  Every step is a kernel on the library's stream, so the whole
+// protocol is captured in the cycle's CUDA graph.
+enum { P2P_DATA = 0, P2P_ACK = 1 };
+static int p2p_signal(tgpu_hier *h, int l, int kind)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, kind == P2P_DATA ? "p2p_signal_data" : "p2p_signal_ack", l);
+	return launch(h->ctx, p2p_signal_kernel, dim3(1), dim3(32), 0, (uint64_t *const *) (kind == P2P_DATA ? L.peer_data_flag : L.peer_ack_flag),
+	              (int) L.peers.size(), L.cnt + (kind == P2P_DATA ? 0 : 2));
+}
+static int p2p_wait(tgpu_hier *h, int l, int kind, int lag)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, kind == P2P_DATA ? "p2p_wait_data" : "p2p_wait_ack", l);
+	return launch(h->ctx, p2p_wait_kernel, dim3(1), dim3(32), 0, (const uint64_t *) (kind == P2P_DATA ? L.data_flags : L.ack_flags),
+	              (const int32_t *) L.peer_rank, (int) L.peers.size(), L.cnt + (kind == P2P_DATA ? 1 : 3), lag, h->p2p_err);
+}
+// store my boundary faces (F, or F + P uc on the boundary cells) into the peers' halo slots and publish them
+static int p2p_push(tgpu_hier *h, int l, double *F, const double *uc)
+{
+	LevelDev &L   = h->levels[l];
+	tgpu_ctx *ctx = h->ctx;
+	if (F != L.Fa && F != L.Fb) return fail(TGPU_ERR_ARG, "p2p_push: not a face buffer of this level");
+	TRY(p2p_wait(h, l, P2P_ACK, 1)); // the peers are done with the previous generation
+	size_t M = 1;
+	for (int i = 0; i < h->D - 1; i++) M *= h->N;
+	if (L.nsend) {
+		Tag             tg(ctx, "p2p_push_faces", l);
+		double *const *pf = (F == L.Fa) ? L.peerFa : L.peerFb;
+		DISPATCH_DN(h->D, h->N, {
+			if (uc) TRY(launch(ctx, push_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
+			else TRY(launch(ctx, push_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
+		});
+	}
+	return p2p_signal(h, l, P2P_DATA);
+}
+static bool exchanges(const tgpu_hier *h, int l)
+{
+	const LevelDev &L = h->levels[l];
+	return L.distributed && h->ctx->nranks > 1 && (L.nsend || L.nrecv);
+}
+// halo exchange of one distributed level.  Peer-to-peer: push + wait.  NCCL fallback (TGPU_P2P=0): pack the
+// faces every peer needs, grouped ncclSend/ncclRecv, scatter what arrived into the halo slots of F.
+// uc != nullptr sends F + (P uc) on the boundary cells (the receiver must not add the correction again:
+// halo slots have no parent, see FaceVals).  Every k_exchange is followed, after the kernels that read the
+// halo, by k_exchange_done.
 static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
 {
 	LevelDev &L   = h->levels[l];
 	tgpu_ctx *ctx = h->ctx;
-	if (!L.distributed || ctx->nranks == 1 || (L.nsend == 0 && L.nrecv == 0)) return TGPU_OK;
+	if (!exchanges(h, l)) return TGPU_OK;
+	if (L.p2p) {
+		TRY(p2p_push(h, l, F, uc));
+		return p2p_wait(h, l, P2P_DATA, 0);
+	}
 	size_t M = 1;
 	for (int i = 0; i < h->D - 1; i++) M *= h->N;
 	Tag tg(ctx, "halo_exchange", l);
@@ -1178,6 +1408,12 @@ static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
 		DISPATCH_DN(h->D, h->N, TRY(launch(ctx, unpack_faces_kernel<DD, NN>, dim3(grid_for(ctx, L.nrecv * M)), dim3(256), 0, (int) L.nrecv, (const int32_t *) L.recv_slot, (const int32_t *) L.recv_side, (const double *) L.recvbuf, F)));
 	}
 	return TGPU_OK;
+}
+// the kernels that read the halo of the last exchange on level l have been enqueued
+static int k_exchange_done(tgpu_hier *h, int l)
+{
+	if (!exchanges(h, l) || !h->levels[l].p2p) return TGPU_OK;
+	return p2p_signal(h, l, P2P_ACK);
 }
 // sum a replicated level vector over the ranks (every cell is written by exactly one rank, the others hold 0)
 static int k_allreduce_sum(tgpu_hier *h, double *v, size_t n)
@@ -1202,7 +1438,8 @@ extern "C" int tgpu_apply(tgpu_hier *h, int level, const tgpu_vec *u, tgpu_vec *
 	if (u == out) return fail(TGPU_ERR_ARG, "tgpu_apply: in-place apply is not supported");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
 	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
-	return k_apply(h, level, 0, u->d, nullptr, h->levels[level].Fa, out->d, nullptr);
+	TRY(k_apply(h, level, 0, u->d, nullptr, h->levels[level].Fa, out->d, nullptr));
+	return k_exchange_done(h, level);
 	API_END
 }
 extern "C" int tgpu_residual(tgpu_hier *h, int level, const tgpu_vec *f, const tgpu_vec *u, tgpu_vec *r)
@@ -1214,7 +1451,8 @@ extern "C" int tgpu_residual(tgpu_hier *h, int level, const tgpu_vec *f, const t
 	if (u == r) return fail(TGPU_ERR_ARG, "tgpu_residual: r must not alias u");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
 	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
-	return k_apply(h, level, 1, u->d, f->d, h->levels[level].Fa, r->d, nullptr);
+	TRY(k_apply(h, level, 1, u->d, f->d, h->levels[level].Fa, r->d, nullptr));
+	return k_exchange_done(h, level);
 	API_END
 }
 extern "C" int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec *u)
@@ -1225,7 +1463,8 @@ extern "C" int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec 
 	if (f == u) return fail(TGPU_ERR_ARG, "tgpu_smooth: f must not alias u");
 	TRY(k_extract_faces(h, level, u->d, h->levels[level].Fa));
 	TRY(k_exchange(h, level, h->levels[level].Fa, nullptr));
-	return k_smooth(h, level, false, false, f->d, u->d, h->levels[level].Fa, nullptr);
+	TRY(k_smooth(h, level, false, false, f->d, u->d, h->levels[level].Fa, nullptr));
+	return k_exchange_done(h, level);
 	API_END
 }
 static int ensure_work(tgpu_hier *h, int l, bool need_r)
@@ -1246,6 +1485,7 @@ extern "C" int tgpu_smooth_jacobi(tgpu_hier *h, int level, const tgpu_vec *f, tg
 	TRY(k_extract_faces(h, level, u->d, L.Fa));
 	TRY(k_exchange(h, level, L.Fa, nullptr));
 	TRY(k_apply(h, level, 1, u->d, f->d, L.Fa, L.r, nullptr));
+	TRY(k_exchange_done(h, level));
 	DISPATCH_DN(h->D, h->N, return launch(h->ctx, jacobi_update_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, u->d, omega));
 	API_END
 }
@@ -1280,6 +1520,7 @@ extern "C" int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_v
 	TRY(k_exchange(h, fine_level, h->levels[fine_level].Fa, nullptr));
 	if (crosses_replication(h, fine_level)) TRY(k_set(h, coarse_f->d, coarse_f->n, 0.0));
 	TRY(k_apply(h, fine_level, 2, u->d, f->d, h->levels[fine_level].Fa, nullptr, coarse_f->d));
+	TRY(k_exchange_done(h, fine_level));
 	if (crosses_replication(h, fine_level)) TRY(k_allreduce_sum(h, coarse_f->d, coarse_f->n));
 	return TGPU_OK;
 	API_END
@@ -1303,7 +1544,8 @@ static int generic_smooth(tgpu_hier *h, int l, const double *f, double *u)
 {
 	TRY(k_extract_faces(h, l, u, h->levels[l].Fa));
 	TRY(k_exchange(h, l, h->levels[l].Fa, nullptr));
-	return k_smooth(h, l, false, false, f, u, h->levels[l].Fa, nullptr);
+	TRY(k_smooth(h, l, false, false, f, u, h->levels[l].Fa, nullptr));
+	return k_exchange_done(h, l);
 }
 static int generic_prep_coarser(tgpu_hier *h, int l, const double *f, const double *u)
 {
@@ -1311,6 +1553,7 @@ static int generic_prep_coarser(tgpu_hier *h, int l, const double *f, const doub
 	TRY(k_extract_faces(h, l, u, L.Fa));
 	TRY(k_exchange(h, l, L.Fa, nullptr));
 	TRY(k_apply(h, l, 1, u, f, L.Fa, L.r, nullptr)); // r = A u; r = -r + f
+	TRY(k_exchange_done(h, l));
 	TRY(k_set(h, C.u, C.ncells, 0.0));               // new_u (zero-initialised Vec)
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
 	TRY(k_restrict(h, l, L.r, C.f));                 // new_f = R r
@@ -1372,6 +1615,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 			const bool emit = (i + 1 < o.coarse_sweeps);
 			if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !emit));
+			if (i > 0) TRY(k_exchange_done(h, l));
 			if (i > 0 && emit) std::swap(Fcur, Falt);
 		}
 		return TGPU_OK;
@@ -1381,17 +1625,26 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	for (int i = 0; i < o.pre_sweeps; i++) {
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !from_faces));
+		if (i > 0) TRY(k_exchange_done(h, l));
 		if (i > 0) std::swap(Fcur, Falt);
 	}
 	// Fcur: faces of the pre-smoothed u; Falt: faces of the iterate before the last pre-sweep (if pre_sweeps > 1)
 	const double *Fold    = o.pre_sweeps > 1 ? Falt : nullptr;
-	const bool    overlap = L.distributed && h->ctx->nranks > 1 && (L.nsend || L.nrecv);
+	const bool    overlap = exchanges(h, l);
 	auto residual_restrict = [&](int p0, int p1) {
 		if (from_faces) return k_face_residual_restrict(h, l, Fcur, Fold, C.f, p0, p1);
 		return k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, p0, p1);
 	};
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
-	if (overlap) {
+	if (overlap && L.p2p) {
+		// the faces of the pre-smoothed u go straight into the neighbours' halo slots; theirs arrive while
+		// the patches without off-rank neighbours are swept
+		TRY(p2p_push(h, l, Fcur, nullptr));
+		TRY(residual_restrict(0, L.n_interior));
+		TRY(p2p_wait(h, l, P2P_DATA, 0));
+		TRY(residual_restrict(L.n_interior, L.P));
+		TRY(k_exchange_done(h, l));
+	} else if (overlap) {
 		// faces of the pre-smoothed u travel on the comm stream while the interior patches are swept
 		TRY(exchange_async(h, l, Fcur, nullptr, L.ev[0], L.ev[1]));
 		TRY(residual_restrict(0, L.n_interior));
@@ -1403,7 +1656,8 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
 	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
-	if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
+	if (overlap && L.p2p) TRY(p2p_push(h, l, Fcur, C.u));
+	else if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
 	for (int i = 0; i < o.post_sweeps; i++) {
 		const bool lastsweep = (i + 1 == o.post_sweeps);
 		const bool emit      = !lastsweep || want_faces;
@@ -1411,10 +1665,14 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		if (i == 0 && overlap) {
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior, lastsweep));
-			CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[3], 0));
+			if (L.p2p) TRY(p2p_wait(h, l, P2P_DATA, 0));
+			else CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[3], 0));
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, L.n_interior, L.P, lastsweep));
-		} else
+			TRY(k_exchange_done(h, l));
+		} else {
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, i == 0 ? C.u : nullptr, 0, -1, lastsweep));
+			if (i > 0) TRY(k_exchange_done(h, l));
+		}
 		std::swap(Fcur, Falt);
 	}
 	return TGPU_OK;
