@@ -29,6 +29,8 @@ CONFIGS = {
     "B4": (3, "4uni.bin", 1, 16, "weak-scaling point for 4 GPUs: 4uni.bin --divide 1 with the lower half (z < 0.5) refined once more, 18,432 patches of 16^3 (75,497,472 cells), 6 levels, trig RHS"),
     "B8": (3, "4uni.bin", 2, 16, "weak-scaling point for 8 GPUs: uniform octree 4uni.bin --divide 2, 32,768 patches of 16^3 (134,217,728 cells), 6 levels, trig RHS"),
     "D16": (3, "4uni.bin", 3, 16, "config D mesh with 16^3 patches: uniform octree 4uni.bin --divide 3, 262,144 patches of 16^3 (1,073,741,824 cells), 7 levels, trig RHS"),
+    "D": (3, "4uni.bin", 2, 32, "config D: uniform octree 4uni.bin --divide 2, 32,768 patches of 32^3 (1,073,741,824 cells), 6 levels, trig RHS"),
+    "D2": (3, "3uni.bin", 1, 32, "3uni.bin --divide 1, 512 patches of 32^3 (16,777,216 cells), 4 levels, trig RHS"),
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16

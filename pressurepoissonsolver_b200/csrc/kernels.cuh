@@ -65,7 +65,6 @@ template <int D, int N> struct Geo {
 	static constexpr int SP  = M * ROW;                  // padded patch size in smem (doubles)
 	static constexpr int NG  = N + 2;                    // row with ghosts
 	static constexpr int GP  = (D == 2) ? NG * NG : NG * NG * NG;
-	static_assert(M <= TGPU_THREADS, "patch face larger than the block");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -115,7 +114,8 @@ template <int N> struct Mags {
 		const bool neg = a >= 2 * N;
 		if (neg) a -= 2 * N;
 		if (a > N) a = 2 * N - a;
-		return neg ? -m[a] : m[a];
+		const double mag = IN_REGS ? m[IN_REGS ? a : 0] : c_mag32[a]; // N = 32: constant-bank operand (compile-time index)
+		return neg ? -mag : mag;
 	}
 };
 
@@ -430,6 +430,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
 	// cp.async while the current group is being solved (double buffering).
 	using G = Geo<D, N>;
+	static_assert(G::M <= TGPU_THREADS, "patch face larger than the block");
 	pdl_launch_dependents();
 	pdl_wait();
 	extern __shared__ double smem[];
@@ -1223,3 +1224,4 @@ __global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, cons
 }
 } // namespace tgpu
 #include "smooth3d16.cuh"
+#include "patch3d32.cuh"

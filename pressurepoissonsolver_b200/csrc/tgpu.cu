@@ -217,6 +217,7 @@ struct tgpu_hier {
 	void *                arena = nullptr;
 	std::vector<void *>   ipc_opened;
 	int *                 p2p_err = nullptr;
+	double *              scratch32 = nullptr; // smooth3d32_kernel: one 256 KB block per resident CTA
 };
 
 struct tgpu_vec {
@@ -305,9 +306,17 @@ static int grid_for(tgpu_ctx *ctx, size_t n, int block = 256, int per_sm = 8)
 		else return fail(TGPU_ERR_UNSUPPORTED, "unsupported (D, n) combination");       \
 	} while (0)
 
+// grid-stride kernels also exist for 32^3 patches; the tile kernels have their own (patch3d32.cuh)
+#define DISPATCH_DN_ALL(D_, N_, ...)                                                  \
+	do {                                                                                \
+		if ((D_) == 3 && (N_) == 32) { constexpr int DD = 3, NN = 32; __VA_ARGS__; }          \
+		else DISPATCH_DN(D_, N_, __VA_ARGS__);                                          \
+	} while (0)
+static bool is_3d32(const tgpu_hier *h) { return h->D == 3 && h->N == 32; }
+
 static bool supported_dn(int D, int N)
 {
-	return (D == 2 && (N == 4 || N == 8 || N == 16 || N == 32)) || (D == 3 && (N == 4 || N == 8 || N == 16));
+	return (D == 2 && (N == 4 || N == 8 || N == 16 || N == 32)) || (D == 3 && (N == 4 || N == 8 || N == 16 || N == 32));
 }
 
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d16()
@@ -326,6 +335,30 @@ static int set_smem_attrs_3d16()
 	TRY((set_smem_attr_3d16<false, true, true, true>()));
 	TRY((set_smem_attr_3d16<false, false, true, true>()));
 	TRY((set_smem_attr_3d16<false, true, true, false>()));
+	return TGPU_OK;
+}
+template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d32()
+{
+	CU(cudaFuncSetAttribute(smooth3d32_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32_smem_bytes()));
+	return TGPU_OK;
+}
+// 32^3 patches: opt-in shared memory sizes and the CTA-private scratch blocks of smooth3d32_kernel
+static int setup_3d32(tgpu_hier *h)
+{
+	TRY((set_smem_attr_3d32<true, true, false, true>()));
+	TRY((set_smem_attr_3d32<true, false, false, true>()));
+	TRY((set_smem_attr_3d32<true, true, false, false>()));
+	TRY((set_smem_attr_3d32<false, true, false, true>()));
+	TRY((set_smem_attr_3d32<false, false, false, true>()));
+	TRY((set_smem_attr_3d32<false, true, false, false>()));
+	TRY((set_smem_attr_3d32<false, true, true, true>()));
+	TRY((set_smem_attr_3d32<false, false, true, true>()));
+	TRY((set_smem_attr_3d32<false, true, true, false>()));
+	CU(cudaFuncSetAttribute(apply3d32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(apply3d32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
+	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
+	CU(cudaMalloc(&h->scratch32, (size_t) h->ctx->sm_count * S32_CTAS_PER_SM * 32768 * sizeof(double)));
 	return TGPU_OK;
 }
 template <int D, int N> static int set_smem_attrs()
@@ -585,7 +618,7 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 	API_BEGIN
 	if (!ctx || !levels || !out || nlevels < 1) return fail(TGPU_ERR_ARG, "tgpu_hierarchy_create: bad argument");
 	if (!supported_dn(D, n))
-		return fail(TGPU_ERR_UNSUPPORTED, "tgpu_hierarchy_create: (D, n) must be one of 2D n=4/8/16/32, 3D n=4/8/16");
+		return fail(TGPU_ERR_UNSUPPORTED, "tgpu_hierarchy_create: (D, n) must be one of 2D n=4/8/16/32, 3D n=4/8/16/32");
 	CU(cudaSetDevice(ctx->device));
 	std::unique_ptr<tgpu_hier> h(new tgpu_hier());
 	h->ctx = ctx;
@@ -674,7 +707,8 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 		}
 		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
 	}
-	DISPATCH_DN(D, n, TRY((set_smem_attrs<DD, NN>())));
+	if (D == 3 && n == 32) TRY(setup_3d32(h.get()));
+	else DISPATCH_DN(D, n, TRY((set_smem_attrs<DD, NN>())));
 	*out = h.release();
 	return TGPU_OK;
 	API_END
@@ -1026,6 +1060,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	for (void *b : h->ipc_opened) cudaIpcCloseMemHandle(b);
 	cudaFree(h->arena);
 	cudaFree(h->p2p_err);
+	cudaFree(h->scratch32);
 	cudaFree(h->eig);
 	delete h;
 	return TGPU_OK;
@@ -1216,7 +1251,7 @@ static int k_extract_faces(tgpu_hier *h, int l, const double *u, double *F)
 {
 	LevelDev &L = h->levels[l];
 	Tag       tg(h->ctx, "extract_faces", l);
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, extract_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, L.P, u, F));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, extract_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, L.P, u, F));
 }
 // mode 0: out = A u; 1: out = f - A u; 2: coarse = R (f - A u).  F must hold the faces of u.
 static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double *f, const double *F, double *out, double *coarse,
@@ -1226,6 +1261,16 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return TGPU_OK;
 	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : "residual_restrict"), l);
+	if (is_3d32(h)) {
+		if (mode == 2) { // no fused form for 32^3 patches: residual into the level's work vector, then restrict
+			if (p0 != 0 || p1 != L.P) return fail(TGPU_ERR_UNSUPPORTED, "residual+restrict on a patch range is not available for 32^3 patches");
+			TRY(launch(h->ctx, apply3d32_kernel<1>, dim3(std::min((p1 - p0) * 4, h->ctx->sm_count * 2)), dim3(TGPU_THREADS), apply3d32_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, L.r));
+			return launch(h->ctx, restrict_kernel<3, 32>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, coarse);
+		}
+		const dim3 grid(std::min((p1 - p0) * 4, h->ctx->sm_count * 2));
+		if (mode == 0) return launch(h->ctx, apply3d32_kernel<0>, grid, dim3(TGPU_THREADS), apply3d32_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, out);
+		return launch(h->ctx, apply3d32_kernel<1>, grid, dim3(TGPU_THREADS), apply3d32_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, out);
+	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
@@ -1258,6 +1303,26 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
+	if (is_3d32(h)) {
+		const dim3   grid(std::min(p1 - p0, h->ctx->sm_count * S32_CTAS_PER_SM)), block(TGPU_THREADS);
+		const size_t sm  = smooth3d32_smem_bytes();
+		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+#define S32_CASE(K, Z, E, PR, W) \
+	case K: return launch(h->ctx, smooth3d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->eig, uc, h->scratch32);
+		switch (key) {
+			S32_CASE(8 | 4 | 1, true, true, false, true)
+			S32_CASE(8 | 1, true, false, false, true)
+			S32_CASE(8 | 4, true, true, false, false)
+			S32_CASE(4 | 1, false, true, false, true)
+			S32_CASE(1, false, false, false, true)
+			S32_CASE(4, false, true, false, false)
+			S32_CASE(4 | 2 | 1, false, true, true, true)
+			S32_CASE(2 | 1, false, false, true, true)
+			S32_CASE(4 | 2, false, true, true, false)
+		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
+		}
+#undef S32_CASE
+	}
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		switch (key) {
@@ -1296,6 +1361,11 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return TGPU_OK;
 	Tag tg(h->ctx, "face_residual_restrict", l);
+	if (is_3d32(h)) {
+		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 4)), block(TGPU_THREADS);
+		if (Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
@@ -1308,19 +1378,19 @@ static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)
 {
 	LevelDev &L = h->levels[l];
 	Tag       tg(h->ctx, "restrict", l);
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, restrict_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, fine, coarse));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, restrict_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, fine, coarse));
 }
 static int k_prolong_add(tgpu_hier *h, int l, const double *coarse, double *fine)
 {
 	LevelDev &L = h->levels[l];
 	Tag       tg(h->ctx, "prolong_add", l);
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, prolong_add_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, fine));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, prolong_add_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, fine));
 }
 static int k_prolong_faces(tgpu_hier *h, int l, const double *coarse, double *F)
 {
 	LevelDev &L = h->levels[l];
 	Tag       tg(h->ctx, "prolong_faces", l);
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, prolong_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, F));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, prolong_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, F));
 }
 static int k_set(tgpu_hier *h, double *v, size_t n, double alpha)
 {
@@ -1360,7 +1430,7 @@ static int p2p_push(tgpu_hier *h, int l, double *F, const double *uc)
 	if (L.nsend) {
 		Tag             tg(ctx, "p2p_push_faces", l);
 		double *const *pf = (F == L.Fa) ? L.peerFa : L.peerFb;
-		DISPATCH_DN(h->D, h->N, {
+		DISPATCH_DN_ALL(h->D, h->N, {
 			if (uc) TRY(launch(ctx, push_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
 			else TRY(launch(ctx, push_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
 		});
@@ -1390,7 +1460,7 @@ static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
 	for (int i = 0; i < h->D - 1; i++) M *= h->N;
 	Tag tg(ctx, "halo_exchange", l);
 	if (L.nsend) {
-		DISPATCH_DN(h->D, h->N, {
+		DISPATCH_DN_ALL(h->D, h->N, {
 			if (uc) TRY(launch(ctx, pack_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const double *) F, uc, L.sendbuf));
 			else TRY(launch(ctx, pack_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const double *) F, uc, L.sendbuf));
 		});
@@ -1405,7 +1475,7 @@ static int k_exchange(tgpu_hier *h, int l, double *F, const double *uc)
 	NC(g_nccl.GroupEnd());
 	}
 	if (L.nrecv) {
-		DISPATCH_DN(h->D, h->N, TRY(launch(ctx, unpack_faces_kernel<DD, NN>, dim3(grid_for(ctx, L.nrecv * M)), dim3(256), 0, (int) L.nrecv, (const int32_t *) L.recv_slot, (const int32_t *) L.recv_side, (const double *) L.recvbuf, F)));
+		DISPATCH_DN_ALL(h->D, h->N, TRY(launch(ctx, unpack_faces_kernel<DD, NN>, dim3(grid_for(ctx, L.nrecv * M)), dim3(256), 0, (int) L.nrecv, (const int32_t *) L.recv_slot, (const int32_t *) L.recv_side, (const double *) L.recvbuf, F)));
 	}
 	return TGPU_OK;
 }
@@ -1486,7 +1556,7 @@ extern "C" int tgpu_smooth_jacobi(tgpu_hier *h, int level, const tgpu_vec *f, tg
 	TRY(k_exchange(h, level, L.Fa, nullptr));
 	TRY(k_apply(h, level, 1, u->d, f->d, L.Fa, L.r, nullptr));
 	TRY(k_exchange_done(h, level));
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, jacobi_update_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, u->d, omega));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, jacobi_update_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, u->d, omega));
 	API_END
 }
 extern "C" int tgpu_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *fine, tgpu_vec *coarse)
@@ -1519,6 +1589,7 @@ extern "C" int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_v
 	TRY(k_extract_faces(h, fine_level, u->d, h->levels[fine_level].Fa));
 	TRY(k_exchange(h, fine_level, h->levels[fine_level].Fa, nullptr));
 	if (crosses_replication(h, fine_level)) TRY(k_set(h, coarse_f->d, coarse_f->n, 0.0));
+	if (is_3d32(h)) TRY(ensure_work(h, fine_level, true));
 	TRY(k_apply(h, fine_level, 2, u->d, f->d, h->levels[fine_level].Fa, nullptr, coarse_f->d));
 	TRY(k_exchange_done(h, fine_level));
 	if (crosses_replication(h, fine_level)) TRY(k_allreduce_sum(h, coarse_f->d, coarse_f->n));
@@ -1825,6 +1896,6 @@ extern "C" int tgpu_init_trig_rhs(tgpu_hier *h, tgpu_vec *f, tgpu_vec *exact)
 	if (exact) TRY(check_level_vec(h, 0, exact, "tgpu_init_trig_rhs"));
 	LevelDev &L = h->levels[0];
 	if (!L.starts) return fail(TGPU_ERR_ARG, "tgpu_init_trig_rhs: hierarchy was created without patch starts");
-	DISPATCH_DN(h->D, h->N, return launch(h->ctx, init_trig_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, exact ? exact->d : (double *) nullptr));
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, init_trig_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, exact ? exact->d : (double *) nullptr));
 	API_END
 }

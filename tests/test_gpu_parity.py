@@ -113,7 +113,8 @@ def test_residual_history_and_bicgstab_vs_reference(gcase):
 
 
 ORACLE_CASES = [("3uni.bin", 3, 16, 0), ("2refine.bin", 3, 16, 0), ("2refine.bin", 3, 8, 1), ("2d2ref.bin", 2, 32, 1),
-                ("2d_multi_refine_8.bin", 2, 16, 0), ("2d2uni.bin", 2, 32, 2), ("multi_refine.bin", 3, 8, 0)]
+                ("2d_multi_refine_8.bin", 2, 16, 0), ("2d2uni.bin", 2, 32, 2), ("multi_refine.bin", 3, 8, 0),
+                ("2uni.bin", 3, 32, 0), ("2refine.bin", 3, 32, 0)]  # 32^3 patches (BASELINE config D) have their own kernels
 
 
 @pytest.mark.parametrize("mesh_file,D,n,divide", ORACLE_CASES)
@@ -222,6 +223,8 @@ def test_error_behaviour(ctx):
         h.vcycle(u0, h.new_vec(0), pps.CycleOpts.default(cycle_type=7))
     with pytest.raises(pps.TgpuError):
         pps.Hierarchy.from_mesh(ctx, mesh, 6)  # unsupported patch size
+    with pytest.raises(pps.TgpuError):
+        pps.Hierarchy.from_mesh(ctx, mesh, 64)
     h.close()
     mesh.close()
 
