@@ -92,6 +92,9 @@ int tgpu_mesh_load(const char *path, int D, tgpu_mesh **mesh);
 int tgpu_mesh_uniform(int D, int num_levels, tgpu_mesh **mesh); /* unit domain, root = level 1 */
 int tgpu_mesh_refine_leaves(tgpu_mesh *mesh);
 int tgpu_mesh_refine_box(tgpu_mesh *mesh, const double *lo, const double *hi); /* refine leaves with centre in [lo, hi) */
+/* Neumann instead of Dirichlet conditions on every domain-boundary side of the levels extracted afterwards
+ * (ThundereggDomGen(tree, ns, neumann = true), ThundereggDomGen.h:92,216-220) */
+int tgpu_mesh_set_neumann(tgpu_mesh *mesh, int on);
 int tgpu_mesh_destroy(tgpu_mesh *mesh);
 int tgpu_mesh_info(const tgpu_mesh *mesh, int *D, int *num_levels, int *num_nodes);
 /* Extract every level (finest first) for n cells per patch side.  The returned descriptors stay

@@ -274,11 +274,18 @@ def extract_levels(tree, n):
     return levels
 
 
-def build_hierarchy(mesh_path, D, n, divide=0):
+def build_hierarchy(mesh_path, D, n, divide=0, neumann=False):
+    """neumann=True: ThundereggDomGen(tree, ns, neumann=true) marks every side without a neighbour
+    (ThundereggDomGen.h:216-220, PatchInfo::setNeumann PatchInfo.h:684-697)."""
     t = Tree.load(mesh_path, D)
     for _ in range(divide):
         t.refine_leaves()
-    return extract_levels(t, n)
+    levels = extract_levels(t, n)
+    if neumann:
+        for L in levels:
+            for s in range(2 * D):
+                L.neumann[L.nbr_type[:, s] == NBR_NONE] |= 1 << s
+    return levels
 
 
 # --------------------------------------------------------------------------------------------
@@ -479,7 +486,8 @@ def patch_solve(L, rhs, lam=0.0):
         denom = denom + lam
         for a in range(D):
             x = np.moveaxis(np.tensordot(x, mats[kinds[a][0]], axes=([D - a], [1])), -1, D - a)
-        x = x / denom
+        with np.errstate(divide="ignore", invalid="ignore"):  # zero mode of an all-Neumann patch, reset below
+            x = x / denom
         if bits == (1 << (2 * D)) - 1:
             x.reshape(sel.size, -1)[:, 0] = 0
         for a in range(D):

@@ -10,7 +10,8 @@
  * the RHS follows apps/3d/steady.cpp:253-265 / apps/2d/steady.cpp:314-316 through
  * Init::initDirichlet{,2d}.
  *
- * usage: ref_gmg D mesh.bin divide n dft|fftw cmd [cmd...]
+ * usage: ref_gmg D mesh.bin divide n dft|fftw[-neumann] cmd [cmd...]
+ *   (suffix -neumann: ThundereggDomGen(tree, ns, neumann = true), apps/3d/steady.cpp:301)
  *   meta:OUT                         hierarchy metadata (format: see dump_meta)
  *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
  *   apply:L:U_IN:OUT                 OUT = A_L U                (level 0 = finest)
@@ -202,6 +203,11 @@ template <size_t D> static int run(int argc, char **argv)
 	int    divide = atoi(argv[3]);
 	int    n      = atoi(argv[4]);
 	string solver = argv[5];
+	bool   neumann = false;
+	if (solver.size() > 8 && solver.substr(solver.size() - 8) == "-neumann") {
+		neumann = true;
+		solver  = solver.substr(0, solver.size() - 8);
+	}
 
 	auto t0 = chrono::steady_clock::now();
 	Tree<D> t(mesh);
@@ -210,7 +216,7 @@ template <size_t D> static int run(int argc, char **argv)
 	ns.fill(n);
 
 	Ctx<D> c;
-	c.dcg.reset(new ThundereggDomGen<D>(t, ns, false));
+	c.dcg.reset(new ThundereggDomGen<D>(t, ns, neumann));
 	shared_ptr<Domain<D>>        finest = c.dcg->getFinestDomain();
 	shared_ptr<PatchOperator<D>> p_op(new StarPatchOp<D>());
 	shared_ptr<IfaceInterp<D>>   p_interp(new typename Traits<D>::Interp());

@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
     "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
-    "tgpu_hierarchy_force_generic_kernels",
+    "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -132,6 +132,7 @@ for _name, _args in {
     "tgpu_comm_unique_id": [_vp], "tgpu_comm_init": [_vp, _vp, C.c_int, C.c_int],
     "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
     "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int],
+    "tgpu_mesh_set_neumann": [_vp, C.c_int],
 }.items():
     getattr(lib, _name).argtypes = _args
     getattr(lib, _name).restype = C.c_int
@@ -207,6 +208,10 @@ class Mesh:
     def refine_leaves(self, times=1):
         for _ in range(times):
             check(lib.tgpu_mesh_refine_leaves(self._p))
+        return self
+
+    def set_neumann(self, on=True):
+        check(lib.tgpu_mesh_set_neumann(self._p, 1 if on else 0))
         return self
 
     def refine_box(self, lo, hi):

@@ -411,6 +411,40 @@ template <int D, int N> __device__ __forceinline__ void prefetch_patch_l2(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Patches with Neumann domain sides (PatchSolvers/FftwPatchSolver.h:115-127, DftPatchSolver.h:115-127,150-165):
+// per axis the transform pair and eigenvalues depend on the two closures,
+//   Dirichlet/Dirichlet DST-II / DST-III, -4 sin^2((k+1) pi/2n)     Neumann/Neumann  DCT-II / DCT-III, -4 sin^2(k pi/2n)
+//   Neumann/Dirichlet   DCT-IV / DCT-IV,  -4 sin^2((k+1/2) pi/2n)   Dirichlet/Neumann DST-IV / DST-IV, same
+// They take a general path: dense n x n transforms with the matrices of DftPatchSolver.h:237-289 read from
+// a table (mats[kind][k][j], kinds in the order below) and the eigenvalue sum formed on the fly from
+// lam[shift kind][k]; an all-Neumann patch gets its zero mode removed (FftwPatchSolver.h:197).
+// ---------------------------------------------------------------------------------------------
+enum { TK_DST_II = 0, TK_DST_III = 1, TK_DCT_II = 2, TK_DCT_III = 3, TK_DCT_IV = 4, TK_DST_IV = 5 };
+struct AxisKind {
+	int fwd, inv, lam;
+};
+__device__ __forceinline__ AxisKind axis_kind(int neumann_bits, int axis)
+{
+	const bool lo = (neumann_bits >> (2 * axis)) & 1, hi = (neumann_bits >> (2 * axis + 1)) & 1;
+	if (lo && hi) return {TK_DCT_II, TK_DCT_III, 1};
+	if (lo) return {TK_DCT_IV, TK_DCT_IV, 2};
+	if (hi) return {TK_DST_IV, TK_DST_IV, 2};
+	return {TK_DST_II, TK_DST_III, 0};
+}
+// y_k = sum_j T[k][j] v_j, written straight into the pencil's shared-memory slots q[k * step]
+template <int N>
+__device__ __forceinline__ void dense_to_smem(const double *__restrict__ T, const double (&v)[N], double *q, int step)
+{
+#pragma unroll 1
+	for (int k = 0; k < N; k++) {
+		double acc = 0.0;
+#pragma unroll
+		for (int j = 0; j < N; j++) acc = fma(__ldg(T + k * N + j), v[j], acc);
+		q[k * step] = acc;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // block-Jacobi smoother: u_p <- S_p^-1 (f_p - (2/h^2) E^T gamma(F_in)),  one exact DST patch solve
 // per patch, all in shared memory / registers.  256 threads handle PPB = 256 / N^(D-1) patches.
 //   ZERO_GUESS: gamma == 0 (first sweep of a cycle, GMG/Cycle.h:118 u->set(0)), F_in is not read.
@@ -423,7 +457,7 @@ template <int D, int N, bool ZERO_GUESS, bool EMIT, bool PROLONG>
 __global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
 smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
               const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-              const double *__restrict__ uc)
+              const double *__restrict__ uc, const double *__restrict__ mats, const double *__restrict__ lam)
 {
 	// works on patches [p0, P) (multi-GPU: interior and boundary patches are separate launches)
 	// Persistent CTAs: each loops over groups of PPB patches (group g = blockIdx.x + k gridDim.x).
@@ -476,12 +510,14 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 
 		double *S = Sall + pp * G::SP;
 		double  cfac = 0.0, h2 = 0.0;
+		int     neu  = 0; // Neumann domain sides of this patch: != 0 takes the general transform path
 		int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
 		double  gam[6]   = {0, 0, 0, 0, 0, 0}; // (2/h^2) gamma of entry m on each side
 		if (valid) {
 			const PatchMeta &pm = meta[p];
 			cfac                = 2.0 * pm.inv_h2;
 			h2                  = pm.h2;
+			neu                 = pm.neumann;
 			if (!ZERO_GUESS) {
 				// entry m of every side is both produced and consumed by thread m: no staging needed
 				int    ty[G::S];
@@ -523,41 +559,70 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				if (ntype[G::S - 2] != NBR_NONE) v[0] -= gam[G::S - 2];
 				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= gam[G::S - 1];
 			}
-			dst2_forward<N>(v, mg);
+			if (neu) {
+				dense_to_smem<N>(mats + axis_kind(neu, D - 1).fwd * N * N, v, S + base, step);
+			} else {
+				dst2_forward<N>(v, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) S[base + k * step] = v[k];
+				for (int k = 0; k < N; k++) S[base + k * step] = v[k];
+			}
 		}
 		__syncthreads();
 		if (D == 3) { // forward along y: pencil (x, z)
 			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-			dst2_forward<N>(v, mg);
+			if (neu) {
+				dense_to_smem<N>(mats + axis_kind(neu, 1).fwd * N * N, v, S + base, G::ROW);
+			} else {
+				dst2_forward<N>(v, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+				for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			}
 			__syncthreads();
 		}
 		// ---- x: forward, divide by the eigenvalues, inverse (pencil = row m) ----
 		{
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
-			dst2_forward<N>(v, mg);
-			// eig is stored transposed, [k_x][row m], so that a warp reads consecutive doubles
-			const double *er = eig + m;
+			if (neu) {
+				const AxisKind kx = axis_kind(neu, 0), ky = axis_kind(neu, 1), kz = axis_kind(neu, 2);
+				dense_to_smem<N>(mats + kx.fwd * N * N, v, S + m * G::ROW, 1);
+				// eigenvalue sum of row m = (k_y, k_z) (2D: k_y) on the fly; scale (2/N)^D as in DftPatchSolver.h:214
+				const double rest  = (D == 2) ? __ldg(lam + ky.lam * N + m) : __ldg(lam + ky.lam * N + m % N) + __ldg(lam + kz.lam * N + m / N);
+				double       scale = h2;
 #pragma unroll
-			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
-			dst3_inverse<N>(v, mg);
+				for (int a = 0; a < D; a++) scale *= 2.0 / N;
+				const bool singular = neu == (1 << (2 * D)) - 1;
 #pragma unroll
-			for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
+				for (int k = 0; k < N; k++) {
+					const double sum = __ldg(lam + kx.lam * N + k) + rest;
+					v[k]             = (singular && k == 0 && m == 0) ? 0.0 : S[m * G::ROW + k] * scale / sum;
+				}
+				dense_to_smem<N>(mats + kx.inv * N * N, v, S + m * G::ROW, 1);
+			} else {
+				dst2_forward<N>(v, mg);
+				// eig is stored transposed, [k_x][row m], so that a warp reads consecutive doubles
+				const double *er = eig + m;
+#pragma unroll
+				for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
+				dst3_inverse<N>(v, mg);
+#pragma unroll
+				for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
+			}
 		}
 		__syncthreads();
 		if (D == 3) { // inverse along y
 			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-			dst3_inverse<N>(v, mg);
+			if (neu) {
+				dense_to_smem<N>(mats + axis_kind(neu, 1).inv * N * N, v, S + base, G::ROW);
+			} else {
+				dst3_inverse<N>(v, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+				for (int k = 0; k < N; k++) S[base + k * G::ROW] = v[k];
+			}
 			__syncthreads();
 		}
 		// ---- inverse along the last axis, write u (and the new faces) ----
@@ -566,8 +631,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			const int step = (D == 2) ? G::ROW : N * G::ROW;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+			if (neu) { // general path: transform through the pencil's own slots, then pick the result up again
+				dense_to_smem<N>(mats + axis_kind(neu, D - 1).inv * N * N, v, S + base, step);
+#pragma unroll
+				for (int k = 0; k < N; k++) v[k] = S[base + k * step];
+			}
 			__syncthreads(); // all reads of this buffer are done: the next iteration may refill it
-			dst3_inverse<N>(v, mg);
+			if (!neu) dst3_inverse<N>(v, mg);
 			if (valid) {
 				double *up = u + (size_t) p * G::NC + m;
 #pragma unroll

@@ -276,6 +276,9 @@ std::vector<HostLevel> Mesh::extractLevels(int n) const
 			}
 			for (int s = 0; s < S; s++) {
 				L.nbr_type[(size_t) k * S + s]       = r.type[s];
+				// ThundereggDomGen(..., neumann = true): every side on the domain boundary (ThundereggDomGen.h:216-220,
+				// PatchInfo::setNeumann PatchInfo.h:684-697 with an always-true predicate)
+				if (neumann && r.type[s] == TGPU_NBR_NONE) L.neumann[k] |= (uint8_t) (1u << s);
 				L.orth_on_coarse[(size_t) k * S + s] = r.orth[s];
 				for (int q = 0; q < Q; q++)
 					if (r.ids[s][q] >= 0) L.nbr_idx[((size_t) k * S + s) * Q + q] = local_of_id[r.ids[s][q]];

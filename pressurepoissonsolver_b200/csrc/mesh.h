@@ -39,6 +39,7 @@ class Mesh
 	int num_levels = 0;
 	int root       = -1;
 	int max_id     = -1;
+	bool neumann   = false; // Neumann instead of Dirichlet conditions on the whole domain boundary
 
 	std::vector<MeshNode> nodes; // indexed by id (ids are dense non-negative ints in every fixture)
 

@@ -209,6 +209,7 @@ struct tgpu_hier {
 	int                   D = 0, N = 0;
 	std::vector<LevelDev> levels;
 	double *              eig = nullptr; // [N^D]
+	double *              mats = nullptr, *lam = nullptr; // Neumann patches: transform matrices [6][N][N], 1-D eigenvalues [3][N]
 	std::vector<GraphEntry> graphs;
 	std::vector<tgpu_vec *> krylov_ws;
 	tgpu_vec *            host_f = nullptr, *host_u = nullptr;
@@ -564,6 +565,12 @@ extern "C" int tgpu_mesh_refine_box(tgpu_mesh *m, const double *lo, const double
 	return TGPU_OK;
 	API_END
 }
+extern "C" int tgpu_mesh_set_neumann(tgpu_mesh *m, int on)
+{
+	if (!m) return fail(TGPU_ERR_ARG, "null mesh");
+	m->mesh.neumann = on != 0;
+	return TGPU_OK;
+}
 extern "C" int tgpu_mesh_destroy(tgpu_mesh *m)
 {
 	delete m;
@@ -706,6 +713,26 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 			eig[(i % n) * M + i / n] = scale / sum;
 		}
 		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
+	}
+	// general transform path (patches with Neumann domain sides): the six matrices of DftPatchSolver.h:237-289,
+	// M[k][j] such that y_k = sum_j M[k][j] x_j, order TK_*; 1-D eigenvalues -4 sin^2((k + shift) pi / 2n), shift 1, 0, 1/2
+	{
+		std::vector<double> mats((size_t) 6 * n * n), lam((size_t) 3 * n);
+		auto M = [&](int kind, int k, int j) -> double & { return mats[((size_t) kind * n + k) * n + j]; };
+		for (int k = 0; k < n; k++)
+			for (int j = 0; j < n; j++) {
+				M(0, k, j) = sin(M_PI / n * ((k + 1) * (j + 0.5)));
+				M(1, k, j) = (j == n - 1) ? ((k % 2 == 0) ? 0.5 : -0.5) : sin(M_PI / n * ((k + 0.5) * (j + 1)));
+				M(2, k, j) = cos(M_PI / n * (k * (j + 0.5)));
+				M(3, k, j) = (j == 0) ? 0.5 : cos(M_PI / n * ((k + 0.5) * j));
+				M(4, k, j) = cos(M_PI / n * ((k + 0.5) * (j + 0.5)));
+				M(5, k, j) = sin(M_PI / n * ((k + 0.5) * (j + 0.5)));
+			}
+		const double shift[3] = {1.0, 0.0, 0.5};
+		for (int t = 0; t < 3; t++)
+			for (int k = 0; k < n; k++) lam[(size_t) t * n + k] = -4.0 * pow(sin((k + shift[t]) * M_PI / (2 * n)), 2);
+		TRY(dev_upload(&h->mats, mats.data(), mats.size()));
+		TRY(dev_upload(&h->lam, lam.data(), lam.size()));
 	}
 	if (D == 3 && n == 32) TRY(setup_3d32(h.get()));
 	else DISPATCH_DN(D, n, TRY((set_smem_attrs<DD, NN>())));
@@ -1061,6 +1088,8 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	cudaFree(h->arena);
 	cudaFree(h->p2p_err);
 	cudaFree(h->scratch32);
+	cudaFree(h->mats);
+	cudaFree(h->lam);
 	cudaFree(h->eig);
 	delete h;
 	return TGPU_OK;
@@ -1242,8 +1271,8 @@ static int check_level_vec(const tgpu_hier *h, int level, const tgpu_vec *v, con
 }
 static int need_smoother(const tgpu_hier *h, int level)
 {
-	if (h->levels[level].has_neumann)
-		return fail(TGPU_ERR_UNSUPPORTED, "patch solver: Neumann domain sides (DCT variants) are not implemented yet");
+	if (h->levels[level].has_neumann && is_3d32(h))
+		return fail(TGPU_ERR_UNSUPPORTED, "patch solver: Neumann domain sides are not implemented for 32^3 patches yet");
 	return TGPU_OK;
 }
 
@@ -1323,7 +1352,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		}
 #undef S32_CASE
 	}
-	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
+	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !L.has_neumann) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		switch (key) {
 		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
@@ -1345,12 +1374,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = h->eig;
-		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
-		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
-		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
-		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
-		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
-		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc);
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
 	});
 }
 // coarse = R (f - A u) for a u that a block-Jacobi sweep has just produced: needs only the faces of the new

@@ -13,6 +13,9 @@ GOLDEN_CASES = ["3d_2uni_n8", "3d_2refine_n8", "3d_2refine_d1_n4", "3d_multi_ref
                 "2d_2d2ref_d1_n8", "2d_multi_refine_8_n4"]
 
 
+NEUMANN_CASES = ["3d_2refine_n8_neumann", "2d_2d2ref_d1_n8_neumann", "3d_2uni_n16_neumann"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

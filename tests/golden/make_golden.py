@@ -38,7 +38,50 @@ def ref(D, mesh, div, n, *cmds, solver="dft"):
     subprocess.check_call([REF, str(D), os.path.join(HERE, "meshes", mesh), str(div), str(n), solver, *cmds])
 
 
+# Neumann domain boundaries (ThundereggDomGen(..., neumann = true)): per-level operator and smoother with both
+# patch solvers, and one V-cycle of a seeded right-hand side
+NEUMANN_CASES = [
+    ("3d_2refine_n8_neumann", 3, "2refine.bin", 0, 8),
+    ("2d_2d2ref_d1_n8_neumann", 2, "2d2ref.bin", 1, 8),
+    ("3d_2uni_n16_neumann", 3, "2uni.bin", 0, 16),
+]
+
+
+def neumann_cases():
+    for name, D, mesh, div, n in NEUMANN_CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            t = lambda f: os.path.join(tmp, f)  # noqa: E731
+            ref(D, mesh, div, n, "meta:" + t("meta"), solver="dft-neumann")
+            levels = go.read_ref_meta(t("meta"))
+            out = {"D": D, "n": n, "divide": div, "mesh": mesh, "nlevels": len(levels)}
+            rng = np.random.default_rng(4321)
+            for l, L in enumerate(levels):
+                out["L%d_neumann" % l] = L.neumann
+                u = rng.standard_normal(L.cells)
+                f = rng.standard_normal(L.cells)
+                u.tofile(t("u"))
+                f.tofile(t("ff"))
+                ref(D, mesh, div, n, "apply:%d:%s:%s" % (l, t("u"), t("au")),
+                    "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("su")), solver="dft-neumann")
+                ref(D, mesh, div, n, "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("su2")), solver="fftw-neumann")
+                out["L%d_in_u" % l], out["L%d_in_f" % l] = u, f
+                out["L%d_apply" % l] = np.fromfile(t("au"))
+                out["L%d_smooth" % l] = np.fromfile(t("su"))
+                out["L%d_smooth_fftw" % l] = np.fromfile(t("su2"))
+            f = rng.standard_normal(levels[0].cells)
+            f -= f.mean()  # compatible right-hand side (apps/3d/steady.cpp:330-334)
+            f.tofile(t("f"))
+            ref(D, mesh, div, n, "vcycle:%s:%s" % (t("f"), t("v")), solver="dft-neumann")
+            out["rhs_f"] = f
+            out["vcycle"] = np.fromfile(t("v"))
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+            print(name, [L.P for L in levels])
+
+
 def main():
+    if "--neumann-only" in sys.argv:
+        return neumann_cases()
+    neumann_cases()
     for name, D, mesh, div, n in CASES:
         with tempfile.TemporaryDirectory() as tmp:
             t = lambda f: os.path.join(tmp, f)  # noqa: E731

@@ -13,7 +13,7 @@ import pytest
 
 import gmg_oracle as go
 import pressurepoissonsolver_b200 as pps
-from conftest import GOLDEN_CASES, MESHES, ROOT, load_golden, rel_l2
+from conftest import GOLDEN_CASES, MESHES, NEUMANN_CASES, ROOT, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -183,6 +183,57 @@ def test_specialised_3d16_kernels_vs_generic(ctx, mesh_file, divide):
     assert rel_l2(res[False, "v32_u"], go.vcycle(levels, fn, pre=3, post=2)) < TOL
     h.close()
     mesh.close()
+
+
+@pytest.mark.parametrize("name", NEUMANN_CASES)
+def test_neumann_vs_reference(ctx, name):
+    """Neumann domain boundaries: per-level operator and smoother and the V-cycle against the reference's
+    golden vectors; the residual-from-faces schedule against the API-granular one."""
+    g = load_golden(name)
+    D, n = int(g["D"]), int(g["n"])
+    mesh = pps.Mesh.load(os.path.join(MESHES, str(g["mesh"])), D).set_neumann(True)
+    mesh.refine_leaves(int(g["divide"]))
+    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+    assert h.nlevels == int(g["nlevels"])
+    for l in range(h.nlevels):
+        u, f, out = h.new_vec(l, g["L%d_in_u" % l]), h.new_vec(l, g["L%d_in_f" % l]), h.new_vec(l)
+        h.apply(l, u, out)
+        assert rel_l2(out.download(), g["L%d_apply" % l]) < TOL
+        h.smooth(l, f, u)
+        assert rel_l2(u.download(), g["L%d_smooth" % l]) < 1e-11
+    f, u = h.new_vec(0, g["rhs_f"]), h.new_vec(0)
+    for fused in (1, 2, 0):
+        h.vcycle(f, u, pps.CycleOpts.default(fused=fused))
+        assert rel_l2(u.download(), g["vcycle"]) < 1e-10, fused
+    h.close()
+    mesh.close()
+
+
+def test_neumann_vs_oracle_seeded(ctx):
+    """larger Neumann cases against the oracle, incl. the D = 3, n = 16 size (which must leave its
+    specialised Dirichlet kernel for the general path) and multi-sweep cycles"""
+    for mesh_file, D, n, divide in (("2refine.bin", 3, 16, 0), ("2d_multi_refine_8.bin", 2, 32, 0), ("3uni.bin", 3, 4, 0)):
+        mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).set_neumann(True)
+        mesh.refine_leaves(divide)
+        h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+        levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), D, n, divide, neumann=True)
+        rng = np.random.default_rng(77)
+        for l, L in enumerate(levels):
+            un, fn = rng.standard_normal(L.shape), rng.standard_normal(L.shape)
+            u, f, out = h.new_vec(l, un), h.new_vec(l, fn), h.new_vec(l)
+            h.apply(l, u, out)
+            assert rel_l2(out.download(), go.apply_op(L, un)) < TOL
+            h.smooth(l, f, u)
+            assert rel_l2(u.download(), go.smooth(L, fn, un)) < 1e-11
+        fn = rng.standard_normal(levels[0].shape)
+        fn -= fn.mean()
+        f, u = h.new_vec(0, fn), h.new_vec(0)
+        h.vcycle(f, u)
+        assert rel_l2(u.download(), go.vcycle(levels, fn)) < 1e-10
+        h.vcycle(f, u, pps.CycleOpts.default(pre_sweeps=2, post_sweeps=2, coarse_sweeps=2))
+        assert rel_l2(u.download(), go.vcycle(levels, fn, pre=2, post=2, coarse_sweeps=2)) < 1e-10
+        h.close()
+        mesh.close()
 
 
 def test_blas1_and_reductions(ctx):

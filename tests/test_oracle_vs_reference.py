@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import gmg_oracle as go
-from conftest import GOLDEN_CASES, MESHES, load_golden, rel_l2
+from conftest import GOLDEN_CASES, MESHES, NEUMANN_CASES, load_golden, rel_l2
 
 TOL = 1e-13  # restatement vs reference: only fp re-association differs
 
@@ -61,6 +61,23 @@ def test_vcycle_and_solvers(case):
     x, its = go.bicgstab(levels, f)
     assert its == int(g["bicgstab_info"][0])
     assert rel_l2(x, g["bicgstab_u"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", NEUMANN_CASES)
+def test_neumann_boundaries(name):
+    """Neumann domain sides (DCT-II/III, DCT-IV, DST-IV patch solves, zero mode of the all-Neumann
+    coarsest patch): operator, smoother with both reference patch solvers, and a V-cycle."""
+    g = load_golden(name)
+    levels = go.build_hierarchy(os.path.join(MESHES, str(g["mesh"])), int(g["D"]), int(g["n"]), int(g["divide"]), neumann=True)
+    assert len(levels) == int(g["nlevels"])
+    for l, L in enumerate(levels):
+        assert np.array_equal(L.neumann, g["L%d_neumann" % l])
+        u = g["L%d_in_u" % l].reshape(L.shape)
+        f = g["L%d_in_f" % l].reshape(L.shape)
+        assert rel_l2(go.apply_op(L, u), g["L%d_apply" % l]) < TOL
+        assert rel_l2(go.smooth(L, f, u), g["L%d_smooth" % l]) < 1e-12
+        assert rel_l2(g["L%d_smooth_fftw" % l], g["L%d_smooth" % l]) < 1e-12
+    assert rel_l2(go.vcycle(levels, g["rhs_f"].reshape(levels[0].shape)), g["vcycle"]) < 1e-11
 
 
 def test_known_answers_from_reference_tests():
