@@ -62,6 +62,8 @@ class Mesh
 	Mesh(const Mesh &) = delete;
 	Mesh &operator=(const Mesh &) = delete;
 	void  refineLeaves() { check(tgpu_mesh_refine_leaves(p)); }
+	/* ThundereggDomGen(tree, ns, neumann = true) (ThundereggDomGen.h:92): Neumann conditions on the domain boundary */
+	void  setNeumann(bool on = true) { check(tgpu_mesh_set_neumann(p, on ? 1 : 0)); }
 };
 
 // the device-resident level hierarchy = what the reference's DomainGenerator + CycleFactory produce
