@@ -157,6 +157,11 @@ int tgpu_bicgstab(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_vec *f, tg
                   int *iterations, double *rel_residual);
 /* host-buffer convenience (the e2e path): f_host -> device, one cycle, u -> u_host */
 int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_pinned, double *u_pinned);
+/* pipelined form for a stream of independent right-hand sides: returns once the work is enqueued; upload of
+ * call k + 1, cycle k and download of result k - 1 overlap (two device slots, copy-in / copy-out streams).
+ * u_pinned of a call is valid after tgpu_vcycle_host_wait. */
+int tgpu_vcycle_host_async(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_pinned, double *u_pinned);
+int tgpu_vcycle_host_wait(tgpu_hier *h);
 
 /* ---- multi-GPU (one process per GPU): Morton partition of the patches + NCCL halo exchange ----
  * Replaces the reference's Zoltan partition / migration (ThundereggDomGen.h:223-648), the interface

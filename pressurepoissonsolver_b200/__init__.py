@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
     "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
-    "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann",
+    "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann", "tgpu_vcycle_host_async", "tgpu_vcycle_host_wait",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -133,6 +133,7 @@ for _name, _args in {
     "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
     "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int],
     "tgpu_mesh_set_neumann": [_vp, C.c_int],
+    "tgpu_vcycle_host_async": [_vp, C.POINTER(CycleOpts), _vp, _vp], "tgpu_vcycle_host_wait": [_vp],
 }.items():
     getattr(lib, _name).argtypes = _args
     getattr(lib, _name).restype = C.c_int
@@ -438,6 +439,13 @@ class Hierarchy:
 
     def vcycle_host(self, f_pinned, u_pinned, opts=None):
         check(lib.tgpu_vcycle_host(self._p, C.byref(opts) if opts is not None else None, f_pinned._p, u_pinned._p))
+
+    def vcycle_host_async(self, f_pinned, u_pinned, opts=None):
+        """pipelined form for a stream of independent right-hand sides; results are valid after vcycle_host_wait()"""
+        check(lib.tgpu_vcycle_host_async(self._p, C.byref(opts) if opts is not None else None, f_pinned._p, u_pinned._p))
+
+    def vcycle_host_wait(self):
+        check(lib.tgpu_vcycle_host_wait(self._p))
 
     def bicgstab(self, f, u, opts=None, tol=1e-12, max_it=1000, precondition=True):
         if precondition and opts is None:

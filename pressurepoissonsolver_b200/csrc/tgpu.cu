@@ -213,6 +213,11 @@ struct tgpu_hier {
 	std::vector<GraphEntry> graphs;
 	std::vector<tgpu_vec *> krylov_ws;
 	tgpu_vec *            host_f = nullptr, *host_u = nullptr;
+	// pipelined host-buffer path (tgpu_vcycle_host_async): two slots, copy-in / copy-out streams
+	tgpu_vec *            pipe_f[2] = {nullptr, nullptr}, *pipe_u[2] = {nullptr, nullptr};
+	cudaStream_t          s_in = nullptr, s_out = nullptr;
+	cudaEvent_t           ev_in[2] = {nullptr, nullptr}, ev_cyc[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+	uint64_t              pipe_count = 0;
 	bool                  generic_kernels = false; // test hook: force the size-generic smoother
 	// peer-to-peer arena: flag rows + the face buffers of the distributed levels, one IPC-exported allocation
 	void *                arena = nullptr;
@@ -1056,6 +1061,15 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	for (tgpu_vec *v : h->krylov_ws) tgpu_vec_destroy(v);
 	tgpu_vec_destroy(h->host_f);
 	tgpu_vec_destroy(h->host_u);
+	for (int k = 0; k < 2; k++) {
+		tgpu_vec_destroy(h->pipe_f[k]);
+		tgpu_vec_destroy(h->pipe_u[k]);
+		if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
+		if (h->ev_cyc[k]) cudaEventDestroy(h->ev_cyc[k]);
+		if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]);
+	}
+	if (h->s_in) cudaStreamDestroy(h->s_in);
+	if (h->s_out) cudaStreamDestroy(h->s_out);
 	for (LevelDev &L : h->levels) {
 		cudaFree(L.meta);
 		cudaFree(L.starts);
@@ -1849,6 +1863,57 @@ extern "C" int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const d
 	TRY(tgpu_vec_upload_async(h->host_f, f_host));
 	TRY(cycle_ptr(h, opts, h->host_f->d, h->host_u->d));
 	TRY(tgpu_vec_download_async(h->host_u, u_host));
+	CU(cudaStreamSynchronize(h->ctx->stream));
+	return TGPU_OK;
+	API_END
+}
+
+// Pipelined form of tgpu_vcycle_host for a stream of independent right-hand sides: the upload of call k + 1
+// runs on a copy-in stream while cycle k is on the main stream and result k - 1 travels back on a copy-out
+// stream (PCIe is full duplex), with two device slots.  The caller owns the pinned buffers; u_pinned of call k
+// is valid after tgpu_vcycle_host_wait, or after call k + 2 has returned and been waited for.
+extern "C" int tgpu_vcycle_host_async(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_host, double *u_host)
+{
+	API_BEGIN
+	if (!h || !f_host || !u_host) return fail(TGPU_ERR_ARG, "tgpu_vcycle_host_async: null argument");
+	tgpu_ctx *ctx = h->ctx;
+	if (!h->s_in) {
+		CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+		for (int k = 0; k < 2; k++) {
+			TRY(tgpu_vec_create(h, 0, &h->pipe_f[k]));
+			TRY(tgpu_vec_create(h, 0, &h->pipe_u[k]));
+			CU(cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&h->ev_cyc[k], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming));
+		}
+		CU(cudaStreamSynchronize(ctx->stream)); // the zero fills of the new vectors
+	}
+	const int    k     = (int) (h->pipe_count & 1);
+	const bool   first = h->pipe_count < 2;
+	const size_t bytes = h->pipe_f[k]->n * sizeof(double);
+	h->pipe_count++;
+	// copy-in: the cycle that last read this slot's f must be done
+	if (!first) CU(cudaStreamWaitEvent(h->s_in, h->ev_cyc[k], 0));
+	CU(cudaMemcpyAsync(h->pipe_f[k]->d, f_host, bytes, cudaMemcpyHostToDevice, h->s_in));
+	CU(cudaEventRecord(h->ev_in[k], h->s_in));
+	// cycle: needs this slot's f, and its u must have left for the host
+	CU(cudaStreamWaitEvent(ctx->stream, h->ev_in[k], 0));
+	if (!first) CU(cudaStreamWaitEvent(ctx->stream, h->ev_out[k], 0));
+	TRY(cycle_ptr(h, opts, h->pipe_f[k]->d, h->pipe_u[k]->d));
+	CU(cudaEventRecord(h->ev_cyc[k], ctx->stream));
+	// copy-out
+	CU(cudaStreamWaitEvent(h->s_out, h->ev_cyc[k], 0));
+	CU(cudaMemcpyAsync(u_host, h->pipe_u[k]->d, bytes, cudaMemcpyDeviceToHost, h->s_out));
+	CU(cudaEventRecord(h->ev_out[k], h->s_out));
+	return TGPU_OK;
+	API_END
+}
+extern "C" int tgpu_vcycle_host_wait(tgpu_hier *h)
+{
+	API_BEGIN
+	if (!h) return fail(TGPU_ERR_ARG, "null hierarchy");
+	if (h->s_out) CU(cudaStreamSynchronize(h->s_out));
 	CU(cudaStreamSynchronize(h->ctx->stream));
 	return TGPU_OK;
 	API_END
