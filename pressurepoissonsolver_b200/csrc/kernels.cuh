@@ -182,9 +182,12 @@ template <int NT> struct Dst3<NT, 1> {
 	__device__ static __forceinline__ void run(double (&v)[1], const Mags<NT> &) { v[0] *= 0.5; }
 };
 
+#ifndef TGPU_TABLE_DST32
+#define TGPU_TABLE_DST32 0 // 1: n = 32 uses the single-split table transforms instead of the recursion
+#endif
 template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N], const Mags<N> &mg)
 {
-	if (Mags<N>::IN_REGS) {
+	if (Mags<N>::IN_REGS || !TGPU_TABLE_DST32) {
 		Dst2<N, N>::run(v, mg);
 	} else { // one symmetric split with constant-bank coefficients
 		constexpr int H = N / 2;
@@ -205,7 +208,7 @@ template <int N> __device__ __forceinline__ void dst2_forward(double (&v)[N], co
 }
 template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N], const Mags<N> &mg)
 {
-	if (Mags<N>::IN_REGS) {
+	if (Mags<N>::IN_REGS || !TGPU_TABLE_DST32) {
 		Dst3<N, N>::run(v, mg);
 	} else {
 		constexpr int H = N / 2;
