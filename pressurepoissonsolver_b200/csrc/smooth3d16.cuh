@@ -134,15 +134,116 @@ template <bool PROLONG> struct SideGamma16 {
 	}
 };
 
-template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
+// Right-hand side of a coarse patch assembled straight from the FINER level's face buffer (first sweep of a
+// level visit in the fused cycle): f_c = R r with r = -(2/h^2) E^T gamma(u_fine) living on the fine patches'
+// boundary cells (see face_residual_restrict_kernel for the identity).  Replaces that kernel's launch and the
+// round trip of f_c through memory before the sweep; the assembled f_c is still stored (the level's later
+// sweeps read it).  Same expressions and summation order as face_residual_restrict_kernel.
+template <int MODE>
+__device__ __forceinline__ double gamma_entry16(const PatchMeta &pm, int p, int s, int m, const FaceVals<3, 16, MODE> &fv)
+{
+	const int ty = pm.nbr_type[s];
+	if (ty == NBR_NONE) return 0.0;
+	if (ty == NBR_NORMAL) {
+		const double a = fv.get(p, pm.parent_idx, pm.orth_on_parent, s, m);
+		const double b = fv.get(pm.nbr_idx[s][0], pm.nbr_parent[s], pm.nbr_orth[s], s ^ 1, m);
+		return 0.5 * a + 0.5 * b;
+	}
+	return iface_gamma<3, 16, MODE>(pm, p, s, m, fv);
+}
+struct FineSrc16 {
+	const PatchMeta *fmeta;    // neighbour table of the finer level
+	const double *   fF;       // its face buffer (boundary slices of the pre-smoothed u)
+	const int32_t *  children; // [coarse patch][8]: fine patch per octant; [1] == -2: [0] is the same patch on the finer level
+	double *         fc_out;   // where f_c is stored
+};
+__device__ __forceinline__ double fine_face_block16(const PatchMeta *__restrict__ fmeta, const double *__restrict__ fF, int q, int s, int m0)
+{
+	const PatchMeta &pq   = fmeta[q];
+	const int        ty   = pq.nbr_type[s];
+	const double     cfac = 2.0 * pq.inv_h2;
+	if (ty == NBR_NONE) return 0.0;
+	double r00, r01, r10, r11;
+	if (ty == NBR_NORMAL) {
+		const double *own = fF + ((size_t) q * 6 + s) * 256 + m0;
+		const double *nbp = fF + ((size_t) pq.nbr_idx[s][0] * 6 + (s ^ 1)) * 256 + m0;
+		const double2 a0 = __ldg(reinterpret_cast<const double2 *>(own)), a1 = __ldg(reinterpret_cast<const double2 *>(own + 16));
+		const double2 b0 = __ldg(reinterpret_cast<const double2 *>(nbp)), b1 = __ldg(reinterpret_cast<const double2 *>(nbp + 16));
+		r00 = cfac * (0.5 * -a0.x + 0.5 * -b0.x);
+		r01 = cfac * (0.5 * -a0.y + 0.5 * -b0.y);
+		r10 = cfac * (0.5 * -a1.x + 0.5 * -b1.x);
+		r11 = cfac * (0.5 * -a1.y + 0.5 * -b1.y);
+	} else {
+		const FaceVals<3, 16, FV_NEG> fv{fF, nullptr, fmeta};
+		r00 = cfac * iface_gamma<3, 16, FV_NEG>(pq, q, s, m0, fv);
+		r01 = cfac * iface_gamma<3, 16, FV_NEG>(pq, q, s, m0 + 1, fv);
+		r10 = cfac * iface_gamma<3, 16, FV_NEG>(pq, q, s, m0 + 16, fv);
+		r11 = cfac * iface_gamma<3, 16, FV_NEG>(pq, q, s, m0 + 17, fv);
+	}
+	return ((r00 + r01) + (r10 + r11)) / 8.0;
+}
+// all 256 threads of the CTA; S = tile of coarse patch p; ends with a CTA barrier
+__device__ __forceinline__ void build_tile_from_fine_faces16(double *S, const FineSrc16 &src, int p, int t)
+{
+	constexpr int ROW = S16_ROW, PL = S16_PL, N = 16;
+	const int lo = t & 15, hi = t >> 4;
+	{
+		double *q = S + lo + hi * ROW;
+#pragma unroll
+		for (int k = 0; k < N; k++) q[k * PL] = 0.0;
+	}
+	__syncthreads();
+	const int32_t *ch = src.children + (size_t) p * 8;
+	if (ch[1] == -2) { // the same patch exists on the finer level: f_c = r, entry t of every side
+		const int        q    = ch[0];
+		const PatchMeta &pq   = src.fmeta[q];
+		const double     cfac = 2.0 * pq.inv_h2;
+		const FaceVals<3, 16, FV_NEG> fv{src.fF, nullptr, src.fmeta};
+		double g[6];
+#pragma unroll
+		for (int s = 0; s < 6; s++) g[s] = cfac * gamma_entry16(pq, q, s, t, fv);
+		S[lo * ROW + hi * PL] += g[0];
+		S[N - 1 + lo * ROW + hi * PL] += g[1];
+		__syncthreads();
+		S[lo + hi * PL] += g[2];
+		S[lo + (N - 1) * ROW + hi * PL] += g[3];
+		__syncthreads();
+		S[lo + hi * ROW] += g[4];
+		S[lo + hi * ROW + (N - 1) * PL] += g[5];
+		__syncthreads();
+		return;
+	}
+	const int m0 = 2 * (lo & 7) + 32 * (hi & 7); // first of the 2 x 2 fine face entries under coarse plane cell (lo, hi)
+	const int oa = lo >> 3, ob = hi >> 3;
+#pragma unroll
+	for (int ax = 0; ax < 3; ax++) {
+		double val[4];
+#pragma unroll
+		for (int pl = 0; pl < 4; pl++) {
+			const int oc = pl >> 1, s = 2 * ax + (pl & 1); // planes 0, 7, 8, 15: octant bit, lower/upper side
+			const int o  = (ax == 0) ? (oc | (oa << 1) | (ob << 2)) : (ax == 1) ? (oa | (oc << 1) | (ob << 2)) : (oa | (ob << 1) | (oc << 2));
+			val[pl]      = fine_face_block16(src.fmeta, src.fF, ch[o], s, m0);
+		}
+#pragma unroll
+		for (int pl = 0; pl < 4; pl++) {
+			const int X   = (pl >> 1) * 8 + (pl & 1) * 7;
+			const int idx = (ax == 0) ? X + lo * ROW + hi * PL : (ax == 1) ? lo + X * ROW + hi * PL : lo + hi * ROW + X * PL;
+			S[idx] += val[pl];
+		}
+		__syncthreads();
+	}
+}
+
+template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false>
 __global__ void __launch_bounds__(TGPU_THREADS, 3)
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-                  const double *__restrict__ uc)
+                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{})
 {
 	constexpr int N = 16, ROW = S16_ROW, PL = S16_PL;
 	using G = Geo<3, 16>;
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
+	static_assert(!SRC_FINE || ZERO_GUESS, "only the first sweep of a level visit takes its right-hand side from the finer level");
 	extern __shared__ __align__(16) double smem[];
 	__shared__ uint64_t                    mbar[2];
 	// neighbour-table entry of the patch after the next (staged with cp.async) and the gather descriptors
@@ -185,7 +286,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 
 	int g = blockIdx.x;
 	if (g >= npatch) return;
-	prefetch(g, 0, false);
+	if (!SRC_FINE) prefetch(g, 0, false);
 	double gz0 = 0.0, gz1 = 0.0; // (2/h^2) gamma of entry t on the two z faces of the current patch
 	SideGamma16<PROLONG> sg;
 	if (!ZERO_GUESS) {
@@ -224,7 +325,10 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		const int       pn   = p0 + gn;  // patch whose gamma is gathered during this iteration
 		const GPatch16 &gp   = GD[b ^ 1]; // its descriptors
 		double          h2;
-		if (ZERO_GUESS) {
+		if (SRC_FINE) {
+			h2 = meta[p].h2;
+			build_tile_from_fine_faces16(S, src, p, t); // (tile b was last read two iterations ago)
+		} else if (ZERO_GUESS) {
 			h2 = meta[p].h2;
 			mbar_wait(&mbar[b], (it >> 1) & 1); // every thread's cp.async of this tile has landed
 		} else {
@@ -239,6 +343,11 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			double *q = S + lo + hi * ROW;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
+			if (SRC_FINE) { // the level's later sweeps read f_c from memory
+				double *fo = src.fc_out + (size_t) p * G::NC + t;
+#pragma unroll
+				for (int k = 0; k < N; k++) fo[k * G::M] = v[k];
+			}
 			if (!ZERO_GUESS) {
 				v[0] -= gz0;
 				v[N - 1] -= gz1;
@@ -265,7 +374,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (!ZERO_GUESS && next) gz1 = sg.finish(gp, 5, meta, pn, t, Fin, uc);
 		}
 		__syncthreads();
-		if (ZERO_GUESS && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
+		if (ZERO_GUESS && !SRC_FINE && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
 		{ // y forward, eigenvalues, y inverse: pencil (k_x, k_z) = (lo, hi)
 			double *q = S + lo + hi * PL;
 #pragma unroll

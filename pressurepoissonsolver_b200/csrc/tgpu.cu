@@ -187,6 +187,7 @@ struct LevelDev {
 	double *   Fa = nullptr, *Fb = nullptr; // face buffers
 	double *   u = nullptr, *f = nullptr, *r = nullptr; // cycle work vectors (lazily allocated)
 	bool       has_neumann = false;
+	int32_t *  children = nullptr; // [P][8] patches of the next finer level per octant ([1] == -2: [0] is the same patch there); null: incomplete
 	// peer-to-peer halo exchange: peers' face buffers and flags mapped with CUDA IPC (see setup_p2p)
 	bool       p2p = false;
 	int32_t *  send_peer = nullptr, *send_ridx = nullptr, *peer_rank = nullptr; // device: per send face / per peer
@@ -325,9 +326,9 @@ static bool supported_dn(int D, int N)
 	return (D == 2 && (N == 4 || N == 8 || N == 16 || N == 32)) || (D == 3 && (N == 4 || N == 8 || N == 16 || N == 32));
 }
 
-template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d16()
+template <bool Z, bool E, bool PR, bool W, bool SF = false> static int set_smem_attr_3d16()
 {
-	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes()));
 	return TGPU_OK;
 }
 static int set_smem_attrs_3d16()
@@ -341,6 +342,9 @@ static int set_smem_attrs_3d16()
 	TRY((set_smem_attr_3d16<false, true, true, true>()));
 	TRY((set_smem_attr_3d16<false, false, true, true>()));
 	TRY((set_smem_attr_3d16<false, true, true, false>()));
+	TRY((set_smem_attr_3d16<true, true, false, true, true>()));
+	TRY((set_smem_attr_3d16<true, false, false, true, true>()));
+	TRY((set_smem_attr_3d16<true, true, false, false, true>()));
 	return TGPU_OK;
 }
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d32()
@@ -702,6 +706,27 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 		CU(cudaMalloc(&L.Fb, L.nface * sizeof(double)));
 		h->levels.push_back(L);
 	}
+	// child tables (3D): lets a coarse sweep assemble its right-hand side from the finer level's faces (smooth3d16.cuh)
+	if (D == 3)
+		for (int l = 0; l + 1 < nlevels; l++) {
+			const TgpuLevelDesc &d  = levels[l];
+			LevelDev &           Lf = h->levels[l], &Lc = h->levels[l + 1];
+			if (!d.parent_idx || !d.orth_on_parent) continue;
+			std::vector<int32_t> ch((size_t) Lc.P * 8, -1);
+			bool                 ok = true;
+			for (int p = 0; p < Lf.P && ok; p++) {
+				const int c = d.parent_idx[p], o = d.orth_on_parent[p];
+				if (c < 0 || c >= Lc.P) ok = false; // parent is not an owned patch of the coarser level
+				else if (o < 0) ch[(size_t) c * 8] = p, ch[(size_t) c * 8 + 1] = -2;
+				else ch[(size_t) c * 8 + o] = p;
+			}
+			for (int c = 0; c < Lc.P && ok; c++) {
+				if (ch[(size_t) c * 8 + 1] == -2) continue;
+				for (int o = 0; o < 8; o++)
+					if (ch[(size_t) c * 8 + o] < 0) ok = false;
+			}
+			if (ok) TRY(dev_upload(&Lc.children, ch.data(), ch.size()));
+		}
 	// eigenvalue table: (2/n)^D / sum_axes(-4 sin^2((k+1) pi / (2n)))  [the 1/h^2 factor is applied per patch]
 	{
 		std::vector<double> lam(n), eig(NC);
@@ -1072,6 +1097,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	if (h->s_out) cudaStreamDestroy(h->s_out);
 	for (LevelDev &L : h->levels) {
 		cudaFree(L.meta);
+		cudaFree(L.children);
 		cudaFree(L.starts);
 		cudaFree(L.spacing);
 		if (!L.p2p) { // otherwise they live in the arena
@@ -1327,16 +1353,26 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 // zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout;
 // uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation);
 // write_u = false (needs emit): only the faces of the new u are wanted (the generic kernel still writes u)
-template <bool Z, bool E, bool PR, bool W>
+template <bool Z, bool E, bool PR, bool W, bool SF = false>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
-                             const double *uc)
+                             const double *uc, FineSrc16 src = FineSrc16{})
 {
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(S16_BLOCK);
-	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
-	              Fout, (const double *) h->eig, uc);
+	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
+	              Fout, (const double *) h->eig, uc, src);
+}
+// can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?
+// Opt-in (TGPU_FINE_SOURCE=1): measured on config B the assembly stage's dependent gathers (children -> neighbour
+// table -> faces, per axis) cost as much per patch as the separate face_residual_restrict launch they replace
+// (0.306 vs 0.279 ms per cycle), so the three-launch schedule stays the default.
+static bool can_source_from_fine(const tgpu_hier *h, int lc)
+{
+	static const bool enabled = getenv("TGPU_FINE_SOURCE") && atoi(getenv("TGPU_FINE_SOURCE")) != 0;
+	return enabled && lc >= 1 && h->D == 3 && h->N == 16 && !h->generic_kernels && h->ctx->nranks == 1 && h->levels[lc].children
+	       && !h->levels[lc].has_neumann;
 }
 static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout,
-                    const double *uc = nullptr, int p0 = 0, int p1 = -1, bool write_u = true)
+                    const double *uc = nullptr, int p0 = 0, int p1 = -1, bool write_u = true, const double *fine_faces = nullptr)
 {
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
@@ -1365,6 +1401,14 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
 		}
 #undef S32_CASE
+	}
+	if (fine_faces) { // right-hand side assembled from the finer level's faces and stored to f (see can_source_from_fine)
+		if (!zero_guess || !can_source_from_fine(h, l)) return fail(TGPU_ERR_ARG, "k_smooth: fine-face source not available");
+		Tag       tg2(h->ctx, write_u ? "smooth_zero_guess_from_fine" : "smooth_zero_guess_faces_from_fine", l);
+		FineSrc16 src{h->levels[l - 1].meta, fine_faces, L.children, const_cast<double *>(f)};
+		if (emit && write_u) return launch_smooth3d16<true, true, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
+		if (emit) return launch_smooth3d16<true, true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
+		return launch_smooth3d16<true, false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
 	}
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !L.has_neumann) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
@@ -1719,7 +1763,9 @@ static int exchange_async(tgpu_hier *h, int l, double *F, const double *uc, cuda
 // materialised: the zero fill of u, the pre-smoothed u itself, the fine residual vector and the interior
 // of the prolonged u; only the last sweep of a level visit writes u.  opts.fused = 2 keeps the PR-1 form
 // of the middle step (residual evaluated from u and f by apply_kernel<2>) for cross-checking.
-static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces)
+// fine_faces != nullptr: f has not been computed; the level's first sweep assembles it from the finer level's faces
+static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces,
+                       const double *fine_faces = nullptr)
 {
 	const int last = (int) h->levels.size() - 1;
 	LevelDev &L    = h->levels[l];
@@ -1728,7 +1774,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		for (int i = 0; i < o.coarse_sweeps; i++) {
 			const bool emit = (i + 1 < o.coarse_sweeps);
 			if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
-			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !emit));
+			TRY(k_smooth(h, l, i == 0, emit, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !emit, i == 0 ? fine_faces : nullptr));
 			if (i > 0) TRY(k_exchange_done(h, l));
 			if (i > 0 && emit) std::swap(Fcur, Falt);
 		}
@@ -1738,7 +1784,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	LevelDev & C          = h->levels[l + 1];
 	for (int i = 0; i < o.pre_sweeps; i++) {
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
-		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !from_faces));
+		TRY(k_smooth(h, l, i == 0, true, f, u, Fcur, i == 0 ? Fcur : Falt, nullptr, 0, -1, !from_faces, i == 0 ? fine_faces : nullptr));
 		if (i > 0) TRY(k_exchange_done(h, l));
 		if (i > 0) std::swap(Fcur, Falt);
 	}
@@ -1749,6 +1795,11 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		if (from_faces) return k_face_residual_restrict(h, l, Fcur, Fold, C.f, p0, p1);
 		return k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, p0, p1);
 	};
+	// residual + restriction fused into the coarser level's first sweep where that kernel exists
+	const bool defer = from_faces && !Fold && can_source_from_fine(h, l + 1);
+	if (defer) {
+		TRY(fused_visit(h, o, l + 1, C.f, C.u, false, Fcur));
+	} else {
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
 	if (overlap && L.p2p) {
 		// the faces of the pre-smoothed u go straight into the neighbours' halo slots; theirs arrive while
@@ -1769,6 +1820,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	}
 	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
+	}
 	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
 	if (overlap && L.p2p) TRY(p2p_push(h, l, Fcur, C.u));
 	else if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
