@@ -1246,6 +1246,143 @@ template <int OP> __global__ void reduce_stage2(int nb, const double *__restrict
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// BiCGStab (BiCGStab.h:45-106) with device-resident scalars: the vector updates of one iteration are fused
+// into three passes and the dot products ride along; the host reads one number (the residual norm) per
+// iteration.  Element-wise expressions are those of the Vector<D> ops the reference calls (Vector.h:218-262),
+// so the iterates match the op-by-op version up to the order of the reductions.
+//   sc[]: 0 rho, 1 alpha, 2 omega, 3 beta, 4 |r|, 5/6 reduction results
+// ---------------------------------------------------------------------------------------------
+enum { SC_RHO = 0, SC_ALPHA = 1, SC_OMEGA = 2, SC_BETA = 3, SC_RNORM = 4, SC_SUM0 = 5, SC_SUM1 = 6 };
+__device__ __forceinline__ void block_partials2(double a0, double a1, double *__restrict__ partial, int stride)
+{
+	__shared__ double ws[2][32];
+	a0 = warp_sum(a0);
+	a1 = warp_sum(a1);
+	if ((threadIdx.x & 31) == 0) {
+		ws[0][threadIdx.x >> 5] = a0;
+		ws[1][threadIdx.x >> 5] = a1;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double x0 = threadIdx.x < (blockDim.x >> 5) ? ws[0][threadIdx.x] : 0.0;
+		double x1 = threadIdx.x < (blockDim.x >> 5) ? ws[1][threadIdx.x] : 0.0;
+		x0        = warp_sum(x0);
+		x1        = warp_sum(x1);
+		if (threadIdx.x == 0) {
+			partial[blockIdx.x]          = x0;
+			partial[stride + blockIdx.x] = x1;
+		}
+	}
+}
+// partial[0][b] = sum a b, partial[1][b] = sum a a
+__global__ void bicg_dots_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ partial, int stride)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	double d0 = 0.0, d1 = 0.0;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		const double x = a[i];
+		d0             = fma(x, b[i], d0);
+		d1             = fma(x, x, d1);
+	}
+	block_partials2(d0, d1, partial, stride);
+}
+// s = r + ap (-alpha)      (s->copy(resid); s->addScaled(-alpha, ap))
+__global__ void bicg_s_kernel(size_t n, const double *__restrict__ r, const double *__restrict__ ap, double *__restrict__ s,
+                              const double *__restrict__ sc)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	const double na = -sc[SC_ALPHA];
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		double v = r[i];
+		v += ap[i] * na;
+		s[i] = v;
+	}
+}
+// x += alpha mp + omega ms;  r += -alpha ap - omega as;  partial sums of r.rhat and r.r
+__global__ void bicg_xr_kernel(size_t n, double *__restrict__ x, const double *__restrict__ mp, const double *__restrict__ ms,
+                               double *__restrict__ r, const double *__restrict__ ap, const double *__restrict__ as,
+                               const double *__restrict__ rhat, const double *__restrict__ sc, double *__restrict__ partial, int stride)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], na = -alpha, no = -omega;
+	double       d0 = 0.0, d1 = 0.0;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		double xv = x[i];
+		xv += mp[i] * alpha + ms[i] * omega;
+		x[i]      = xv;
+		double rv = r[i];
+		rv += ap[i] * na + as[i] * no;
+		r[i] = rv;
+		d0   = fma(rv, rhat[i], d0);
+		d1   = fma(rv, rv, d1);
+	}
+	block_partials2(d0, d1, partial, stride);
+}
+// p += -omega ap;  p = beta p + r
+__global__ void bicg_p_kernel(size_t n, double *__restrict__ p, const double *__restrict__ ap, const double *__restrict__ r,
+                              const double *__restrict__ sc)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	const double no = -sc[SC_OMEGA], beta = sc[SC_BETA];
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+		double v = p[i];
+		v += ap[i] * no;
+		p[i] = beta * v + r[i];
+	}
+}
+// finishes the two reductions (-> sc[SC_SUM0/1]) and, unless an all-reduce over the ranks has to come first,
+// updates the scalars of the given step (bicg_scalars)
+__device__ __forceinline__ void bicg_scalars(int step, double *sc)
+{
+	const double s0 = sc[SC_SUM0], s1 = sc[SC_SUM1];
+	if (step == 1) sc[SC_ALPHA] = sc[SC_RHO] / s0;                // alpha = rho / (rhat . ap)
+	else if (step == 2) sc[SC_OMEGA] = s0 / s1;                    // omega = (as . s) / (as . as)
+	else if (step == 3) {                                           // rho_new = r . rhat, beta, |r|
+		sc[SC_BETA]  = s0 * sc[SC_ALPHA] / (sc[SC_RHO] * sc[SC_OMEGA]);
+		sc[SC_RHO]   = s0;
+		sc[SC_RNORM] = sqrt(s1);
+	} else if (step == 0) {                                         // set-up: rho = rhat . r, |r|
+		sc[SC_RHO]   = s0;
+		sc[SC_RNORM] = sqrt(s1);
+	}
+}
+__global__ void bicg_finish_kernel(int nb, int stride, const double *__restrict__ partial, double *__restrict__ sc, int step, int update)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	double a0 = 0.0, a1 = 0.0;
+	for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+		a0 += partial[i];
+		a1 += partial[stride + i];
+	}
+	__shared__ double ws[2][32];
+	a0 = warp_sum(a0);
+	a1 = warp_sum(a1);
+	if ((threadIdx.x & 31) == 0) {
+		ws[0][threadIdx.x >> 5] = a0;
+		ws[1][threadIdx.x >> 5] = a1;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double x0 = 0.0, x1 = 0.0;
+		for (int w = 0; w < (int) (blockDim.x >> 5); w++) x0 += ws[0][w], x1 += ws[1][w];
+		sc[SC_SUM0] = x0;
+		sc[SC_SUM1] = x1;
+		if (update) bicg_scalars(step, sc);
+	}
+}
+__global__ void bicg_scalars_kernel(double *__restrict__ sc, int step)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	if (threadIdx.x == 0) bicg_scalars(step, sc);
+}
+
 // manufactured trig problem (apps/3d/steady.cpp:253-265, apps/2d/steady.cpp:314-316) with the
 // Dirichlet data folded into f on domain-boundary cells (apps/shared/Init.cpp:183-241,329-357)
 template <int D> __device__ __forceinline__ double trig_exact(double x, double y, double z)
