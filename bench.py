@@ -255,8 +255,11 @@ def main():
     # the library's pipelined entry point is used: upload of step k + 1, cycle k and download of step k - 1 overlap
     # (PCIe is full duplex); two pinned input and two pinned output buffers alternate.  The serial, one-call-at-a-time
     # form (tgpu_vcycle_host) is reported next to it.
-    fps, ups = [pps.PinnedBuffer(cells) for _ in range(2)], [pps.PinnedBuffer(cells) for _ in range(2)]
-    for b_ in fps:
+    # (one input buffer serves both slots when a vector exceeds 1 GB per rank: the right-hand sides are equal anyway)
+    fps = [pps.PinnedBuffer(cells)]
+    fps.append(pps.PinnedBuffer(cells) if cells * 8 <= (1 << 30) else fps[0])
+    ups = [pps.PinnedBuffer(cells) for _ in range(2)]
+    for b_ in fps[:1] if fps[1] is fps[0] else fps:
         b_.array[:] = f.download()
     for k in range(2):
         h.vcycle_host(fps[k], ups[k], opts)
