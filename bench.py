@@ -33,6 +33,10 @@ CONFIGS = {
     "D2": (3, "3uni.bin", 1, 32, "3uni.bin --divide 1, 512 patches of 32^3 (16,777,216 cells), 4 levels, trig RHS"),
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the two finest-level smoother launches of config B
+# (ncu --set full, profiles/r01_v7_ncu_full_summary.txt: 134.8 + 22.8 MB faces-only sweep, 205.6 + 90.8 MB post-sweep)
+NCU_TRAFFIC_BYTES = (134.8e6 + 22.8e6 + 205.6e6 + 90.8e6) / 2
+NCU_TRAFFIC_SOURCE = "profiles/r01_v7_ncu_full_summary.txt (mean of the two smoother launches on the finest level)"
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
 SMOOTH_BYTES_PER_CELL = 16.0      # dominant kernel: read f, write u
 
@@ -295,7 +299,8 @@ def main():
                    "parallelism": "1 GPU" if world == 1 else "%d GPUs: patches split along a Morton curve, NCCL halo-face exchange; %d cells on rank 0, %d in total" % (world, cells, total_cells)},
         "roofline": {"bound": "hbm", "kernel": "smooth_kernel (block-Jacobi DST patch solve) on the finest level (rank 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "ms_per_launch": dom_ms,
+                     "traffic": NCU_TRAFFIC_BYTES if (cfg == "B" and world == 1) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "peak_source": peak_src, "ms_per_launch": dom_ms,
                      "algorithmic_bytes_per_launch": SMOOTH_BYTES_PER_CELL * cells, "share_of_step": smooth_share,
                      "vcycle_algorithmic_gbs": cycle_gbs, "vcycle_frac": cycle_gbs / peak,
                      "vcycle_bytes_per_dof": cycle_bytes / cells},
