@@ -125,6 +125,8 @@ def main():
     ap.add_argument("--config", default="B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cycle-only", action="store_true", help="only the device-resident V-cycle timing (big single-GPU reference runs)")
+    ap.add_argument("--no-large-reference", action="store_true", help="skip the 1-GPU run of the N > 1 workload (config D16)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -220,75 +222,77 @@ def main():
     cycle_bytes = ALGO_BYTES_PER_CELL_VISIT * sum(level_cells)
     cycle_gbs = cycle_bytes / (ms_per_step * 1e-3) / 1e9
 
-    # ---- time to 1e-10 relative residual (north star): BiCGStab with the V-cycle as right preconditioner
-    # (apps/3d/steady.cpp:522, BiCGStab.h:45-106) and the stationary iteration u += V(f - A u), both from u = 0 ----
-    x, r, e = h.new_vec(0), h.new_vec(0), h.new_vec(0)
-    h.bicgstab(f, x, opts, tol=1e-10, max_it=100)  # warm-up (graph capture for the Krylov work vectors)
-    x.set(0.0)
-    ctx.sync()
-    t0 = time.perf_counter()
-    its, rel = h.bicgstab(f, x, opts, tol=1e-10, max_it=100)
-    ctx.sync()
-    bicg_ms = (time.perf_counter() - t0) * 1e3
-    fnorm = f.two_norm()
-    x.set(0.0)
-    ctx.sync()
-    t0 = time.perf_counter()
-    ncyc, srel = 0, 1.0
-    while srel > 1e-10 and ncyc < 100:
-        h.residual(0, f, x, r)
-        srel = r.two_norm() / fnorm
-        if srel <= 1e-10:
-            break
-        h.vcycle(r, e, opts)
-        x.add(e)
-        ncyc += 1
-    ctx.sync()
-    stat_ms = (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        t = torch.tensor([bicg_ms, stat_ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        bicg_ms, stat_ms = float(t[0]), float(t[1])
-    solve = {"tolerance": 1e-10, "bicgstab_ms": bicg_ms, "bicgstab_iterations": its, "bicgstab_rel_residual": rel,
-             "stationary_ms": stat_ms, "stationary_cycles": ncyc, "stationary_rel_residual": srel,
-             "note": "wall clock around the C-ABI calls, u = 0 start, includes the norm/dot host round trips"}
-    del x, r, e
+    solve, e2e_ms, serial_ms = None, float("nan"), float("nan")
+    if not args.cycle_only:
+        # ---- time to 1e-10 relative residual (north star): BiCGStab with the V-cycle as right preconditioner
+        # (apps/3d/steady.cpp:522, BiCGStab.h:45-106) and the stationary iteration u += V(f - A u), both from u = 0 ----
+        x, r, e = h.new_vec(0), h.new_vec(0), h.new_vec(0)
+        h.bicgstab(f, x, opts, tol=1e-10, max_it=100)  # warm-up (graph capture for the Krylov work vectors)
+        x.set(0.0)
+        ctx.sync()
+        t0 = time.perf_counter()
+        its, rel = h.bicgstab(f, x, opts, tol=1e-10, max_it=100)
+        ctx.sync()
+        bicg_ms = (time.perf_counter() - t0) * 1e3
+        fnorm = f.two_norm()
+        x.set(0.0)
+        ctx.sync()
+        t0 = time.perf_counter()
+        ncyc, srel = 0, 1.0
+        while srel > 1e-10 and ncyc < 100:
+            h.residual(0, f, x, r)
+            srel = r.two_norm() / fnorm
+            if srel <= 1e-10:
+                break
+            h.vcycle(r, e, opts)
+            x.add(e)
+            ncyc += 1
+        ctx.sync()
+        stat_ms = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([bicg_ms, stat_ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bicg_ms, stat_ms = float(t[0]), float(t[1])
+        solve = {"tolerance": 1e-10, "bicgstab_ms": bicg_ms, "bicgstab_iterations": its, "bicgstab_rel_residual": rel,
+                 "stationary_ms": stat_ms, "stationary_cycles": ncyc, "stationary_rel_residual": srel,
+                 "note": "wall clock around the C-ABI calls, u = 0 start, includes the norm/dot host round trips"}
+        del x, r, e
 
-    # ---- e2e: host buffers through the C-ABI.  Every step copies its own right-hand side from pinned host memory to
-    # the device and its result back (both inside the timed region).  The steps are independent right-hand sides, so
-    # the library's pipelined entry point is used: upload of step k + 1, cycle k and download of step k - 1 overlap
-    # (PCIe is full duplex); two pinned input and two pinned output buffers alternate.  The serial, one-call-at-a-time
-    # form (tgpu_vcycle_host) is reported next to it.
-    # (one input buffer serves both slots when a vector exceeds 1 GB per rank: the right-hand sides are equal anyway)
-    fps = [pps.PinnedBuffer(cells)]
-    fps.append(pps.PinnedBuffer(cells) if cells * 8 <= (1 << 30) else fps[0])
-    ups = [pps.PinnedBuffer(cells) for _ in range(2)]
-    for b_ in fps[:1] if fps[1] is fps[0] else fps:
-        b_.array[:] = f.download()
-    for k in range(2):
-        h.vcycle_host(fps[k], ups[k], opts)
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        h.vcycle_host(fps[k & 1], ups[k & 1], opts)
-    serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    for k in range(4):
-        h.vcycle_host_async(fps[k & 1], ups[k & 1], opts)
-    h.vcycle_host_wait()
-    if dist is not None:
-        dist.barrier()
-    pipe_steps = 2 * e2e_steps
-    t0 = time.perf_counter()
-    for k in range(pipe_steps):
-        h.vcycle_host_async(fps[k & 1], ups[k & 1], opts)
-    h.vcycle_host_wait()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / pipe_steps
-    if dist is not None:
-        t = torch.tensor([e2e_ms, serial_ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, serial_ms = float(t[0]), float(t[1])
-    u_ref = u.download()
-    assert np.array_equal(ups[0].array, u_ref) and np.array_equal(ups[1].array, u_ref)  # same f, same cycle, bit for bit
+        # ---- e2e: host buffers through the C-ABI.  Every step copies its own right-hand side from pinned host memory to
+        # the device and its result back (both inside the timed region).  The steps are independent right-hand sides, so
+        # the library's pipelined entry point is used: upload of step k + 1, cycle k and download of step k - 1 overlap
+        # (PCIe is full duplex); two pinned input and two pinned output buffers alternate.  The serial, one-call-at-a-time
+        # form (tgpu_vcycle_host) is reported next to it.
+        # (one input buffer serves both slots when a vector exceeds 1 GB per rank: the right-hand sides are equal anyway)
+        fps = [pps.PinnedBuffer(cells)]
+        fps.append(pps.PinnedBuffer(cells) if cells * 8 <= (1 << 30) else fps[0])
+        ups = [pps.PinnedBuffer(cells) for _ in range(2)]
+        for b_ in fps[:1] if fps[1] is fps[0] else fps:
+            b_.array[:] = f.download()
+        for k in range(2):
+            h.vcycle_host(fps[k], ups[k], opts)
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            h.vcycle_host(fps[k & 1], ups[k & 1], opts)
+        serial_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        for k in range(4):
+            h.vcycle_host_async(fps[k & 1], ups[k & 1], opts)
+        h.vcycle_host_wait()
+        if dist is not None:
+            dist.barrier()
+        pipe_steps = 2 * e2e_steps
+        t0 = time.perf_counter()
+        for k in range(pipe_steps):
+            h.vcycle_host_async(fps[k & 1], ups[k & 1], opts)
+        h.vcycle_host_wait()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / pipe_steps
+        if dist is not None:
+            t = torch.tensor([e2e_ms, serial_ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms, serial_ms = float(t[0]), float(t[1])
+        u_ref = u.download()
+        assert np.array_equal(ups[0].array, u_ref) and np.array_equal(ups[1].array, u_ref)  # same f, same cycle, bit for bit
 
     line = {
         "metric": "fp64 GMG V-cycle DOF/s", "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -313,11 +317,25 @@ def main():
         "clocks": sampler.summary(),
         "kernel_profile_ms_per_step": {"%s@L%d" % k: round(v[1] / args.steps, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
     }
+    if args.cycle_only:
+        line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_BIN):
         res = cpu_reference_run("small", 3, 1)
         line["cpu_baseline"] = {"value": res["dof_per_s"], "unit": "DOF/s", "cores": 1, "kind": "reference",
                                 "sample": "reference Cycle::apply (oracle/_ref/ref_gmg, DftPatchSolver, 1 rank = 1 core) on " + res["desc"]
                                           + "; median of 3 cycles after 1 warm-up; DOF/s per V-cycle is size-independent to ~5% (3.56e6 at 2.1M cells vs 3.42e6 at 16.8M cells measured in the build container)"}
+    if rank == 0 and world == 1 and cfg == "B" and not args.cycle_only and not args.no_large_reference:
+        # the N > 1 runs share the 1.07 B-cell mesh of config D (16^3 patches); its single-GPU number, measured here in a
+        # child process with the same kernels, is the denominator for strong-scaling efficiency on that mesh
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "D16", "--cycle-only", "--steps", "5", "--warmup", "3",
+                                  "--no-cpu-baseline"], capture_output=True, text=True, timeout=600).stdout
+            big = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+            line["large_mesh_reference"] = {"workload": big["config"]["workload"], "n_gpus": 1, "value": big["value"], "unit": "DOF/s",
+                                            "ms_per_step": big["ms_per_step"], "steps": big["steps"],
+                                            "vcycle_frac_of_hbm_roofline": big["roofline"]["vcycle_frac"]}
+        except Exception as ex:  # never let the extra line break the contract line
+            line["large_mesh_reference"] = {"error": str(ex)[:200]}
     if os.environ.get("BENCH_ALL_RANKS") and rank != 0:
         print("rank %d profile: %s" % (rank, json.dumps(line["kernel_profile_ms_per_step"])), file=sys.stderr, flush=True)
     if rank == 0:

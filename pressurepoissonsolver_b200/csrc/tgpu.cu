@@ -1629,8 +1629,9 @@ extern "C" int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec 
 static int ensure_work(tgpu_hier *h, int l, bool need_r)
 {
 	LevelDev &L = h->levels[l];
-	if (!L.u) CU(cudaMalloc(&L.u, L.ncells * sizeof(double)));
-	if (!L.f) CU(cudaMalloc(&L.f, L.ncells * sizeof(double)));
+	// the finest level works on the caller's f and u; r only exists for the API-granular schedule (GMG/Cycle.h:59)
+	if (l > 0 && !L.u) CU(cudaMalloc(&L.u, L.ncells * sizeof(double)));
+	if (l > 0 && !L.f) CU(cudaMalloc(&L.f, L.ncells * sizeof(double)));
 	if (need_r && !L.r) CU(cudaMalloc(&L.r, L.ncells * sizeof(double)));
 	return TGPU_OK;
 }
@@ -1864,7 +1865,8 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	tgpu_ctx *ctx = h->ctx;
 	for (size_t l = 0; l < h->levels.size(); l++) {
 		TRY(need_smoother(h, (int) l));
-		TRY(ensure_work(h, (int) l, true));
+		const bool fused_sched = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+		TRY(ensure_work(h, (int) l, !fused_sched || (o.fused == 2 && is_3d32(h))));
 	}
 	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u);
 	for (GraphEntry &g : h->graphs)
