@@ -13,8 +13,8 @@ HERE = os.path.join(ROOT, "pressurepoissonsolver_b200")
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtgpu.so")
 SOURCES = [os.path.join(CSRC, "tgpu.cu"), os.path.join(CSRC, "mesh.cpp")]
-DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "mesh.h"),
-                  os.path.join(ROOT, "include", "tgpu.h")]
+DEPS = SOURCES + [os.path.join(CSRC, n) for n in sorted(os.listdir(CSRC)) if n.endswith((".cuh", ".h"))] + [
+    os.path.join(ROOT, "include", "tgpu.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-cudart", "static"]

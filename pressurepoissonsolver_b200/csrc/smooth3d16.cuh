@@ -55,6 +55,53 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 	: "memory");
 }
 
+// Tridiagonal solve along one axis once the other two are diagonalised ("matrix decomposition": two transform
+// pairs + one Thomas solve instead of three transform pairs; same patch solve as FftwPatchSolver.h:174-206 /
+// DftPatchSolver.h:173-216 in exact arithmetic, 56 fp64 operations per pencil instead of 248).
+// For the pencil with transform indices (k_a, k_b) the remaining system is  M y = h^2 r,
+//   M = tridiag(1, d_j, 1),  d_j = mu - 2 (mu - 3 at both ends: the Dirichlet closure of StarPatchOp.h:46-64),
+//   mu = -4 sin^2((k_a+1) pi/2n) - 4 sin^2((k_b+1) pi/2n).
+// M is symmetric under j -> n-1-j, so it is eliminated from both ends towards the middle with ONE set of
+// multipliers a_0 = 1/d_0, a_j = 1/(d_j - a_{j-1}) (two independent dependency chains of n/2), leaving
+//   y_j + a_j y_{j+1} = rho_j (j < n/2),  y_{n-1-j} + a_j y_{n-2-j} = rho'_j,  and a 2 x 2 system in the middle.
+// tab[j * 256 + pencil] = a_j (j < n/2), tab[(n/2) * 256 + pencil] = 1 / (1 - a_{n/2-1}^2); the (2/n)^2 of the two
+// transform pairs (DftPatchSolver.h:214) and h^2 are folded into the right-hand side.
+#ifndef TGPU_S16_TRIDIAG
+#define TGPU_S16_TRIDIAG 1
+#endif
+template <int N> struct TriSolve {
+	static constexpr int H = N / 2;
+	// v -> (rho_0..rho_{H-1}, rho'_{H-1}..rho'_0), both scaled
+	__device__ static __forceinline__ void forward(double (&v)[N], const double *__restrict__ tab, double h2)
+	{
+		const double hs = h2 * (4.0 / (N * N));
+		double       a  = __ldg(tab);
+		double       sa = hs * a;
+		v[0]            = v[0] * sa;
+		v[N - 1]        = v[N - 1] * sa;
+#pragma unroll
+		for (int j = 1; j < H; j++) {
+			a            = __ldg(tab + j * 256);
+			sa           = hs * a;
+			v[j]         = fma(-a, v[j - 1], v[j] * sa);
+			v[N - 1 - j] = fma(-a, v[N - j], v[N - 1 - j] * sa);
+		}
+	}
+	__device__ static __forceinline__ void backward(double (&v)[N], const double *__restrict__ tab)
+	{
+		const double a = __ldg(tab + (H - 1) * 256), kap = __ldg(tab + H * 256);
+		const double yt = kap * fma(-a, v[H], v[H - 1]), yb = kap * fma(-a, v[H - 1], v[H]);
+		v[H - 1] = yt;
+		v[H]     = yb;
+#pragma unroll
+		for (int j = H - 2; j >= 0; j--) {
+			const double aj = __ldg(tab + j * 256);
+			v[j]            = fma(-aj, v[j + 1], v[j]);
+			v[N - 1 - j]    = fma(-aj, v[N - 2 - j], v[N - 1 - j]);
+		}
+	}
+};
+
 constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
 constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
 constexpr size_t smooth3d16_smem_bytes() { return sizeof(double) * 2 * S16_TILE; }
@@ -72,11 +119,14 @@ __device__ __noinline__ double iface_gamma_slow16(const PatchMeta *__restrict__ 
 //   (2/h^2) gamma = c (0.5 (a0[t] + a1[o]) + 0.5 (b0[t] + wb b1[o])),  o = the entry's offset on the coarse plane
 // a0/b0: own / neighbour face slice (FaceVals), a1/b1: the parent patches' cells under them
 // (DrctIntp.h:92-111; only read when the prolongation is fused in), c = 0 on sides without a neighbour,
-// wb = 0 for halo faces that already carry the correction.  Sides that need the general code
-// (coarse/fine neighbours, parents of equal size) are flagged in `slow`.
+// wb = 0 for halo faces that already carry the correction.  sa/sb: 1 = the parent is a refined patch (two
+// entries per coarse cell, o = entry >> 1 per axis), 0 = the "parent" is the same patch on the coarser level
+// (leaves of an adaptive mesh that are not at the finest tree level: copy-add, DrctIntp.h:107-110).
+// Sides that need the general code (coarse/fine neighbours) are flagged in `slow`.
 struct GDesc16 {
 	const double *a0, *b0, *a1, *b1;
 	double        c, wb;
+	int           sa, sb;
 };
 struct GPatch16 {
 	GDesc16 d[6];
@@ -96,32 +146,38 @@ __device__ __forceinline__ void make_gdesc16(const PatchMeta &pm, int p, int s, 
 	d.a1 = d.b1 = PROLONG ? uc : F;
 	d.c         = (ty == NBR_NONE) ? 0.0 : 2.0 * pm.inv_h2;
 	d.wb        = 1.0;
+	d.sa = d.sb = 1;
 	if (ty == NBR_NORMAL) {
 		d.b0 = F + ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 256;
 		if (PROLONG) {
 			const int o = pm.orth_on_parent, qp = pm.nbr_parent[s], qo = pm.nbr_orth[s];
-			if (o < 0 || (qp >= 0 && qo < 0)) slow = true;
-			d.a1 = uc + (size_t) pm.parent_idx * 4096 + 8 * ((o & 1) + 16 * ((o >> 1) & 1) + 256 * ((o >> 2) & 1)) + ((s & 1) ? 7 * st : 0);
-			if (qp >= 0) d.b1 = uc + (size_t) qp * 4096 + 8 * ((qo & 1) + 16 * ((qo >> 1) & 1) + 256 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 7 * st);
-			else d.b1 = d.a1, d.wb = 0.0;
+			if (o >= 0) d.a1 = uc + (size_t) pm.parent_idx * 4096 + 8 * ((o & 1) + 16 * ((o >> 1) & 1) + 256 * ((o >> 2) & 1)) + ((s & 1) ? 7 * st : 0);
+			else d.a1 = uc + (size_t) pm.parent_idx * 4096 + ((s & 1) ? 15 * st : 0), d.sa = 0;
+			if (qp < 0) d.b1 = d.a1, d.sb = d.sa, d.wb = 0.0;
+			else if (qo >= 0) d.b1 = uc + (size_t) qp * 4096 + 8 * ((qo & 1) + 16 * ((qo >> 1) & 1) + 256 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 7 * st);
+			else d.b1 = uc + (size_t) qp * 4096 + ((s & 1) ? 0 : 15 * st), d.sb = 0;
 		}
 	}
 	if (slow) {
 		d.a0 = d.b0 = F + ((size_t) p * 6 + s) * 256; // harmless addresses; the value comes from iface_gamma_slow16
 		d.a1 = d.b1 = PROLONG ? uc : F;
+		d.sa = d.sb = 1;
 	}
 	out.slow[s] = slow;
 }
 template <bool PROLONG> struct SideGamma16 {
 	double a0, a1, b0, b1;
-	__device__ __forceinline__ void issue(const GDesc16 &d, int t, int off)
+	// AX: face-normal axis; entry t = (lo, hi) lies over cell (lo >> s) * A + (hi >> s) * B of the parent's plane
+	template <int AX> __device__ __forceinline__ void issue(const GDesc16 &d, int t, int lo, int hi)
 	{
+		constexpr int A = (AX == 0) ? 16 : 1, B = (AX == 2) ? 16 : 256;
 		a0 = __ldg(d.a0 + t);
 		b0 = __ldg(d.b0 + t);
 		a1 = b1 = 0.0;
 		if (PROLONG) {
-			a1 = __ldg(d.a1 + off);
-			b1 = __ldg(d.b1 + off);
+			const int sa = d.sa, sb = d.sb;
+			a1 = __ldg(d.a1 + ((lo >> sa) * A + (hi >> sa) * B));
+			b1 = __ldg(d.b1 + ((lo >> sb) * A + (hi >> sb) * B));
 		}
 	}
 	__device__ __forceinline__ double finish(const GPatch16 &gp, int s, const PatchMeta *__restrict__ meta, int p, int t,
@@ -253,8 +309,6 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	__shared__ GPatch16             GD[2];
 	const int t = threadIdx.x, lo = t & 15, hi = t >> 4;
 	const int npatch = P - p0;
-	// offset of entry t's cell on the parent's plane, per face-normal axis
-	const int off[3] = {(lo >> 1) * 16 + (hi >> 1) * 256, (lo >> 1) + (hi >> 1) * 256, (lo >> 1) + (hi >> 1) * 16};
 	if (t == 0) {
 		mbar_init(&mbar[0], TGPU_THREADS);
 		mbar_init(&mbar[1], TGPU_THREADS);
@@ -298,12 +352,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		double gx[4];
 #pragma unroll
 		for (int s = 0; s < 4; s++) {
-			sg.issue(GD[0].d[s], t, off[s >> 1]);
+			if (s < 2) sg.template issue<0>(GD[0].d[s], t, lo, hi);
+			else sg.template issue<1>(GD[0].d[s], t, lo, hi);
 			gx[s] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
 		}
-		sg.issue(GD[0].d[4], t, off[2]);
+		sg.template issue<2>(GD[0].d[4], t, lo, hi);
 		gz0 = sg.finish(GD[0], 4, meta, p, t, Fin, uc);
-		sg.issue(GD[0].d[5], t, off[2]);
+		sg.template issue<2>(GD[0].d[5], t, lo, hi);
 		gz1 = sg.finish(GD[0], 5, meta, p, t, Fin, uc);
 		mbar_wait(&mbar[0], 0);
 		// x faces: entry t = (y, z) = (lo, hi); y faces: entry t = (x, z) = (lo, hi); they share edge cells
@@ -351,7 +406,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (!ZERO_GUESS) {
 				v[0] -= gz0;
 				v[N - 1] -= gz1;
-				if (next) sg.issue(gp.d[4], t, off[2]);
+				if (next) sg.template issue<2>(gp.d[4], t, lo, hi);
 			}
 			dst2_forward<N>(v, mg);
 #pragma unroll
@@ -367,7 +422,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
-			if (!ZERO_GUESS && next) sg.issue(gp.d[5], t, off[2]);
+			if (!ZERO_GUESS && next) sg.template issue<2>(gp.d[5], t, lo, hi);
 			dst2_forward<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
@@ -375,21 +430,30 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		}
 		__syncthreads();
 		if (ZERO_GUESS && !SRC_FINE && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
-		{ // y forward, eigenvalues, y inverse: pencil (k_x, k_z) = (lo, hi)
+		{ // y: pencil (k_x, k_z) = (lo, hi)
 			double *q = S + lo + hi * PL;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * ROW];
-			if (!ZERO_GUESS && next) sg.issue(gp.d[0], t, off[0]);
+			if (!ZERO_GUESS && next) sg.template issue<0>(gp.d[0], t, lo, hi);
+#if TGPU_S16_TRIDIAG
+			// z and x are diagonalised: what is left per (k_x, k_z) is a tridiagonal system along y
+			TriSolve<N>::forward(v, eig + t, h2);
+#else
 			dst2_forward<N>(v, mg);
 			const double *er = eig + t; // eig[k_y * 256 + k_x + 16 k_z] (the table is symmetric in the axes)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
+#endif
 			double gx0 = 0.0, gx1 = 0.0;
 			if (!ZERO_GUESS && next) {
 				gx0 = sg.finish(gp, 0, meta, pn, t, Fin, uc);
-				sg.issue(gp.d[1], t, off[0]);
+				sg.template issue<0>(gp.d[1], t, lo, hi);
 			}
+#if TGPU_S16_TRIDIAG
+			TriSolve<N>::backward(v, eig + t);
+#else
 			dst3_inverse<N>(v, mg);
+#endif
 #pragma unroll
 			for (int k = 0; k < N; k++) q[k * ROW] = v[k];
 			if (!ZERO_GUESS && next) {
@@ -411,7 +475,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
-			if (!ZERO_GUESS && next) sg.issue(gp.d[2], t, off[1]);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[2], t, lo, hi);
 			dst3_inverse<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
@@ -422,7 +486,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			double *q = S + lo + hi * ROW; // z inverse: pencil (x, y) = (lo, hi)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
-			if (!ZERO_GUESS && next) sg.issue(gp.d[3], t, off[1]);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi);
 			dst3_inverse<N>(v, mg);
 			double *up = u + (size_t) p * G::NC + t;
 #pragma unroll
@@ -450,7 +514,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			}
 		} else {
 			__syncthreads();
-			if (!ZERO_GUESS && next) sg.issue(gp.d[3], t, off[1]);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi);
 			// Only the boundary-cell slices of u are needed.  Warp 0: the x = 0 and x = 15 columns, warp 1:
 			// the y = 0 and y = 15 rows (+ 4 interior pencils): full inverse transform; warps 2-7: the other
 			// 192 interior pencils, z-face values only:

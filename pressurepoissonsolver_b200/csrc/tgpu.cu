@@ -210,6 +210,7 @@ struct tgpu_hier {
 	int                   D = 0, N = 0;
 	std::vector<LevelDev> levels;
 	double *              eig = nullptr; // [N^D]
+	double *              tri = nullptr; // D = 3: [N/2 + 1][N^2] tridiagonal multipliers (TriSolve)
 	double *              mats = nullptr, *lam = nullptr; // Neumann patches: transform matrices [6][N][N], 1-D eigenvalues [3][N]
 	std::vector<GraphEntry> graphs;
 	std::vector<tgpu_vec *> krylov_ws;
@@ -744,6 +745,28 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 			eig[(i % n) * M + i / n] = scale / sum;
 		}
 		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
+		// D = 3: multipliers of the two-sided tridiagonal elimination along y for every (k_x, k_z) (TriSolve, smooth3d16.cuh)
+		if (D == 3) {
+			const int                H = n / 2;
+			std::vector<double>      tri((size_t) (H + 1) * n * n);
+			std::vector<long double> ll(n);
+			for (int k = 0; k < n; k++) {
+				const long double sn = sinl((k + 1) * 3.141592653589793238462643383279502884L / (2 * n));
+				ll[k]                = -4.0L * sn * sn;
+			}
+			for (int kz = 0; kz < n; kz++)
+				for (int kx = 0; kx < n; kx++) {
+					const long double mu = ll[kx] + ll[kz];
+					long double       a  = 0.0L;
+					for (int j = 0; j < H; j++) {
+						const long double d = mu - (j == 0 ? 3.0L : 2.0L);
+						a                   = 1.0L / (d - (j == 0 ? 0.0L : a));
+						tri[(size_t) j * n * n + kx + n * kz] = (double) a;
+					}
+					tri[(size_t) H * n * n + kx + n * kz] = (double) (1.0L / (1.0L - a * a));
+				}
+			TRY(dev_upload(&h->tri, tri.data(), tri.size()));
+		}
 	}
 	// general transform path (patches with Neumann domain sides): the six matrices of DftPatchSolver.h:237-289,
 	// M[k][j] such that y_k = sum_j M[k][j] x_j, order TK_*; 1-D eigenvalues -4 sin^2((k + shift) pi / 2n), shift 1, 0, 1/2
@@ -1133,6 +1156,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	cudaFree(h->mats);
 	cudaFree(h->lam);
 	cudaFree(h->eig);
+	cudaFree(h->tri);
 	delete h;
 	return TGPU_OK;
 }
@@ -1361,7 +1385,7 @@ static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, co
 {
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(S16_BLOCK);
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
-	              Fout, (const double *) h->eig, uc, src);
+	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src);
 }
 // can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?
 // Opt-in (TGPU_FINE_SOURCE=1): measured on config B the assembly stage's dependent gathers (children -> neighbour
