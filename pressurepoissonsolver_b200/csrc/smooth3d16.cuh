@@ -104,7 +104,16 @@ template <int N> struct TriSolve {
 
 constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
 constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
-constexpr size_t smooth3d16_smem_bytes() { return sizeof(double) * 2 * S16_TILE; }
+// Sweeps from a zero guess have no interface values to fold into the right-hand side, so f needs no staging:
+// it is loaded straight into the z pencils (the next patch is pulled into L2 meanwhile), one tile per CTA and
+// 64 registers per thread let four CTAs share an SM.  The other variants stage f with cp.async in a second
+// tile (the boundary cells are updated in place there) and run three CTAs per SM.
+__host__ __device__ constexpr bool   s16_direct(bool zero_guess, bool src_fine) { return zero_guess && !src_fine; }
+__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return s16_direct(zero_guess, src_fine) ? 4 : 3; }
+__host__ __device__ constexpr size_t smooth3d16_smem_bytes(bool zero_guess = false, bool src_fine = false)
+{
+	return sizeof(double) * (s16_direct(zero_guess, src_fine) ? 1 : 2) * S16_TILE;
+}
 
 // refinement-boundary sides are rare: keep their (large) code out of line
 template <bool PROLONG>
@@ -123,69 +132,79 @@ __device__ __noinline__ double iface_gamma_slow16(const PatchMeta *__restrict__ 
 // entries per coarse cell, o = entry >> 1 per axis), 0 = the "parent" is the same patch on the coarser level
 // (leaves of an adaptive mesh that are not at the finest tree level: copy-add, DrctIntp.h:107-110).
 // Sides that need the general code (coarse/fine neighbours) are flagged in `slow`.
-struct GDesc16 {
-	const double *a0, *b0, *a1, *b1;
-	double        c, wb;
-	int           sa, sb;
+struct __align__(16) GDesc16 {
+	unsigned a0, b0, a1, b1; // element offsets into F (a0, b0) and into uc (a1, b1; F when no prolongation is fused in)
+	double   c;
+	int      flags, pad;
 };
+enum { GD_SA = 1, GD_SB = 2, GD_WB = 4, GD_SLOW = 8 };
 struct GPatch16 {
 	GDesc16 d[6];
 	double  h2;
-	int     slow[6]; // side needs iface_gamma_slow16
 };
 template <bool PROLONG>
-__device__ __forceinline__ void make_gdesc16(const PatchMeta &pm, int p, int s, const double *__restrict__ F,
-                                             const double *__restrict__ uc, GPatch16 &out)
+__device__ __forceinline__ void make_gdesc16(const PatchMeta &pm, int p, int s, GPatch16 &out)
 {
 	GDesc16 &  d   = out.d[s];
 	const int  ty  = pm.nbr_type[s];
 	const int  ax  = s >> 1;
 	const int  st  = (ax == 0) ? 1 : (ax == 1 ? 16 : 256); // stride of the face-normal axis
 	bool       slow = ty > NBR_NORMAL;
-	d.a0 = d.b0 = F + ((size_t) p * 6 + s) * 256;
-	d.a1 = d.b1 = PROLONG ? uc : F;
+	d.a0 = d.b0 = ((unsigned) p * 6 + s) * 256;
+	d.a1 = d.b1 = 0;
 	d.c         = (ty == NBR_NONE) ? 0.0 : 2.0 * pm.inv_h2;
-	d.wb        = 1.0;
-	d.sa = d.sb = 1;
+	int fl      = GD_SA | GD_SB | GD_WB;
 	if (ty == NBR_NORMAL) {
-		d.b0 = F + ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 256;
+		d.b0 = ((unsigned) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 256;
 		if (PROLONG) {
 			const int o = pm.orth_on_parent, qp = pm.nbr_parent[s], qo = pm.nbr_orth[s];
-			if (o >= 0) d.a1 = uc + (size_t) pm.parent_idx * 4096 + 8 * ((o & 1) + 16 * ((o >> 1) & 1) + 256 * ((o >> 2) & 1)) + ((s & 1) ? 7 * st : 0);
-			else d.a1 = uc + (size_t) pm.parent_idx * 4096 + ((s & 1) ? 15 * st : 0), d.sa = 0;
-			if (qp < 0) d.b1 = d.a1, d.sb = d.sa, d.wb = 0.0;
-			else if (qo >= 0) d.b1 = uc + (size_t) qp * 4096 + 8 * ((qo & 1) + 16 * ((qo >> 1) & 1) + 256 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 7 * st);
-			else d.b1 = uc + (size_t) qp * 4096 + ((s & 1) ? 0 : 15 * st), d.sb = 0;
+			if (o >= 0) d.a1 = (unsigned) pm.parent_idx * 4096 + 8 * ((o & 1) + 16 * ((o >> 1) & 1) + 256 * ((o >> 2) & 1)) + ((s & 1) ? 7 * st : 0);
+			else d.a1 = (unsigned) pm.parent_idx * 4096 + ((s & 1) ? 15 * st : 0), fl &= ~GD_SA;
+			if (qp < 0) d.b1 = d.a1, fl = (fl & ~(GD_SB | GD_WB)) | ((fl & GD_SA) ? GD_SB : 0);
+			else if (qo >= 0) d.b1 = (unsigned) qp * 4096 + 8 * ((qo & 1) + 16 * ((qo >> 1) & 1) + 256 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 7 * st);
+			else d.b1 = (unsigned) qp * 4096 + ((s & 1) ? 0 : 15 * st), fl &= ~GD_SB;
 		}
 	}
 	if (slow) {
-		d.a0 = d.b0 = F + ((size_t) p * 6 + s) * 256; // harmless addresses; the value comes from iface_gamma_slow16
-		d.a1 = d.b1 = PROLONG ? uc : F;
-		d.sa = d.sb = 1;
+		d.a0 = d.b0 = ((unsigned) p * 6 + s) * 256; // harmless addresses; the value comes from iface_gamma_slow16
+		d.a1 = d.b1 = 0;
+		fl          = GD_SA | GD_SB | GD_WB | GD_SLOW;
 	}
-	out.slow[s] = slow;
+	d.flags = fl;
 }
 template <bool PROLONG> struct SideGamma16 {
 	double a0, a1, b0, b1;
 	// AX: face-normal axis; entry t = (lo, hi) lies over cell (lo >> s) * A + (hi >> s) * B of the parent's plane
-	template <int AX> __device__ __forceinline__ void issue(const GDesc16 &d, int t, int lo, int hi)
+	template <int AX>
+	__device__ __forceinline__ void issue(const GDesc16 &d, int t, int lo, int hi, const double *__restrict__ F, const double *__restrict__ uc)
 	{
 		constexpr int A = (AX == 0) ? 16 : 1, B = (AX == 2) ? 16 : 256;
-		a0 = __ldg(d.a0 + t);
-		b0 = __ldg(d.b0 + t);
+		const uint4   o = *reinterpret_cast<const uint4 *>(&d);
+		a0 = __ldg(F + o.x + t);
+		b0 = __ldg(F + o.y + t);
 		a1 = b1 = 0.0;
 		if (PROLONG) {
-			const int sa = d.sa, sb = d.sb;
-			a1 = __ldg(d.a1 + ((lo >> sa) * A + (hi >> sa) * B));
-			b1 = __ldg(d.b1 + ((lo >> sb) * A + (hi >> sb) * B));
+			const int fl = d.flags, sa = fl & GD_SA, sb = (fl >> 1) & 1;
+#if S16_ABL == 1
+			a1 = __ldg(uc + o.z + t + sa);
+			b1 = __ldg(uc + o.w + t + sb);
+#elif S16_ABL == 2
+			a1 = (double) (o.z + sa);
+			b1 = (double) (o.w + sb);
+#else
+			a1 = __ldg(uc + o.z + ((lo >> sa) * A + (hi >> sa) * B));
+			b1 = __ldg(uc + o.w + ((lo >> sb) * A + (hi >> sb) * B));
+#endif
 		}
 	}
 	__device__ __forceinline__ double finish(const GPatch16 &gp, int s, const PatchMeta *__restrict__ meta, int p, int t,
 	                                         const double *__restrict__ F, const double *__restrict__ uc) const
 	{
-		const GDesc16 &d = gp.d[s];
-		double         g = d.c * (0.5 * (a0 + a1) + 0.5 * (b0 + d.wb * b1));
-		if (gp.slow[s]) g = d.c * iface_gamma_slow16<PROLONG>(meta, p, s, t, F, uc);
+		const GDesc16 &d  = gp.d[s];
+		const double   c  = d.c;
+		const int      fl = d.flags;
+		double         g  = c * (0.5 * (a0 + a1) + 0.5 * (b0 + ((fl & GD_WB) ? b1 : 0.0)));
+		if (fl & GD_SLOW) g = c * iface_gamma_slow16<PROLONG>(meta, p, s, t, F, uc);
 		return g;
 	}
 };
@@ -291,7 +310,7 @@ __device__ __forceinline__ void build_tile_from_fine_faces16(double *S, const Fi
 }
 
 template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false>
-__global__ void __launch_bounds__(TGPU_THREADS, 3)
+__global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE))
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
                   const double *__restrict__ uc, FineSrc16 src = FineSrc16{})
@@ -334,13 +353,14 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	};
 	// one thread per side (lane 31 of warps 0-5) resolves the descriptors of patch q into GD[slot]
 	auto describe = [&](const PatchMeta &pm, int q, int slot) {
-		if ((t & 31) == 31 && t < 6 * 32) make_gdesc16<PROLONG>(pm, q, t >> 5, Fin, uc, GD[slot]);
+		if ((t & 31) == 31 && t < 6 * 32) make_gdesc16<PROLONG>(pm, q, t >> 5, GD[slot]);
 		if (t == 6 * 32 + 31) GD[slot].h2 = pm.h2;
 	};
 
 	int g = blockIdx.x;
 	if (g >= npatch) return;
-	if (!SRC_FINE) prefetch(g, 0, false);
+	constexpr bool DIRECT = s16_direct(ZERO_GUESS, SRC_FINE); // f goes straight from memory into the z pencils, one tile
+	if (!SRC_FINE && !DIRECT) prefetch(g, 0, false);
 	double gz0 = 0.0, gz1 = 0.0; // (2/h^2) gamma of entry t on the two z faces of the current patch
 	SideGamma16<PROLONG> sg;
 	if (!ZERO_GUESS) {
@@ -352,13 +372,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		double gx[4];
 #pragma unroll
 		for (int s = 0; s < 4; s++) {
-			if (s < 2) sg.template issue<0>(GD[0].d[s], t, lo, hi);
-			else sg.template issue<1>(GD[0].d[s], t, lo, hi);
+			if (s < 2) sg.template issue<0>(GD[0].d[s], t, lo, hi, Fin, uc);
+			else sg.template issue<1>(GD[0].d[s], t, lo, hi, Fin, uc);
 			gx[s] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
 		}
-		sg.template issue<2>(GD[0].d[4], t, lo, hi);
+		sg.template issue<2>(GD[0].d[4], t, lo, hi, Fin, uc);
 		gz0 = sg.finish(GD[0], 4, meta, p, t, Fin, uc);
-		sg.template issue<2>(GD[0].d[5], t, lo, hi);
+		sg.template issue<2>(GD[0].d[5], t, lo, hi, Fin, uc);
 		gz1 = sg.finish(GD[0], 5, meta, p, t, Fin, uc);
 		mbar_wait(&mbar[0], 0);
 		// x faces: entry t = (y, z) = (lo, hi); y faces: entry t = (x, z) = (lo, hi); they share edge cells
@@ -372,7 +392,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	}
 	for (int it = 0; g < npatch; g += gridDim.x, it++) {
 		const int       b    = it & 1;
-		double *        S    = smem + b * S16_TILE;
+		double *        S    = smem + (DIRECT ? 0 : b) * S16_TILE;
 		double *        Sn   = smem + (b ^ 1) * S16_TILE;
 		const int       p    = p0 + g;
 		const int       gn   = g + gridDim.x;
@@ -383,6 +403,9 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		if (SRC_FINE) {
 			h2 = meta[p].h2;
 			build_tile_from_fine_faces16(S, src, p, t); // (tile b was last read two iterations ago)
+		} else if (DIRECT) {
+			h2 = meta[p].h2;
+			__syncthreads(); // the previous patch's last stage has read the tile
 		} else if (ZERO_GUESS) {
 			h2 = meta[p].h2;
 			mbar_wait(&mbar[b], (it >> 1) & 1); // every thread's cp.async of this tile has landed
@@ -396,8 +419,17 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		double v[N];
 		{ // z forward: pencil (x, y) = (lo, hi)
 			double *q = S + lo + hi * ROW;
+			if (DIRECT) {
+				const double *fp = f + (size_t) p * G::NC + t;
 #pragma unroll
-			for (int k = 0; k < N; k++) v[k] = q[k * PL];
+				for (int k = 0; k < N; k++) v[k] = __ldcs(fp + k * G::M);
+				if (next) { // pull the next patch into L2 while this one is transformed: 256 lines of 128 bytes
+					prefetch_l2(f + (size_t) pn * G::NC + t * 16);
+				}
+			} else {
+#pragma unroll
+				for (int k = 0; k < N; k++) v[k] = q[k * PL];
+			}
 			if (SRC_FINE) { // the level's later sweeps read f_c from memory
 				double *fo = src.fc_out + (size_t) p * G::NC + t;
 #pragma unroll
@@ -406,7 +438,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (!ZERO_GUESS) {
 				v[0] -= gz0;
 				v[N - 1] -= gz1;
-				if (next) sg.template issue<2>(gp.d[4], t, lo, hi);
+				if (next) sg.template issue<2>(gp.d[4], t, lo, hi, Fin, uc);
 			}
 			dst2_forward<N>(v, mg);
 #pragma unroll
@@ -422,19 +454,19 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
-			if (!ZERO_GUESS && next) sg.template issue<2>(gp.d[5], t, lo, hi);
+			if (!ZERO_GUESS && next) sg.template issue<2>(gp.d[5], t, lo, hi, Fin, uc);
 			dst2_forward<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
 			if (!ZERO_GUESS && next) gz1 = sg.finish(gp, 5, meta, pn, t, Fin, uc);
 		}
 		__syncthreads();
-		if (ZERO_GUESS && !SRC_FINE && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
+		if (ZERO_GUESS && !SRC_FINE && !DIRECT && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
 		{ // y: pencil (k_x, k_z) = (lo, hi)
 			double *q = S + lo + hi * PL;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * ROW];
-			if (!ZERO_GUESS && next) sg.template issue<0>(gp.d[0], t, lo, hi);
+			if (!ZERO_GUESS && next) sg.template issue<0>(gp.d[0], t, lo, hi, Fin, uc);
 #if TGPU_S16_TRIDIAG
 			// z and x are diagonalised: what is left per (k_x, k_z) is a tridiagonal system along y
 			TriSolve<N>::forward(v, eig + t, h2);
@@ -447,7 +479,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			double gx0 = 0.0, gx1 = 0.0;
 			if (!ZERO_GUESS && next) {
 				gx0 = sg.finish(gp, 0, meta, pn, t, Fin, uc);
-				sg.template issue<0>(gp.d[1], t, lo, hi);
+				sg.template issue<0>(gp.d[1], t, lo, hi, Fin, uc);
 			}
 #if TGPU_S16_TRIDIAG
 			TriSolve<N>::backward(v, eig + t);
@@ -475,7 +507,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j]        = d.x;
 				v[2 * j + 1]    = d.y;
 			}
-			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[2], t, lo, hi);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[2], t, lo, hi, Fin, uc);
 			dst3_inverse<N>(v, mg);
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
@@ -486,7 +518,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			double *q = S + lo + hi * ROW; // z inverse: pencil (x, y) = (lo, hi)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
-			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi, Fin, uc);
 			dst3_inverse<N>(v, mg);
 			double *up = u + (size_t) p * G::NC + t;
 #pragma unroll
@@ -514,7 +546,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			}
 		} else {
 			__syncthreads();
-			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi);
+			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi, Fin, uc);
 			// Only the boundary-cell slices of u are needed.  Warp 0: the x = 0 and x = 15 columns, warp 1:
 			// the y = 0 and y = 15 rows (+ 4 interior pencils): full inverse transform; warps 2-7: the other
 			// 192 interior pencils, z-face values only:

@@ -1383,8 +1383,8 @@ template <bool Z, bool E, bool PR, bool W, bool SF = false>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
                              const double *uc, FineSrc16 src = FineSrc16{})
 {
-	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 3)), block(S16_BLOCK);
-	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
+	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * s16_ctas_per_sm(Z, SF))), block(S16_BLOCK);
+	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
 	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src);
 }
 // can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?

@@ -92,12 +92,14 @@ int main(int argc, char **argv)
 	attr(smooth3d16_kernel<false, false, true, true>);
 	attr(smooth3d16_kernel<false, false, false, true>);
 	attr(smooth3d16_kernel<false, true, false, false>);
-	const int grid = std::min(P, sms * 3);
+	const int grid = std::min(P, sms * s16_ctas_per_sm(false, false));
 	const dim3 blk(S16_BLOCK);
 	printf("G=%d P=%d cells=%zu grid=%d\n", G, P, nc, grid);
 	const double b16 = 16.0 * nc;
-	time_it("zero_guess faces-only", reps, b16, [&] { smooth3d16_kernel<true, true, false, false><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
-	time_it("zero_guess write_u", reps, b16, [&] { smooth3d16_kernel<true, false, false, true><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
+	const size_t smz = smooth3d16_smem_bytes(true, false);
+	const int    gridz = std::min(P, sms * s16_ctas_per_sm(true, false));
+	time_it("zero_guess faces-only", reps, b16, [&] { smooth3d16_kernel<true, true, false, false><<<gridz, blk, smz>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
+	time_it("zero_guess write_u", reps, b16, [&] { smooth3d16_kernel<true, false, false, true><<<gridz, blk, smz>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
 	time_it("plain gamma write_u", reps, b16, [&] { smooth3d16_kernel<false, false, false, true><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
 	time_it("plain gamma faces-only", reps, b16, [&] { smooth3d16_kernel<false, true, false, false><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
 	if (G > 1) time_it("prolong gamma write_u", reps, b16, [&] { smooth3d16_kernel<false, false, true, true><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
