@@ -10,14 +10,17 @@
 //   * transform order z, x, (y forward, eigenvalues, y inverse), x, z with warp w owning the rows
 //     y in {2w, 2w+1}: the z<->x transposes stay inside a warp (__syncwarp instead of a CTA barrier),
 //     leaving two CTA barriers around the y phase (+1 when gamma has to be subtracted first);
-//   * f streams in with 16-byte cp.async into the second buffer, completion tracked by an mbarrier
-//     (cp.async.mbarrier.arrive), so "the tile has landed" costs no CTA barrier;
+//   * f is loaded straight from memory into the z pencils (a warp's load covers two whole 128-byte lines) while
+//     a prefetch pulls the next patch into L2: no staging tile, one tile per CTA; sweeps from a zero guess fit
+//     64 registers and run four CTAs per SM, the others three;
+//   * the y axis is not transformed: with z and x diagonalised each (k_x, k_z) pencil is a tridiagonal system,
+//     solved by a two-sided elimination with tabulated multipliers (TriSolve, 56 operations instead of 248);
 //   * the interface values gamma of the NEXT patch are gathered one side per transform: the four loads
 //     of a side (own face, neighbour face, and the coarse correction under both when the prolongation
 //     is fused in) are issued before a transform and combined after it, so their L2/HBM latency hides
-//     behind ~116 DFMAs instead of stalling the whole CTA at the top of an iteration; x- and y-face
-//     values are subtracted in place from the next tile (already landed), z-face values wait in
-//     two registers;
+//     behind the transform instead of stalling the whole CTA at the top of an iteration; x- and y-face
+//     values wait in a 8 KB shared-memory face buffer and are subtracted from the boundary pencils right
+//     after the next patch's load, z-face values wait in two registers;
 //   * WRITE_U = false (sweeps whose u is only ever seen through its boundary slices: every sweep but
 //     the last of a level visit in the fused cycle): the last inverse transform is evaluated in full
 //     only for the 60 pencils on the patch boundary (warps 0-1); the other pencils compute just their
@@ -31,30 +34,6 @@ __device__ __forceinline__ void     cp_async16(double *smem_dst, const double *g
 {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-// the executing thread's arrival fires once all of its earlier cp.async have landed
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar)
-{
-	asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-	asm volatile(
-	"{\n"
-	".reg .pred p;\n"
-	"TGPU_MBAR_WAIT:\n"
-	"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	"@p bra TGPU_MBAR_DONE;\n"
-	"bra TGPU_MBAR_WAIT;\n"
-	"TGPU_MBAR_DONE:\n"
-	"}\n" ::"r"(smem_u32(bar)),
-	"r"(parity)
-	: "memory");
-}
-
 // Tridiagonal solve along one axis once the other two are diagonalised ("matrix decomposition": two transform
 // pairs + one Thomas solve instead of three transform pairs; same patch solve as FftwPatchSolver.h:174-206 /
 // DftPatchSolver.h:173-216 in exact arithmetic, 56 fp64 operations per pencil instead of 248).
@@ -102,14 +81,16 @@ template <int N> struct TriSolve {
 	}
 };
 
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
 constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
 // Sweeps from a zero guess have no interface values to fold into the right-hand side, so f needs no staging:
 // it is loaded straight into the z pencils (the next patch is pulled into L2 meanwhile), one tile per CTA and
 // 64 registers per thread let four CTAs share an SM.  The other variants stage f with cp.async in a second
 // tile (the boundary cells are updated in place there) and run three CTAs per SM.
-__host__ __device__ constexpr bool   s16_direct(bool zero_guess, bool src_fine) { return zero_guess && !src_fine; }
-__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return s16_direct(zero_guess, src_fine) ? 4 : 3; }
+__host__ __device__ constexpr bool   s16_direct(bool, bool src_fine) { return !src_fine; }
+__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return (zero_guess && !src_fine) ? 4 : 3; }
 __host__ __device__ constexpr size_t smooth3d16_smem_bytes(bool zero_guess = false, bool src_fine = false)
 {
 	return sizeof(double) * (s16_direct(zero_guess, src_fine) ? 1 : 2) * S16_TILE;
@@ -320,37 +301,21 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
 	static_assert(!SRC_FINE || ZERO_GUESS, "only the first sweep of a level visit takes its right-hand side from the finer level");
 	extern __shared__ __align__(16) double smem[];
-	__shared__ uint64_t                    mbar[2];
 	// neighbour-table entry of the patch after the next (staged with cp.async) and the gather descriptors
 	// of the current / next patch derived from it
 	constexpr int                   MW = (int) (sizeof(PatchMeta) / sizeof(double));
 	__shared__ __align__(16) double metaS[MW];
 	__shared__ GPatch16             GD[2];
+	// (2/h^2) gamma on the x and y faces of the patch about to be solved, entry t of side s at Gs[s * 256 + t]
+	// (the z-face values stay in the registers of the thread that needs them)
+	__shared__ double Gs[ZERO_GUESS ? 1 : 4 * 256];
 	const int t = threadIdx.x, lo = t & 15, hi = t >> 4;
 	const int npatch = P - p0;
-	if (t == 0) {
-		mbar_init(&mbar[0], TGPU_THREADS);
-		mbar_init(&mbar[1], TGPU_THREADS);
-	}
-	__syncthreads();
 	Mags<N> mg;
 	mg.load();
 	pdl_launch_dependents();
 	pdl_wait();
 
-	// f of patch g -> tile b; with_meta: also the table entry of the patch after it -> metaS
-	auto prefetch = [&](int g, int b, bool with_meta) {
-		const double *src = f + (size_t) (p0 + g) * G::NC;
-		double *      dst = smem + b * S16_TILE;
-#pragma unroll
-		for (int i = 0; i < 8; i++) {
-			const int c = t + TGPU_THREADS * i, row = c >> 3; // 16-byte chunk c of the patch, row = y + 16 z
-			cp_async16(dst + (row & 15) * ROW + (row >> 4) * PL + (c & 7) * 2, src + c * 2);
-		}
-		if (with_meta && t < MW && g + (int) gridDim.x < npatch)
-			cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + p0 + g + gridDim.x) + t, true);
-		cp_async_mbar_arrive(&mbar[b]);
-	};
 	// one thread per side (lane 31 of warps 0-5) resolves the descriptors of patch q into GD[slot]
 	auto describe = [&](const PatchMeta &pm, int q, int slot) {
 		if ((t & 31) == 31 && t < 6 * 32) make_gdesc16<PROLONG>(pm, q, t >> 5, GD[slot]);
@@ -360,7 +325,6 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	int g = blockIdx.x;
 	if (g >= npatch) return;
 	constexpr bool DIRECT = s16_direct(ZERO_GUESS, SRC_FINE); // f goes straight from memory into the z pencils, one tile
-	if (!SRC_FINE && !DIRECT) prefetch(g, 0, false);
 	double gz0 = 0.0, gz1 = 0.0; // (2/h^2) gamma of entry t on the two z faces of the current patch
 	SideGamma16<PROLONG> sg;
 	if (!ZERO_GUESS) {
@@ -369,31 +333,20 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		describe(meta[p], p, 0);
 		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
 		__syncthreads();
-		double gx[4];
 #pragma unroll
 		for (int s = 0; s < 4; s++) {
 			if (s < 2) sg.template issue<0>(GD[0].d[s], t, lo, hi, Fin, uc);
 			else sg.template issue<1>(GD[0].d[s], t, lo, hi, Fin, uc);
-			gx[s] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
+			Gs[s * 256 + t] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
 		}
 		sg.template issue<2>(GD[0].d[4], t, lo, hi, Fin, uc);
 		gz0 = sg.finish(GD[0], 4, meta, p, t, Fin, uc);
 		sg.template issue<2>(GD[0].d[5], t, lo, hi, Fin, uc);
 		gz1 = sg.finish(GD[0], 5, meta, p, t, Fin, uc);
-		mbar_wait(&mbar[0], 0);
-		// x faces: entry t = (y, z) = (lo, hi); y faces: entry t = (x, z) = (lo, hi); they share edge cells
-		double *r = smem + lo * ROW + hi * PL;
-		r[0] -= gx[0];
-		r[N - 1] -= gx[1];
-		__syncthreads();
-		double *c = smem + lo + hi * PL;
-		c[0] -= gx[2];
-		c[(N - 1) * ROW] -= gx[3];
 	}
 	for (int it = 0; g < npatch; g += gridDim.x, it++) {
 		const int       b    = it & 1;
 		double *        S    = smem + (DIRECT ? 0 : b) * S16_TILE;
-		double *        Sn   = smem + (b ^ 1) * S16_TILE;
 		const int       p    = p0 + g;
 		const int       gn   = g + gridDim.x;
 		const bool      next = gn < npatch;
@@ -403,18 +356,14 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		if (SRC_FINE) {
 			h2 = meta[p].h2;
 			build_tile_from_fine_faces16(S, src, p, t); // (tile b was last read two iterations ago)
-		} else if (DIRECT) {
-			h2 = meta[p].h2;
-			__syncthreads(); // the previous patch's last stage has read the tile
-		} else if (ZERO_GUESS) {
-			h2 = meta[p].h2;
-			mbar_wait(&mbar[b], (it >> 1) & 1); // every thread's cp.async of this tile has landed
 		} else {
-			// boundary-cell updates of this tile (made during the previous iteration) and the descriptors
-			// become visible; every thread is past the previous iteration: the other tile may be refilled
+			// the previous patch's last stage has read the tile; Gs and the descriptors written during the
+			// previous iteration become visible
 			__syncthreads();
-			h2 = GD[b].h2;
-			if (next) prefetch(gn, b ^ 1, true); // + the table entry of the patch after the next -> metaS
+			h2 = ZERO_GUESS ? meta[p].h2 : GD[b].h2;
+			// table entry of the patch after the next -> metaS (read by describe() after the next barrier but one)
+			if (!ZERO_GUESS && t < MW && gn + (int) gridDim.x < npatch)
+				cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pn + gridDim.x) + t, true);
 		}
 		double v[N];
 		{ // z forward: pencil (x, y) = (lo, hi)
@@ -438,6 +387,18 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (!ZERO_GUESS) {
 				v[0] -= gz0;
 				v[N - 1] -= gz1;
+				// x faces: entry (y, z) belongs to the pencils x = 0 / 15; y faces: entry (x, z) to y = 0 / 15
+				// (edge pencils take both, like StarPatchOp::addInterfaceToRHS visiting every side)
+				if (lo == 0 || lo == N - 1) {
+					const double *gq = Gs + (lo == 0 ? 0 : 256) + hi;
+#pragma unroll
+					for (int k = 0; k < N; k++) v[k] -= gq[16 * k];
+				}
+				if (hi == 0 || hi == N - 1) {
+					const double *gq = Gs + (hi == 0 ? 512 : 768) + lo;
+#pragma unroll
+					for (int k = 0; k < N; k++) v[k] -= gq[16 * k];
+				}
 				if (next) sg.template issue<2>(gp.d[4], t, lo, hi, Fin, uc);
 			}
 			dst2_forward<N>(v, mg);
@@ -460,8 +421,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
 			if (!ZERO_GUESS && next) gz1 = sg.finish(gp, 5, meta, pn, t, Fin, uc);
 		}
+		if (!ZERO_GUESS) cp_async_wait_all(); // metaS has landed (made visible by the barrier)
 		__syncthreads();
-		if (ZERO_GUESS && !SRC_FINE && !DIRECT && next) prefetch(gn, b ^ 1, false); // every thread is past the previous iteration
 		{ // y: pencil (k_x, k_z) = (lo, hi)
 			double *q = S + lo + hi * PL;
 #pragma unroll
@@ -490,15 +451,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			for (int k = 0; k < N; k++) q[k * ROW] = v[k];
 			if (!ZERO_GUESS && next) {
 				gx1 = sg.finish(gp, 1, meta, pn, t, Fin, uc);
-				mbar_wait(&mbar[b ^ 1], ((it + 1) >> 1) & 1); // the next tile (and metaS) has landed
-				double *r = Sn + lo * ROW + hi * PL;           // x faces of the next patch: entry t = (y, z)
-				r[0] -= gx0;
-				r[N - 1] -= gx1;
+				Gs[t]       = gx0; // (this patch's values were consumed before the barrier above)
+				Gs[256 + t] = gx1;
 				// descriptors of the patch after the next; GD[b] was last read before this iteration's first barrier
 				if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + gridDim.x, b);
 			}
 		}
-		__syncthreads(); // (also orders the x-face updates of the next tile before its y-face updates)
+		__syncthreads();
 		double gy0 = 0.0;
 		{ // x inverse
 #pragma unroll
@@ -602,10 +561,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			}
 		}
 		if (!ZERO_GUESS && next) {
-			const double gy1 = sg.finish(gp, 3, meta, pn, t, Fin, uc);
-			double *     c   = Sn + lo + hi * PL; // y faces of the next patch: entry t = (x, z)
-			c[0] -= gy0;
-			c[(N - 1) * ROW] -= gy1;
+			Gs[512 + t] = gy0;
+			Gs[768 + t] = sg.finish(gp, 3, meta, pn, t, Fin, uc);
 		}
 	}
 }

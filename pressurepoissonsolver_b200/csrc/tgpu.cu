@@ -330,7 +330,7 @@ static bool supported_dn(int D, int N)
 
 template <bool Z, bool E, bool PR, bool W, bool SF = false> static int set_smem_attr_3d16()
 {
-	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
 	return TGPU_OK;
 }
 static int set_smem_attrs_3d16()
