@@ -232,6 +232,54 @@ template <int N> __device__ __forceinline__ void dst3_inverse(double (&v)[N], co
 	}
 }
 
+#ifndef TGPU_S16_TRIDIAG
+#define TGPU_S16_TRIDIAG 1 // 0: every axis is transformed (the tables passed as `eig` differ, see tgpu.cu)
+#endif
+// Tridiagonal solve along one axis once the other axes are diagonalised ("matrix decomposition": two transform
+// pairs + one Thomas solve instead of three transform pairs; same patch solve as FftwPatchSolver.h:174-206 /
+// DftPatchSolver.h:173-216 in exact arithmetic, 56 fp64 operations per pencil instead of 248).
+// For the pencil with transform indices (k_a, k_b) the remaining system is  M y = h^2 r,
+//   M = tridiag(1, d_j, 1),  d_j = mu - 2 (mu - 3 at both ends: the Dirichlet closure of StarPatchOp.h:46-64),
+//   mu = -4 sin^2((k_a+1) pi/2n) - 4 sin^2((k_b+1) pi/2n).
+// M is symmetric under j -> n-1-j, so it is eliminated from both ends towards the middle with ONE set of
+// multipliers a_0 = 1/d_0, a_j = 1/(d_j - a_{j-1}) (two independent dependency chains of n/2), leaving
+//   y_j + a_j y_{j+1} = rho_j (j < n/2),  y_{n-1-j} + a_j y_{n-2-j} = rho'_j,  and a 2 x 2 system in the middle.
+// tab[j * STRIDE + pencil] = a_j (j < n/2), tab[(n/2) * STRIDE + pencil] = 1 / (1 - a_{n/2-1}^2); the (2/n)^(D-1) of
+// the transform pairs (DftPatchSolver.h:214) and h^2 are folded into the right-hand side.  (2D: mu has one term.)
+template <int N, int STRIDE = 256> struct TriSolve { // STRIDE: pencils per table row
+	static constexpr int H = N / 2;
+	// v -> (rho_0..rho_{H-1}, rho'_{H-1}..rho'_0), both scaled
+	// hs = h^2 (2/n)^(D-1): the scaling of the D-1 transform pairs (DftPatchSolver.h:214)
+	__device__ static __forceinline__ void forward(double (&v)[N], const double *__restrict__ tab, double hs)
+	{
+		double       a  = __ldg(tab);
+		double       sa = hs * a;
+		v[0]            = v[0] * sa;
+		v[N - 1]        = v[N - 1] * sa;
+#pragma unroll
+		for (int j = 1; j < H; j++) {
+			a            = __ldg(tab + j * STRIDE);
+			sa           = hs * a;
+			v[j]         = fma(-a, v[j - 1], v[j] * sa);
+			v[N - 1 - j] = fma(-a, v[N - j], v[N - 1 - j] * sa);
+		}
+	}
+	__device__ static __forceinline__ void backward(double (&v)[N], const double *__restrict__ tab)
+	{
+		const double a = __ldg(tab + (H - 1) * STRIDE), kap = __ldg(tab + H * STRIDE);
+		const double yt = kap * fma(-a, v[H], v[H - 1]), yb = kap * fma(-a, v[H - 1], v[H]);
+		v[H - 1] = yt;
+		v[H]     = yb;
+#pragma unroll
+		for (int j = H - 2; j >= 0; j--) {
+			const double aj = __ldg(tab + j * STRIDE);
+			v[j]            = fma(-aj, v[j + 1], v[j]);
+			v[N - 1 - j]    = fma(-aj, v[N - 2 - j], v[N - 1 - j]);
+		}
+	}
+};
+
+
 // cp.async (LDGSTS) 8-byte copy global -> shared; !valid zero-fills (src-size 0)
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid)
 {
@@ -604,12 +652,18 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				}
 				dense_to_smem<N>(mats + kx.inv * N * N, v, S + m * G::ROW, 1);
 			} else {
+#if TGPU_S16_TRIDIAG
+				// the other axes are diagonalised: row m is a tridiagonal system along x (TriSolve); eig = multiplier table
+				TriSolve<N, G::M>::forward(v, eig + m, h2 * ((D == 2) ? 2.0 / N : 4.0 / (N * N)));
+				TriSolve<N, G::M>::backward(v, eig + m);
+#else
 				dst2_forward<N>(v, mg);
 				// eig is stored transposed, [k_x][row m], so that a warp reads consecutive doubles
 				const double *er = eig + m;
 #pragma unroll
 				for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
 				dst3_inverse<N>(v, mg);
+#endif
 #pragma unroll
 				for (int k = 0; k < N; k++) S[m * G::ROW + k] = v[k];
 			}

@@ -122,11 +122,10 @@ smooth3d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			double *  q  = W + ky * N + lo;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[(size_t) k * M];
-			Dst2<N, N>::run(v, mg);
-			const double *er = eig + ky * N + lo; // the table is symmetric in the axes: [k_z][k_y][k_x] works as well
-#pragma unroll
-			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + (size_t) k * M);
-			Dst3<N, N>::run(v, mg);
+			// x and y are diagonalised: a tridiagonal system along z per (k_x, k_y) (TriSolve, smooth3d16.cuh);
+			// eig = the table of elimination multipliers [17][k_y][k_x]
+			TriSolve<N, M>::forward(v, eig + ky * N + lo, h2 * (4.0 / (N * N)));
+			TriSolve<N, M>::backward(v, eig + ky * N + lo);
 #pragma unroll
 			for (int k = 0; k < N; k++) q[(size_t) k * M] = v[k];
 		}

@@ -34,53 +34,6 @@ __device__ __forceinline__ void     cp_async16(double *smem_dst, const double *g
 {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-// Tridiagonal solve along one axis once the other two are diagonalised ("matrix decomposition": two transform
-// pairs + one Thomas solve instead of three transform pairs; same patch solve as FftwPatchSolver.h:174-206 /
-// DftPatchSolver.h:173-216 in exact arithmetic, 56 fp64 operations per pencil instead of 248).
-// For the pencil with transform indices (k_a, k_b) the remaining system is  M y = h^2 r,
-//   M = tridiag(1, d_j, 1),  d_j = mu - 2 (mu - 3 at both ends: the Dirichlet closure of StarPatchOp.h:46-64),
-//   mu = -4 sin^2((k_a+1) pi/2n) - 4 sin^2((k_b+1) pi/2n).
-// M is symmetric under j -> n-1-j, so it is eliminated from both ends towards the middle with ONE set of
-// multipliers a_0 = 1/d_0, a_j = 1/(d_j - a_{j-1}) (two independent dependency chains of n/2), leaving
-//   y_j + a_j y_{j+1} = rho_j (j < n/2),  y_{n-1-j} + a_j y_{n-2-j} = rho'_j,  and a 2 x 2 system in the middle.
-// tab[j * 256 + pencil] = a_j (j < n/2), tab[(n/2) * 256 + pencil] = 1 / (1 - a_{n/2-1}^2); the (2/n)^2 of the two
-// transform pairs (DftPatchSolver.h:214) and h^2 are folded into the right-hand side.
-#ifndef TGPU_S16_TRIDIAG
-#define TGPU_S16_TRIDIAG 1
-#endif
-template <int N> struct TriSolve {
-	static constexpr int H = N / 2;
-	// v -> (rho_0..rho_{H-1}, rho'_{H-1}..rho'_0), both scaled
-	__device__ static __forceinline__ void forward(double (&v)[N], const double *__restrict__ tab, double h2)
-	{
-		const double hs = h2 * (4.0 / (N * N));
-		double       a  = __ldg(tab);
-		double       sa = hs * a;
-		v[0]            = v[0] * sa;
-		v[N - 1]        = v[N - 1] * sa;
-#pragma unroll
-		for (int j = 1; j < H; j++) {
-			a            = __ldg(tab + j * 256);
-			sa           = hs * a;
-			v[j]         = fma(-a, v[j - 1], v[j] * sa);
-			v[N - 1 - j] = fma(-a, v[N - j], v[N - 1 - j] * sa);
-		}
-	}
-	__device__ static __forceinline__ void backward(double (&v)[N], const double *__restrict__ tab)
-	{
-		const double a = __ldg(tab + (H - 1) * 256), kap = __ldg(tab + H * 256);
-		const double yt = kap * fma(-a, v[H], v[H - 1]), yb = kap * fma(-a, v[H - 1], v[H]);
-		v[H - 1] = yt;
-		v[H]     = yb;
-#pragma unroll
-		for (int j = H - 2; j >= 0; j--) {
-			const double aj = __ldg(tab + j * 256);
-			v[j]            = fma(-aj, v[j + 1], v[j]);
-			v[N - 1 - j]    = fma(-aj, v[N - 2 - j], v[N - 1 - j]);
-		}
-	}
-};
-
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
@@ -430,7 +383,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (!ZERO_GUESS && next) sg.template issue<0>(gp.d[0], t, lo, hi, Fin, uc);
 #if TGPU_S16_TRIDIAG
 			// z and x are diagonalised: what is left per (k_x, k_z) is a tridiagonal system along y
-			TriSolve<N>::forward(v, eig + t, h2);
+			TriSolve<N>::forward(v, eig + t, h2 * (4.0 / (N * N)));
 #else
 			dst2_forward<N>(v, mg);
 			const double *er = eig + t; // eig[k_y * 256 + k_x + 16 k_z] (the table is symmetric in the axes)

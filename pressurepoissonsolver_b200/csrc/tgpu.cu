@@ -210,7 +210,7 @@ struct tgpu_hier {
 	int                   D = 0, N = 0;
 	std::vector<LevelDev> levels;
 	double *              eig = nullptr; // [N^D]
-	double *              tri = nullptr; // D = 3: [N/2 + 1][N^2] tridiagonal multipliers (TriSolve)
+	double *              tri = nullptr; // [N/2 + 1][N^(D-1)] tridiagonal multipliers (TriSolve)
 	double *              mats = nullptr, *lam = nullptr; // Neumann patches: transform matrices [6][N][N], 1-D eigenvalues [3][N]
 	std::vector<GraphEntry> graphs;
 	std::vector<tgpu_vec *> krylov_ws;
@@ -745,26 +745,26 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 			eig[(i % n) * M + i / n] = scale / sum;
 		}
 		TRY(dev_upload(&h->eig, eig.data(), eig.size()));
-		// D = 3: multipliers of the two-sided tridiagonal elimination along y for every (k_x, k_z) (TriSolve, smooth3d16.cuh)
-		if (D == 3) {
+		// multipliers of the two-sided tridiagonal elimination along the axis that is not transformed, for every
+		// pencil of the other axes' transform indices (TriSolve, kernels.cuh): [n/2 + 1][n^(D-1)]
+		{
 			const int                H = n / 2;
-			std::vector<double>      tri((size_t) (H + 1) * n * n);
+			std::vector<double>      tri((size_t) (H + 1) * M);
 			std::vector<long double> ll(n);
 			for (int k = 0; k < n; k++) {
 				const long double sn = sinl((k + 1) * 3.141592653589793238462643383279502884L / (2 * n));
 				ll[k]                = -4.0L * sn * sn;
 			}
-			for (int kz = 0; kz < n; kz++)
-				for (int kx = 0; kx < n; kx++) {
-					const long double mu = ll[kx] + ll[kz];
-					long double       a  = 0.0L;
-					for (int j = 0; j < H; j++) {
-						const long double d = mu - (j == 0 ? 3.0L : 2.0L);
-						a                   = 1.0L / (d - (j == 0 ? 0.0L : a));
-						tri[(size_t) j * n * n + kx + n * kz] = (double) a;
-					}
-					tri[(size_t) H * n * n + kx + n * kz] = (double) (1.0L / (1.0L - a * a));
+			for (size_t m = 0; m < M; m++) {
+				const long double mu = (D == 2) ? ll[m] : ll[m % n] + ll[m / n];
+				long double       a  = 0.0L;
+				for (int j = 0; j < H; j++) {
+					const long double d = mu - (j == 0 ? 3.0L : 2.0L);
+					a                   = 1.0L / (d - (j == 0 ? 0.0L : a));
+					tri[(size_t) j * M + m] = (double) a;
 				}
+				tri[(size_t) H * M + m] = (double) (1.0L / (1.0L - a * a));
+			}
 			TRY(dev_upload(&h->tri, tri.data(), tri.size()));
 		}
 	}
@@ -1413,7 +1413,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm  = smooth3d32_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 #define S32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth3d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->eig, uc, h->scratch32);
+	case K: return launch(h->ctx, smooth3d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, h->scratch32);
 		switch (key) {
 			S32_CASE(8 | 4 | 1, true, true, false, true)
 			S32_CASE(8 | 1, true, false, false, true)
@@ -1457,7 +1457,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const dim3 grid(std::min(nblk, h->ctx->sm_count * smooth_min_blocks<NN>())), block(TGPU_THREADS);
 		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
-		const double *   eig  = h->eig;
+		const double *   eig  = TGPU_S16_TRIDIAG ? h->tri : h->eig;
 		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
 		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
 		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
