@@ -184,6 +184,270 @@ smooth3d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// smooth3d32c_kernel: the 32^3 patch solve on a pair of SMs (thread-block cluster of two CTAs), whole patch
+// resident in shared memory, no scratch block.
+//   The z axis is not transformed (TriSolve, kernels.cuh): with x and y diagonalised, every (k_x, k_y) pencil
+//   is a tridiagonal system along z whose two-sided elimination runs from z = 0 upwards and from z = 31
+//   downwards with the same multipliers.  That is exactly a split over two CTAs: CTA 0 owns the planes
+//   z = 0..15, CTA 1 the planes z = 31..16 (local plane j <-> elimination step j in both), and the only data the
+//   halves exchange is the last plane of eliminated right-hand sides (8 KB each way, read through distributed
+//   shared memory after one cluster barrier) for the 2 x 2 system in the middle.
+//   Per CTA: 512 threads = 16 warps, warp w owns local plane w for the y and x transforms (warp-local
+//   transposes), the z recurrences are element-wise over the planes (two pencils per thread).
+//   f goes straight from memory into the y pencils (a warp's load = one 256-byte row) and u straight from the
+//   y pencils back to memory: HBM sees f once and u once, shared memory holds the 16 planes (136 KB).
+// Same arithmetic as smooth3d32_kernel / smooth_kernel (SchurHelper.h:319-331, FftwPatchSolver.h:174-206).
+// ---------------------------------------------------------------------------------------------
+constexpr int    C32_THREADS = 512, C32_ROW = 34, C32_PL = 32 * C32_ROW, C32_TILE = 16 * C32_PL;
+// tile + two exchange planes (double buffered) + z-face interface values + per-warp x/y-face values + x-face output staging
+constexpr size_t smooth3d32c_smem_bytes() { return sizeof(double) * (C32_TILE + 2 * 1024 + 1024 + 16 * 128 + 16 * 64); }
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+	unsigned r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// value at the same shared-memory address in CTA `rank` of the cluster
+__device__ __forceinline__ double ld_dsmem(const double *local, unsigned rank)
+{
+	unsigned a = (unsigned) __cvta_generic_to_shared(local), ra;
+	double   v;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(a), "r"(rank));
+	asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(ra) : "memory");
+	return v;
+}
+template <bool PROLONG>
+__device__ __noinline__ double gamma_entry32(const PatchMeta *__restrict__ meta, int p, int s, int m, const double *__restrict__ F,
+                                             const double *__restrict__ uc)
+{
+	const FaceVals<3, 32, PROLONG ? FV_PROLONG : FV_PLAIN> fv{F, uc, meta};
+	return gamma_entry(meta[p], p, s, m, fv);
+}
+// One interface value split into "issue the loads" and "combine": same-level neighbours inline (same expressions
+// as gamma_entry), anything else through the general code at combine time.
+template <bool PROLONG> struct Gam32 {
+	double a0, b0, a1, b1;
+	int    slow;
+	__device__ __forceinline__ void issue(const PatchMeta &pm, int p, int s, int m, const double *__restrict__ F, const double *__restrict__ uc)
+	{
+		constexpr int N = 32, M = N * N, NC = M * N;
+		const int     ty = pm.nbr_type[s];
+		slow             = ty > NBR_NORMAL;
+		a0 = b0 = a1 = b1 = 0.0;
+		if (ty == NBR_NORMAL) {
+			a0 = __ldg(F + ((size_t) p * 6 + s) * M + m);
+			b0 = __ldg(F + ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * M + m);
+			if (PROLONG) {
+				int c[3];
+				if (pm.parent_idx >= 0) {
+					face_cell<3, N>(s, m, c);
+					a1 = __ldg(uc + (size_t) pm.parent_idx * NC + parent_cell<3, N>(pm.orth_on_parent, c));
+				}
+				const int qp = pm.nbr_parent[s];
+				if (qp >= 0) { // < 0: halo slot whose face arrived with the correction added
+					face_cell<3, N>(s ^ 1, m, c);
+					b1 = __ldg(uc + (size_t) qp * NC + parent_cell<3, N>(pm.nbr_orth[s], c));
+				}
+			}
+		}
+	}
+	__device__ __forceinline__ double finish(const PatchMeta *__restrict__ meta, int p, int s, int m, const double *__restrict__ F,
+	                                         const double *__restrict__ uc, double cfac) const
+	{
+		if (slow) return cfac * gamma_entry32<PROLONG>(meta, p, s, m, F, uc);
+		return cfac * (0.5 * (a0 + a1) + 0.5 * (b0 + b1));
+	}
+};
+
+template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C32_THREADS, 1)
+smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
+                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
+                   const double *__restrict__ uc)
+{
+	constexpr int N = 32, ROW = C32_ROW, PL = C32_PL, M = N * N, NC = N * N * N;
+	extern __shared__ __align__(16) double S[];
+	double *       X    = S + C32_TILE;  // [2][M] last eliminated plane, for the peer
+	double *       GZ   = X + 2 * M;     // [M] (2/h^2) gamma on this half's z face
+	double *       GXY  = GZ + M;        // [16 warps][4][32] x- and y-face values of a plane
+	double *       EX   = GXY + 16 * 128; // [16 warps][2][32] staging of the new x-face slices
+	const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
+	const unsigned rank = cluster_ctarank();
+	const int      z    = rank == 0 ? w : N - 1 - w; // plane of the patch behind local plane w
+	const int      sz   = rank == 0 ? 4 : 5;         // the z side this half touches
+	const int      ncl = gridDim.x / 2, npatch = P - p0;
+	double *       gxy  = GXY + w * 128;
+	const int      mf   = lane + N * z; // x faces: entry (y, z) = (lane, z); y faces: entry (x, z) = (lane, z)
+	Mags<N>        mg;
+	mg.load();
+	pdl_launch_dependents();
+	pdl_wait();
+	int g = blockIdx.x / 2;
+	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
+		const int    p    = p0 + g;
+		const double cfac = 2.0 * meta[p].inv_h2;
+#pragma unroll
+		for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = cfac * gamma_entry32<PROLONG>(meta, p, s, mf, Fin, uc);
+		GZ[t]       = cfac * gamma_entry32<PROLONG>(meta, p, sz, t, Fin, uc);
+		GZ[t + 512] = cfac * gamma_entry32<PROLONG>(meta, p, sz, t + 512, Fin, uc);
+		__syncthreads();
+	}
+	for (int it = 0; g < npatch; g += ncl, it++) {
+		const int    p    = p0 + g;
+		const bool   next = g + ncl < npatch;
+		const int    pn   = p + ncl;
+		const double h2   = meta[p].h2;
+		double       v[N];
+		{ // y forward: pencil (x, z) = (lane, z), straight from memory
+			const double *fp = f + (size_t) p * NC + (size_t) z * M + lane;
+#pragma unroll
+			for (int k = 0; k < N; k++) v[k] = __ldcs(fp + k * N);
+			if (next) { // the same plane of the next patch -> L2 (64 lines)
+				const double *fn = f + (size_t) pn * NC + (size_t) z * M + lane * 32;
+				prefetch_l2(fn);
+				prefetch_l2(fn + 16);
+			}
+			if (!ZERO_GUESS) {
+				v[0] -= gxy[64 + lane];
+				v[N - 1] -= gxy[96 + lane];
+				if (lane == 0 || lane == N - 1) {
+					const double *q = gxy + (lane ? 32 : 0);
+#pragma unroll
+					for (int k = 0; k < N; k++) v[k] -= q[k];
+				}
+				if (w == 0) {
+#pragma unroll
+					for (int k = 0; k < N; k++) v[k] -= GZ[lane + N * k];
+				}
+			}
+			Dst2<N, N>::run(v, mg);
+			double *col = S + w * PL + lane;
+#pragma unroll
+			for (int k = 0; k < N; k++) col[k * ROW] = v[k];
+		}
+		__syncwarp();
+		double2 *rowp = reinterpret_cast<double2 *>(S + w * PL + lane * ROW); // row (k_y, plane) = (lane, w)
+		{ // x forward
+#pragma unroll
+			for (int j = 0; j < N / 2; j++) {
+				const double2 d = rowp[j];
+				v[2 * j]        = d.x;
+				v[2 * j + 1]    = d.y;
+			}
+			Dst2<N, N>::run(v, mg);
+#pragma unroll
+			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+		}
+		__syncthreads();
+		// z: elimination step j on local plane j, in place; pencils (k_x, k_y) = (lane, w) and (lane, w + 16).
+		// The interface values of the NEXT patch are gathered around this phase (the transform registers are free here).
+		// (two batches of three: loads issued before the elimination / the back substitution, combined after it)
+		Gam32<PROLONG> gm[3];
+		double         cfn = 0.0;
+		if (!ZERO_GUESS && next) {
+			const PatchMeta &pq = meta[pn];
+			cfn                 = 2.0 * pq.inv_h2;
+#pragma unroll
+			for (int s = 0; s < 3; s++) gm[s].issue(pq, pn, s, mf, Fin, uc);
+		}
+		const double hs = h2 * (4.0 / (N * N));
+		double *     Xo = X + (it & 1) * M;
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			const int     ky = w + 16 * q;
+			double *      zp = S + ky * ROW + lane;
+			const double *tb = tri + ky * N + lane;
+			double        rho = 0.0;
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				const double a = __ldg(tb + j * M);
+				const double r = zp[j * PL] * (hs * a);
+				rho            = (j == 0) ? r : fma(-a, rho, r);
+				zp[j * PL]     = rho;
+			}
+			Xo[ky * N + lane] = rho;
+		}
+		if (!ZERO_GUESS && next) { // (the buffers were consumed before this iteration's first barrier)
+#pragma unroll
+			for (int s = 0; s < 3; s++) gxy[s * 32 + lane] = gm[s].finish(meta, pn, s, mf, Fin, uc, cfn);
+			const PatchMeta &pq = meta[pn];
+			gm[0].issue(pq, pn, 3, mf, Fin, uc);
+			gm[1].issue(pq, pn, sz, t, Fin, uc);
+			gm[2].issue(pq, pn, sz, t + 512, Fin, uc);
+		}
+		cluster_sync_all(); // both halves are eliminated; the peer's last plane is readable
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			const int     ky = w + 16 * q;
+			double *      zp = S + ky * ROW + lane;
+			const double *tb = tri + ky * N + lane;
+			const double  a15 = __ldg(tb + 15 * M), kap = __ldg(tb + 16 * M);
+			double        y   = kap * fma(-a15, ld_dsmem(Xo + ky * N + lane, rank ^ 1), zp[15 * PL]);
+			zp[15 * PL]       = y;
+#pragma unroll
+			for (int j = 14; j >= 0; j--) {
+				y          = fma(-__ldg(tb + j * M), y, zp[j * PL]);
+				zp[j * PL] = y;
+			}
+		}
+		if (!ZERO_GUESS && next) {
+			gxy[96 + lane] = gm[0].finish(meta, pn, 3, mf, Fin, uc, cfn);
+			GZ[t]          = gm[1].finish(meta, pn, sz, t, Fin, uc, cfn);
+			GZ[t + 512]    = gm[2].finish(meta, pn, sz, t + 512, Fin, uc, cfn);
+		}
+		__syncthreads();
+		{ // x inverse
+#pragma unroll
+			for (int j = 0; j < N / 2; j++) {
+				const double2 d = rowp[j];
+				v[2 * j]        = d.x;
+				v[2 * j + 1]    = d.y;
+			}
+			Dst3<N, N>::run(v, mg);
+#pragma unroll
+			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+		}
+		__syncwarp();
+		{ // y inverse: pencil (x, z) = (lane, z), straight to memory
+			const double *col = S + w * PL + lane;
+#pragma unroll
+			for (int k = 0; k < N; k++) v[k] = col[k * ROW];
+			Dst3<N, N>::run(v, mg);
+			if (WRITE_U) {
+				double *up = u + (size_t) p * NC + (size_t) z * M + lane;
+#pragma unroll
+				for (int k = 0; k < N; k++) up[k * N] = v[k];
+			}
+			if (EMIT) {
+				double *Fp = Fout + (size_t) p * 6 * M;
+				Fp[2 * M + mf] = v[0]; // y faces: entry (x, z)
+				Fp[3 * M + mf] = v[N - 1];
+				if (w == 0) { // z face of this half: entries (x, y)
+					double *Fz = Fp + sz * M + lane;
+#pragma unroll
+					for (int k = 0; k < N; k++) Fz[N * k] = v[k];
+				}
+				double *ex = EX + w * 64;
+				if (lane == 0 || lane == N - 1) { // x faces: entries (y, z), held by lanes 0 and 31
+					double *q = ex + (lane ? 32 : 0);
+#pragma unroll
+					for (int k = 0; k < N; k++) q[k] = v[k];
+				}
+				__syncwarp();
+				Fp[0 * M + mf] = ex[lane];
+				Fp[1 * M + mf] = ex[32 + lane];
+			}
+		}
+		__syncwarp();
+	}
+	cluster_sync_all(); // a CTA must not exit while its peer may still read its exchange plane
+}
+
+// ---------------------------------------------------------------------------------------------
 // operator apply / residual for 32^3 patches: one (patch, z slab) item per iteration.  Tile with a
 // ghost layer [10][34][36] (interior rows start 16-byte aligned at column 2).  MODE 0: out = A u,
 // MODE 1: out = f - A u.  Ghost = 2 gamma - a (neighbour), -a (Dirichlet), +a (Neumann), StarPatchOp.h:46-64.

@@ -226,7 +226,6 @@ struct tgpu_hier {
 	void *                arena = nullptr;
 	std::vector<void *>   ipc_opened;
 	int *                 p2p_err = nullptr;
-	double *              scratch32 = nullptr; // smooth3d32_kernel: one 256 KB block per resident CTA
 };
 
 struct tgpu_vec {
@@ -351,10 +350,10 @@ static int set_smem_attrs_3d16()
 }
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d32()
 {
-	CU(cudaFuncSetAttribute(smooth3d32_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth3d32c_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32c_smem_bytes()));
 	return TGPU_OK;
 }
-// 32^3 patches: opt-in shared memory sizes and the CTA-private scratch blocks of smooth3d32_kernel
+// 32^3 patches: opt-in shared memory sizes
 static int setup_3d32(tgpu_hier *h)
 {
 	TRY((set_smem_attr_3d32<true, true, false, true>()));
@@ -370,7 +369,6 @@ static int setup_3d32(tgpu_hier *h)
 	CU(cudaFuncSetAttribute(apply3d32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
-	CU(cudaMalloc(&h->scratch32, (size_t) h->ctx->sm_count * S32_CTAS_PER_SM * 32768 * sizeof(double)));
 	return TGPU_OK;
 }
 template <int D, int N> static int set_smem_attrs()
@@ -1151,7 +1149,6 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	for (void *b : h->ipc_opened) cudaIpcCloseMemHandle(b);
 	cudaFree(h->arena);
 	cudaFree(h->p2p_err);
-	cudaFree(h->scratch32);
 	cudaFree(h->krylov_sc);
 	cudaFree(h->mats);
 	cudaFree(h->lam);
@@ -1409,11 +1406,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
 	if (is_3d32(h)) {
-		const dim3   grid(std::min(p1 - p0, h->ctx->sm_count * S32_CTAS_PER_SM)), block(TGPU_THREADS);
-		const size_t sm  = smooth3d32_smem_bytes();
+		// one cluster of two CTAs (two SMs) per patch, see smooth3d32c_kernel
+		const dim3   grid(2 * std::min(p1 - p0, h->ctx->sm_count / 2)), block(C32_THREADS);
+		const size_t sm  = smooth3d32c_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 #define S32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth3d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, h->scratch32);
+	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc);
 		switch (key) {
 			S32_CASE(8 | 4 | 1, true, true, false, true)
 			S32_CASE(8 | 1, true, false, false, true)
