@@ -21,6 +21,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "dst4_fast.cuh"
 
 namespace tgpu
 {
@@ -119,6 +120,14 @@ template <int N> struct Mags {
 	}
 };
 
+#ifndef TGPU_FAST_DST4
+#define TGPU_FAST_DST4 1 // dense halves of size 8 and 16 through dst4_fast.cuh (45 / 119 instructions instead of 64 / 256)
+#endif
+template <int H> __device__ __forceinline__ void dst4_fast(const double (&x)[H], double (&y)[H])
+{
+	if constexpr (H == 16) dst4_16(x, y);
+	else if constexpr (H == 8) dst4_8(x, y);
+}
 // DST-II of a register pencil.  S[k][j] = sin(pi (k+1)(2j+1) / 2n)  (DftPatchSolver.h:262-268).
 // Symmetry S[k][n-1-j] = (-1)^k S[k][j] splits the transform into
 //   even k = 2m:   sum_j sin(pi (2m+1)(2j+1) / 2n) e_j        (dense n/2 x n/2, a DST-IV)
@@ -136,12 +145,19 @@ template <int NT, int n> struct Dst2 {
 			e[j] = v[j] + v[n - 1 - j];
 			o[j] = v[j] - v[n - 1 - j];
 		}
+		if (TGPU_FAST_DST4 && (H == 16 || H == 8)) { // the even outputs are a DST-IV of e: FFT-based straight-line code
+			double y[H];
+			dst4_fast<H>(e, y);
 #pragma unroll
-		for (int mm = 0; mm < H; mm++) {
-			double acc = 0.0;
+			for (int mm = 0; mm < H; mm++) v[2 * mm] = y[mm];
+		} else {
 #pragma unroll
-			for (int j = 0; j < H; j++) acc = fma(mg.sinq(SC * (2 * mm + 1) * (2 * j + 1)), e[j], acc);
-			v[2 * mm] = acc;
+			for (int mm = 0; mm < H; mm++) {
+				double acc = 0.0;
+#pragma unroll
+				for (int j = 0; j < H; j++) acc = fma(mg.sinq(SC * (2 * mm + 1) * (2 * j + 1)), e[j], acc);
+				v[2 * mm] = acc;
+			}
 		}
 		Dst2<NT, H>::run(o, mg);
 #pragma unroll
@@ -163,12 +179,19 @@ template <int NT, int n> struct Dst3 {
 		double        E[H], O[H];
 #pragma unroll
 		for (int l = 0; l < H; l++) O[l] = v[2 * l + 1];
+		if (TGPU_FAST_DST4 && (H == 16 || H == 8)) { // E is a DST-IV of the even inputs
+			double x[H];
 #pragma unroll
-		for (int i = 0; i < H; i++) {
-			double acc = 0.0;
+			for (int l = 0; l < H; l++) x[l] = v[2 * l];
+			dst4_fast<H>(x, E);
+		} else {
 #pragma unroll
-			for (int l = 0; l < H; l++) acc = fma(mg.sinq(SC * (2 * i + 1) * (2 * l + 1)), v[2 * l], acc);
-			E[i] = acc;
+			for (int i = 0; i < H; i++) {
+				double acc = 0.0;
+#pragma unroll
+				for (int l = 0; l < H; l++) acc = fma(mg.sinq(SC * (2 * i + 1) * (2 * l + 1)), v[2 * l], acc);
+				E[i] = acc;
+			}
 		}
 		Dst3<NT, H>::run(O, mg);
 #pragma unroll
