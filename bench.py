@@ -35,8 +35,8 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two finest-level smoother launches of config B
 # (ncu --set full, profiles/r01_v7_ncu_full_summary.txt: 134.8 + 22.8 MB faces-only sweep, 205.6 + 90.8 MB post-sweep)
-NCU_TRAFFIC_BYTES = (134.8e6 + 22.8e6 + 205.6e6 + 90.8e6) / 2
-NCU_TRAFFIC_SOURCE = "profiles/r01_v7_ncu_full_summary.txt (mean of the two smoother launches on the finest level)"
+NCU_TRAFFIC_BYTES = (134.8e6 + 4.9e6 + 202.2e6 + 86.5e6) / 2
+NCU_TRAFFIC_SOURCE = "profiles/r01_v9_ncu_full_summary.txt (mean of the two smoother launches on the finest level, IDs 0 and 12)"
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
 SMOOTH_BYTES_PER_CELL = 16.0      # dominant kernel: read f, write u
 
@@ -301,7 +301,7 @@ def main():
         "config": {"workload": desc, "cycle": "V(1,1), 1 coarse sweep, all levels down to the root patch", "cells": cells,
                    "levels": level_cells, "l2": "inputs larger than L2 (f and u are %.0f MB each, L2 is 126 MB)" % (cells * 8 / 1e6),
                    "parallelism": "1 GPU" if world == 1 else "%d GPUs: patches split along a Morton curve, NCCL halo-face exchange; %d cells on rank 0, %d in total" % (world, cells, total_cells)},
-        "roofline": {"bound": "hbm", "kernel": "smooth_kernel (block-Jacobi DST patch solve) on the finest level (rank 0)",
+        "roofline": {"bound": "hbm", "kernel": "block-Jacobi patch-solve smoother (smooth3d16_kernel / smooth3d32c_kernel / smooth_kernel by patch size) on the finest level, mean of the pre- and post-smoothing launch (rank 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": NCU_TRAFFIC_BYTES if (cfg == "B" and world == 1) else None, "traffic_source": NCU_TRAFFIC_SOURCE,
                      "peak_source": peak_src, "ms_per_launch": dom_ms,
@@ -327,15 +327,17 @@ def main():
     if rank == 0 and world == 1 and cfg == "B" and not args.cycle_only and not args.no_large_reference:
         # the N > 1 runs share the 1.07 B-cell mesh of config D (16^3 patches); its single-GPU number, measured here in a
         # child process with the same kernels, is the denominator for strong-scaling efficiency on that mesh
-        try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", "D16", "--cycle-only", "--steps", "5", "--warmup", "3",
-                                  "--no-cpu-baseline"], capture_output=True, text=True, timeout=600).stdout
-            big = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
-            line["large_mesh_reference"] = {"workload": big["config"]["workload"], "n_gpus": 1, "value": big["value"], "unit": "DOF/s",
-                                            "ms_per_step": big["ms_per_step"], "steps": big["steps"],
-                                            "vcycle_frac_of_hbm_roofline": big["roofline"]["vcycle_frac"]}
-        except Exception as ex:  # never let the extra line break the contract line
-            line["large_mesh_reference"] = {"error": str(ex)[:200]}
+        # (key large_mesh_reference); the same for BASELINE config D as named, with 32^3 patches (large_mesh_reference_32)
+        for key, big_cfg in (("large_mesh_reference", "D16"), ("large_mesh_reference_32", "D")):
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", big_cfg, "--cycle-only", "--steps", "5", "--warmup", "3",
+                                      "--no-cpu-baseline"], capture_output=True, text=True, timeout=600).stdout
+                big = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+                line[key] = {"workload": big["config"]["workload"], "n_gpus": 1, "value": big["value"], "unit": "DOF/s",
+                             "ms_per_step": big["ms_per_step"], "steps": big["steps"],
+                             "vcycle_frac_of_hbm_roofline": big["roofline"]["vcycle_frac"]}
+            except Exception as ex:  # never let the extra line break the contract line
+                line[key] = {"error": str(ex)[:200]}
     if os.environ.get("BENCH_ALL_RANKS") and rank != 0:
         print("rank %d profile: %s" % (rank, json.dumps(line["kernel_profile_ms_per_step"])), file=sys.stderr, flush=True)
     if rank == 0:

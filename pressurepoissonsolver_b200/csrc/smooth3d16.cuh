@@ -43,7 +43,10 @@ constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
 // 64 registers per thread let four CTAs share an SM.  The other variants stage f with cp.async in a second
 // tile (the boundary cells are updated in place there) and run three CTAs per SM.
 __host__ __device__ constexpr bool   s16_direct(bool, bool src_fine) { return !src_fine; }
-__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return (zero_guess && !src_fine) ? 4 : 3; }
+#ifndef S16_GAMMA_CTAS
+#define S16_GAMMA_CTAS 3
+#endif
+__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return src_fine ? 3 : (zero_guess ? 4 : S16_GAMMA_CTAS); }
 __host__ __device__ constexpr size_t smooth3d16_smem_bytes(bool zero_guess = false, bool src_fine = false)
 {
 	return sizeof(double) * (s16_direct(zero_guess, src_fine) ? 1 : 2) * S16_TILE;

@@ -92,3 +92,21 @@ def test_distributed_cycle_matches_reference(name):
     assert abs(ret[0]["fnorm"] / np.linalg.norm(g["rhs_f"]) - 1) < 1e-13
     assert ret[0]["its"] == int(g["bicgstab_info"][0])
     assert rel_l2(gather("x"), g["bicgstab_u"]) < 1e-10
+
+
+@pytest.mark.parametrize("n,divide", [(16, 1), (32, 0)])
+def test_distributed_cycle_specialised_kernels_match_oracle(n, divide):
+    """The D = 3 kernels specialised for 16^3 (smooth3d16) and 32^3 (cluster-pair smooth3d32c) patches, launched on
+    interior / boundary patch ranges with halo faces from the peers, against the oracle on a refined octree."""
+    world = min(_ngpu(), 2)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gmg_oracle as go
+    levels = go.build_hierarchy(os.path.join(MESHES, "2refine.bin"), 3, n, divide)
+    fn = np.random.default_rng(11).standard_normal(levels[0].shape)
+    ret, gather, ncells = run_distributed(world, "2refine.bin", 3, n, divide, fn)
+    assert ret[0]["ndist"] >= 1 and ncells == fn.size
+    ref = go.vcycle(levels, fn)
+    assert rel_l2(gather("vcycle"), ref.reshape(-1, n ** 3)) < 1e-12
+    assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
