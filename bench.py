@@ -160,7 +160,11 @@ def main():
         mesh.refine_box((0.0, 0.0, 0.0), (1.0, 1.0, 0.5))
     if world > 1:
         # levels with fewer than ~2048 patches in total are cheaper to replicate than to exchange halos for
-        part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=max(32, 2048 // world))
+        # (the threshold is in cells: a 32^3 patch counts for eight 16^3 patches)
+        mpr = max(32, 2048 // world)
+        if n > 16:
+            mpr = max(4, mpr * 16 ** D // n ** D)
+        part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=mpr)
         h = pps.Hierarchy.from_partition(ctx, part)
     else:
         h = pps.Hierarchy.from_mesh(ctx, mesh, n)
