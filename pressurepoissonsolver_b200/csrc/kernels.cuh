@@ -1512,3 +1512,4 @@ __global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, cons
 } // namespace tgpu
 #include "smooth3d16.cuh"
 #include "patch3d32.cuh"
+#include "smooth2d32.cuh"

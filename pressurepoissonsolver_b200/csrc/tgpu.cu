@@ -348,6 +348,24 @@ static int set_smem_attrs_3d16()
 	TRY((set_smem_attr_3d16<true, true, false, false, true>()));
 	return TGPU_OK;
 }
+template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_2d32()
+{
+	CU(cudaFuncSetAttribute(smooth2d32_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth2d32_smem_bytes()));
+	return TGPU_OK;
+}
+static int setup_2d32()
+{
+	TRY((set_smem_attr_2d32<true, true, false, true>()));
+	TRY((set_smem_attr_2d32<true, false, false, true>()));
+	TRY((set_smem_attr_2d32<true, true, false, false>()));
+	TRY((set_smem_attr_2d32<false, true, false, true>()));
+	TRY((set_smem_attr_2d32<false, false, false, true>()));
+	TRY((set_smem_attr_2d32<false, true, false, false>()));
+	TRY((set_smem_attr_2d32<false, true, true, true>()));
+	TRY((set_smem_attr_2d32<false, false, true, true>()));
+	TRY((set_smem_attr_2d32<false, true, true, false>()));
+	return TGPU_OK;
+}
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d32()
 {
 	CU(cudaFuncSetAttribute(smooth3d32c_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32c_smem_bytes()));
@@ -788,6 +806,7 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 	}
 	if (D == 3 && n == 32) TRY(setup_3d32(h.get()));
 	else DISPATCH_DN(D, n, TRY((set_smem_attrs<DD, NN>())));
+	if (D == 2 && n == 32) TRY(setup_2d32());
 	*out = h.release();
 	return TGPU_OK;
 	API_END
@@ -1448,6 +1467,27 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
 		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
 		}
+	}
+	if (h->D == 2 && h->N == 32 && !h->generic_kernels && !L.has_neumann) { // one warp per patch, see smooth2d32.cuh
+		const int    nblk = (p1 - p0 + Q32_WARPS - 1) / Q32_WARPS;
+		const dim3   grid(std::min(nblk, h->ctx->sm_count * 2)), block(TGPU_THREADS);
+		const size_t sm  = smooth2d32_smem_bytes();
+		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+#define Q32_CASE(K, Z, E, PR, W) \
+	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc);
+		switch (key) {
+			Q32_CASE(8 | 4 | 1, true, true, false, true)
+			Q32_CASE(8 | 1, true, false, false, true)
+			Q32_CASE(8 | 4, true, true, false, false)
+			Q32_CASE(4 | 1, false, true, false, true)
+			Q32_CASE(1, false, false, false, true)
+			Q32_CASE(4, false, true, false, false)
+			Q32_CASE(4 | 2 | 1, false, true, true, true)
+			Q32_CASE(2 | 1, false, false, true, true)
+			Q32_CASE(4 | 2, false, true, true, false)
+		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
+		}
+#undef Q32_CASE
 	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
