@@ -31,6 +31,8 @@ CONFIGS = {
     "D16": (3, "4uni.bin", 3, 16, "config D mesh with 16^3 patches: uniform octree 4uni.bin --divide 3, 262,144 patches of 16^3 (1,073,741,824 cells), 7 levels, trig RHS"),
     "D": (3, "4uni.bin", 2, 32, "config D: uniform octree 4uni.bin --divide 2, 32,768 patches of 32^3 (1,073,741,824 cells), 6 levels, trig RHS"),
     "D2": (3, "3uni.bin", 1, 32, "3uni.bin --divide 1, 512 patches of 32^3 (16,777,216 cells), 4 levels, trig RHS"),
+    "E": (2, "2d_multi_refine_8.bin", 4, 32, "config E: apps/2d/steady2d GMG, deeply refined quadtree multi_refine_8.bin (tree levels 3-9) --divide 4, 40,960 patches of 32^2 (41,943,040 cells), trig RHS"),
+    "E5": (2, "2d_multi_refine_8.bin", 5, 32, "config E, one more --divide: 163,840 patches of 32^2 (167,772,160 cells), trig RHS"),
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two finest-level smoother launches of config B
