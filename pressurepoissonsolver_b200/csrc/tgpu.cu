@@ -198,6 +198,8 @@ struct LevelDev {
 };
 
 struct GraphEntry {
+	bool    want_faces = false;
+	double *faces      = nullptr;
 	const double *  f;
 	double *        u;
 	TgpuCycleOpts   opts;
@@ -210,6 +212,7 @@ struct tgpu_hier {
 	int                   D = 0, N = 0;
 	std::vector<LevelDev> levels;
 	double *              eig = nullptr; // [N^D]
+	double *              cycle_faces = nullptr; // boundary slices of the last cycle's result (level 0), if it was asked to emit them
 	double *              tri = nullptr; // [N/2 + 1][N^(D-1)] tridiagonal multipliers (TriSolve)
 	double *              mats = nullptr, *lam = nullptr; // Neumann patches: transform matrices [6][N][N], 1-D eigenvalues [3][N]
 	std::vector<GraphEntry> graphs;
@@ -1906,18 +1909,22 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		}
 		std::swap(Fcur, Falt);
 	}
+	if (l == 0 && want_faces) h->cycle_faces = Fcur; // the last sweep emitted the slices of u here
 	return TGPU_OK;
 }
-static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u)
+// want_faces: the caller applies the operator to the result next (BiCGStab: v = A M^-1 p), so the last sweep also
+// writes the result's boundary slices (h->cycle_faces != nullptr afterwards) and no extraction pass is needed
+static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u, bool want_faces = false)
 {
 	const bool fused = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
-	if (fused) return fused_visit(h, o, 0, f, u, false);
+	h->cycle_faces   = nullptr;
+	if (fused) return fused_visit(h, o, 0, f, u, want_faces && h->levels.size() > 1);
 	TRY(k_set(h, u, h->levels[0].ncells, 0.0)); // Cycle::apply: u->set(0)
 	return generic_visit(h, o, 0, f, u);
 }
 static bool same_opts(const TgpuCycleOpts &a, const TgpuCycleOpts &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
 
-static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, double *u)
+static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, double *u, bool want_faces = false)
 {
 	TgpuCycleOpts o;
 	if (opts) o = *opts;
@@ -1930,9 +1937,10 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 		const bool fused_sched = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
 		TRY(ensure_work(h, (int) l, !fused_sched || (o.fused == 2 && is_3d32(h))));
 	}
-	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u);
+	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u, want_faces);
 	for (GraphEntry &g : h->graphs)
-		if (g.f == f && g.u == u && same_opts(g.opts, o)) {
+		if (g.f == f && g.u == u && g.want_faces == want_faces && same_opts(g.opts, o)) {
+			h->cycle_faces = g.faces;
 			CU(cudaGraphLaunch(g.exec, ctx->stream));
 			ctx->launches += g.kernels;
 			return TGPU_OK;
@@ -1942,7 +1950,7 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	ctx->capturing    = true;
 	ctx->captured     = 0;
 	CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-	int         rc = run_cycle(h, o, f, u);
+	int         rc = run_cycle(h, o, f, u, want_faces);
 	cudaError_t e  = cudaStreamEndCapture(ctx->stream, &graph);
 	ctx->capturing = false;
 	if (rc != TGPU_OK) {
@@ -1952,6 +1960,7 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	if (e != cudaSuccess) return fail(TGPU_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
 	GraphEntry g;
 	g.f = f, g.u = u, g.opts = o, g.kernels = ctx->captured;
+	g.want_faces = want_faces, g.faces = h->cycle_faces;
 	CU(cudaGraphInstantiate(&g.exec, graph, 0));
 	cudaGraphDestroy(graph);
 	if (h->graphs.size() >= 8) {
@@ -2059,7 +2068,14 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 	const int    nb     = std::min(stride, grid_for(ctx, n, 256, 8));
 	double *     sc     = h->krylov_sc;
 	auto A = [&](const tgpu_vec *in, tgpu_vec *out) { return tgpu_apply(h, 0, in, out); };
-	auto M = [&](const tgpu_vec *in, tgpu_vec *out) { return cycle_ptr(h, opts, in->d, out->d); };
+	// the preconditioner's last sweep emits the boundary slices of its result, which is all A needs besides the result
+	auto M = [&](const tgpu_vec *in, tgpu_vec *out) { return cycle_ptr(h, opts, in->d, out->d, true); };
+	auto AM = [&](const tgpu_vec *in, tgpu_vec *out) { // out = A in for in = the vector M has just produced
+		if (!h->cycle_faces) return tgpu_apply(h, 0, in, out);
+		TRY(k_exchange(h, 0, h->cycle_faces, nullptr));
+		TRY(k_apply(h, 0, 0, in->d, nullptr, h->cycle_faces, out->d, nullptr));
+		return k_exchange_done(h, 0);
+	};
 	auto finish = [&](int step) {
 		Tag tg(ctx, "bicg_scalars", 0);
 		TRY(launch(ctx, bicg_finish_kernel, dim3(1), dim3(256), 0, nb, stride, (const double *) ctx->d_partial, sc, step, dist ? 0 : 1));
@@ -2094,8 +2110,10 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 		if (prec) {
 			TRY(M(p, mp));
 			pp = mp;
+			TRY(AM(pp, ap));
+		} else {
+			TRY(A(pp, ap));
 		}
-		TRY(A(pp, ap));
 		TRY(dots(rhat, ap, 1)); // alpha
 		{
 			Tag tg(ctx, "bicg_s", 0);
@@ -2104,8 +2122,10 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 		if (prec) {
 			TRY(M(s, ms));
 			ss = ms;
+			TRY(AM(ss, as));
+		} else {
+			TRY(A(ss, as));
 		}
-		TRY(A(ss, as));
 		TRY(dots(as, s, 2)); // omega
 		{
 			Tag tg(ctx, "bicg_xr", 0);
