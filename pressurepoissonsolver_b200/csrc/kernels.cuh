@@ -931,86 +931,168 @@ template <int D, int N> constexpr size_t apply_smem_bytes() { return sizeof(doub
 // fine residual is written; the only difference to GMG/Cycle.h:59-66 is the rounding noise of the patch
 // solve (~1e-16 relative) that the reference's r carries in the patch interiors.
 // ---------------------------------------------------------------------------------------------
+// one patch (all G::M threads of its slot; every thread of the CTA must call): Rp = the slot's [S][M] staging
+template <int D, int N, bool DIFF>
+__device__ __forceinline__ void frr_patch(const PatchMeta *__restrict__ meta, int p, bool valid, int m, double (*Rp)[Geo<D, N>::M],
+                                          const double *__restrict__ Fnew, const double *__restrict__ Fold, double *__restrict__ coarse)
+{
+	using G         = Geo<D, N>;
+	constexpr int H = N / 2;
+	int           orth = -1, parent = 0;
+	if (valid) {
+		const PatchMeta &pm = meta[p];
+		orth                = pm.orth_on_parent;
+		parent              = pm.parent_idx;
+		const double cfac   = 2.0 * pm.inv_h2;
+		int          ty[G::S];
+		double       own[G::S], gm[G::S];
+		const FaceVals<D, N, DIFF ? FV_DIFF : FV_NEG> fv{Fnew, Fold, meta};
+		gamma_all_sides(pm, p, m, fv, ty, own, gm);
+#pragma unroll
+		for (int s = 0; s < G::S; s++) Rp[s][m] = (ty[s] == NBR_NONE) ? 0.0 : cfac * gm[s];
+	}
+	__syncthreads();
+	if (valid) {
+		double *dst = coarse + (size_t) parent * G::NC;
+		if (orth < 0) { // patch present on both levels: coarse = r (dense, zero in the interior)
+			const int x = m % N, y = (D == 2) ? 0 : m / N;
+#pragma unroll 4
+			for (int k = 0; k < N; k++) {
+				double v = 0.0;
+				if (D == 2) {
+					if (x == 0) v += Rp[0][k];
+					if (x == N - 1) v += Rp[1][k];
+					if (k == 0) v += Rp[2][x];
+					if (k == N - 1) v += Rp[3][x];
+				} else {
+					if (x == 0) v += Rp[0][y + N * k];
+					if (x == N - 1) v += Rp[1][y + N * k];
+					if (y == 0) v += Rp[2][x + N * k];
+					if (y == N - 1) v += Rp[3][x + N * k];
+					if (k == 0) v += Rp[4][m];
+					if (k == N - 1) v += Rp[5][m];
+				}
+				dst[k * G::M + m] = v;
+			}
+		} else {
+			const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
+			constexpr int CC = G::NC >> D; // coarse cells under this fine patch
+			for (int c = m; c < CC; c += G::M) {
+				const int X = c % H, Y = (c / H) % H, Z = (D == 2) ? 0 : c / (H * H);
+				double    v = 0.0;
+				if (D == 2) {
+					auto blk = [&](int s, int I) { return (Rp[s][2 * I] + Rp[s][2 * I + 1]) / 4.0; };
+					if (X == 0) v += blk(0, Y);
+					if (X == H - 1) v += blk(1, Y);
+					if (Y == 0) v += blk(2, X);
+					if (Y == H - 1) v += blk(3, X);
+					dst[(Y + oy) * N + (X + ox)] = v;
+				} else {
+					auto blk = [&](int s, int I, int J) {
+						const double *q = &Rp[s][2 * I + N * 2 * J];
+						return ((q[0] + q[1]) + (q[N] + q[N + 1])) / 8.0;
+					};
+					if (X == 0) v += blk(0, Y, Z);
+					if (X == H - 1) v += blk(1, Y, Z);
+					if (Y == 0) v += blk(2, X, Z);
+					if (Y == H - 1) v += blk(3, X, Z);
+					if (Z == 0) v += blk(4, X, Y);
+					if (Z == H - 1) v += blk(5, X, Y);
+					dst[((Z + oz) * N + (Y + oy)) * N + (X + ox)] = v;
+				}
+			}
+		}
+	}
+	__syncthreads();
+}
 template <int D, int N, bool DIFF>
 __global__ void __launch_bounds__(TGPU_THREADS)
 face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
                               const double *__restrict__ Fold, double *__restrict__ coarse)
 {
-	using G         = Geo<D, N>;
+	using G = Geo<D, N>;
 	pdl_launch_dependents();
 	pdl_wait();
-	constexpr int H = N / 2;
 	__shared__ double R[G::PPB][G::S][G::M];
 	const int t = threadIdx.x, pp = t / G::M, m = t % G::M;
 	const int nblk = (P - p0 + G::PPB - 1) / G::PPB;
 	for (int g = blockIdx.x; g < nblk; g += gridDim.x) {
-		const int  p     = p0 + g * G::PPB + pp;
-		const bool valid = p < P;
-		int        orth = -1, parent = 0;
-		if (valid) {
-			const PatchMeta &pm = meta[p];
-			orth                = pm.orth_on_parent;
-			parent              = pm.parent_idx;
-			const double cfac   = 2.0 * pm.inv_h2;
-			int          ty[G::S];
-			double       own[G::S], gm[G::S];
-			const FaceVals<D, N, DIFF ? FV_DIFF : FV_NEG> fv{Fnew, Fold, meta};
-			gamma_all_sides(pm, p, m, fv, ty, own, gm);
+		const int p = p0 + g * G::PPB + pp;
+		frr_patch<D, N, DIFF>(meta, p, p < P, m, R[pp], Fnew, Fold, coarse);
+	}
+}
+// D = 3, N = 16: refined patches whose six sides have same-level neighbours (or none) -- every patch of a uniform
+// level -- go through a leaner path: one thread per COARSE face entry (6 x 64 per patch) loads its 2 x 2 block of the
+// patch's and the neighbour's slices with four 128-bit loads and stores the block average; the 512 coarse cells are
+// then assembled two per thread and stored as double2.  Same expressions and summation order as frr_patch (the
+// results are bit-identical); other patches take frr_patch.
+#ifndef FRR16_MINB
+#define FRR16_MINB 8 // 32 registers: every CTA of the grid (8 per SM) resident at once; the kernel is latency bound
+#endif
+template <bool DIFF>
+__global__ void __launch_bounds__(TGPU_THREADS, FRR16_MINB)
+face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
+                                const double *__restrict__ Fold, double *__restrict__ coarse)
+{
+	using G = Geo<3, 16>;
+	pdl_launch_dependents();
+	pdl_wait();
+	__shared__ __align__(16) double R[G::S][G::M]; // fast path uses the first 6 x 64 entries as Rc[s][c]
+	const int t = threadIdx.x;
+	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
+		const int        p  = p0 + g;
+		const PatchMeta &pm = meta[p];
+		bool             fast = pm.orth_on_parent >= 0;
 #pragma unroll
-			for (int s = 0; s < G::S; s++) R[pp][s][m] = (ty[s] == NBR_NONE) ? 0.0 : cfac * gm[s];
+		for (int s = 0; s < 6; s++) fast = fast && pm.nbr_type[s] <= NBR_NORMAL;
+		if (!fast) { // CTA-uniform
+			frr_patch<3, 16, DIFF>(meta, p, true, t, R, Fnew, Fold, coarse);
+			continue;
+		}
+		const double cfac = 2.0 * pm.inv_h2;
+		double *     Rc   = &R[0][0];
+		for (int e = t; e < 6 * 64; e += TGPU_THREADS) {
+			const int s = e >> 6, c = e & 63, m0 = 2 * (c & 7) + 32 * (c >> 3);
+			double    val = 0.0;
+			if (pm.nbr_type[s] == NBR_NORMAL) {
+				const size_t oa = ((size_t) p * 6 + s) * 256 + m0, ob = ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 256 + m0;
+				auto ld = [&](size_t o) {
+					double2 v = __ldg(reinterpret_cast<const double2 *>(Fnew + o));
+					if (DIFF) {
+						const double2 w = __ldg(reinterpret_cast<const double2 *>(Fold + o));
+						v.x = w.x - v.x, v.y = w.y - v.y;
+					} else {
+						v.x = -v.x, v.y = -v.y;
+					}
+					return v;
+				};
+				const double2 a0 = ld(oa), a1 = ld(oa + 16), b0 = ld(ob), b1 = ld(ob + 16);
+				const double  r00 = cfac * (0.5 * a0.x + 0.5 * b0.x), r01 = cfac * (0.5 * a0.y + 0.5 * b0.y);
+				const double  r10 = cfac * (0.5 * a1.x + 0.5 * b1.x), r11 = cfac * (0.5 * a1.y + 0.5 * b1.y);
+				val               = ((r00 + r01) + (r10 + r11)) / 8.0;
+			}
+			Rc[e] = val;
 		}
 		__syncthreads();
-		if (valid) {
-			double *dst                = coarse + (size_t) parent * G::NC;
-			const double(*Rp)[G::M]    = R[pp];
-			if (orth < 0) { // patch present on both levels: coarse = r (dense, zero in the interior)
-				const int x = m % N, y = (D == 2) ? 0 : m / N;
-#pragma unroll 4
-				for (int k = 0; k < N; k++) {
-					double v = 0.0;
-					if (D == 2) {
-						if (x == 0) v += Rp[0][k];
-						if (x == N - 1) v += Rp[1][k];
-						if (k == 0) v += Rp[2][x];
-						if (k == N - 1) v += Rp[3][x];
-					} else {
-						if (x == 0) v += Rp[0][y + N * k];
-						if (x == N - 1) v += Rp[1][y + N * k];
-						if (y == 0) v += Rp[2][x + N * k];
-						if (y == N - 1) v += Rp[3][x + N * k];
-						if (k == 0) v += Rp[4][m];
-						if (k == N - 1) v += Rp[5][m];
-					}
-					dst[k * G::M + m] = v;
-				}
-			} else {
-				const int ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
-				constexpr int CC = G::NC >> D; // coarse cells under this fine patch
-				for (int c = m; c < CC; c += G::M) {
-					const int X = c % H, Y = (c / H) % H, Z = (D == 2) ? 0 : c / (H * H);
-					double    v = 0.0;
-					if (D == 2) {
-						auto blk = [&](int s, int I) { return (Rp[s][2 * I] + Rp[s][2 * I + 1]) / 4.0; };
-						if (X == 0) v += blk(0, Y);
-						if (X == H - 1) v += blk(1, Y);
-						if (Y == 0) v += blk(2, X);
-						if (Y == H - 1) v += blk(3, X);
-						dst[(Y + oy) * N + (X + ox)] = v;
-					} else {
-						auto blk = [&](int s, int I, int J) {
-							const double *q = &Rp[s][2 * I + N * 2 * J];
-							return ((q[0] + q[1]) + (q[N] + q[N + 1])) / 8.0;
-						};
-						if (X == 0) v += blk(0, Y, Z);
-						if (X == H - 1) v += blk(1, Y, Z);
-						if (Y == 0) v += blk(2, X, Z);
-						if (Y == H - 1) v += blk(3, X, Z);
-						if (Z == 0) v += blk(4, X, Y);
-						if (Z == H - 1) v += blk(5, X, Y);
-						dst[((Z + oz) * N + (Y + oy)) * N + (X + ox)] = v;
-					}
-				}
+		{
+			const int orth = pm.orth_on_parent;
+			const int ox = (orth & 1) * 8, oy = ((orth >> 1) & 1) * 8, oz = ((orth >> 2) & 1) * 8;
+			const int X = (t & 3) * 2, Y = (t >> 2) & 7, Z = t >> 5; // cells (X, Y, Z) and (X + 1, Y, Z) of the octant
+			double    v[2];
+#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				const int x = X + i;
+				double    a = 0.0;
+				if (x == 0) a += Rc[0 * 64 + Y + 8 * Z];
+				if (x == 7) a += Rc[1 * 64 + Y + 8 * Z];
+				if (Y == 0) a += Rc[2 * 64 + x + 8 * Z];
+				if (Y == 7) a += Rc[3 * 64 + x + 8 * Z];
+				if (Z == 0) a += Rc[4 * 64 + x + 8 * Y];
+				if (Z == 7) a += Rc[5 * 64 + x + 8 * Y];
+				v[i] = a;
 			}
+			double *dst = coarse + (size_t) pm.parent_idx * G::NC + ((Z + oz) * 16 + (Y + oy)) * 16 + (X + ox);
+			*reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
 		}
 		__syncthreads();
 	}

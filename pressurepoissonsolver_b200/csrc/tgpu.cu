@@ -1520,6 +1520,11 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 		if (Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
 		return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
 	}
+	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
+		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 8)), block(TGPU_THREADS);
+		if (Fold) return launch(h->ctx, face_residual_restrict16_kernel<true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		return launch(h->ctx, face_residual_restrict16_kernel<false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;

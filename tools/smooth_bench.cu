@@ -104,6 +104,16 @@ int main(int argc, char **argv)
 	time_it("plain gamma faces-only", reps, b16, [&] { smooth3d16_kernel<false, true, false, false><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
 	if (G > 1) time_it("prolong gamma write_u", reps, b16, [&] { smooth3d16_kernel<false, false, true, true><<<grid, blk, sm>>>(meta, 0, P, f, u, Fa, Fb, eig, uc); });
 	if (G > 1) time_it("face_residual_restrict", reps, b16, [&] { face_residual_restrict_kernel<3, 16, false><<<std::min(P, sms * 8), 256>>>(meta, 0, P, Fa, nullptr, coarse); });
+	if (G > 1) {
+		double *coarse2;
+		CK(cudaMalloc(&coarse2, ncc * 8));
+		time_it("face_residual_restrict16", reps, b16, [&] { face_residual_restrict16_kernel<false><<<std::min(P, sms * 8), 256>>>(meta, 0, P, Fa, nullptr, coarse2); });
+		std::vector<double> a(ncc), b(ncc);
+		CK(cudaMemcpy(a.data(), coarse, ncc * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), coarse2, ncc * 8, cudaMemcpyDeviceToHost));
+		size_t bad = 0;
+		for (size_t i = 0; i < ncc; i++) bad += a[i] != b[i];
+		printf("   coarse right-hand side: %zu of %zu entries differ\n", bad, ncc);
+	}
 	CK(cudaGetLastError());
 	return 0;
 }
