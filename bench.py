@@ -36,9 +36,9 @@ CONFIGS = {
     "small": (3, "3uni.bin", 1, 16, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the two finest-level smoother launches of config B
-# (ncu --set full, profiles/r01_v7_ncu_full_summary.txt: 134.8 + 22.8 MB faces-only sweep, 205.6 + 90.8 MB post-sweep)
-NCU_TRAFFIC_BYTES = (134.8e6 + 4.9e6 + 202.2e6 + 86.5e6) / 2
-NCU_TRAFFIC_SOURCE = "profiles/r01_v9_ncu_full_summary.txt (mean of the two smoother launches on the finest level, IDs 0 and 12)"
+# (ncu --set full, profiles/r01_v11_ncu_full_summary.txt: 134.8 + 5.2 MB faces-only sweep, 202.2 + 85.9 MB post-sweep)
+NCU_TRAFFIC_BYTES = (134.8e6 + 5.2e6 + 202.2e6 + 85.9e6) / 2
+NCU_TRAFFIC_SOURCE = "profiles/r01_v11_ncu_full_summary.txt (mean of the two smoother launches on the finest level, IDs 0 and 12)"
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
 SMOOTH_BYTES_PER_CELL = 16.0      # dominant kernel: read f, write u
 
