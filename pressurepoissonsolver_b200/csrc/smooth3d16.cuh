@@ -122,16 +122,8 @@ template <bool PROLONG> struct SideGamma16 {
 		a1 = b1 = 0.0;
 		if (PROLONG) {
 			const int fl = d.flags, sa = fl & GD_SA, sb = (fl >> 1) & 1;
-#if S16_ABL == 1
-			a1 = __ldg(uc + o.z + t + sa);
-			b1 = __ldg(uc + o.w + t + sb);
-#elif S16_ABL == 2
-			a1 = (double) (o.z + sa);
-			b1 = (double) (o.w + sb);
-#else
 			a1 = __ldg(uc + o.z + ((lo >> sa) * A + (hi >> sa) * B));
 			b1 = __ldg(uc + o.w + ((lo >> sb) * A + (hi >> sb) * B));
-#endif
 		}
 	}
 	__device__ __forceinline__ double finish(const GPatch16 &gp, int s, const PatchMeta *__restrict__ meta, int p, int t,
