@@ -448,6 +448,89 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 }
 
 // ---------------------------------------------------------------------------------------------
+// smooth3d32n_kernel: 32^3 levels that contain patches with Neumann domain sides (PatchSolvers/FftwPatchSolver.h:
+// 115-127,197; DftPatchSolver.h:115-127,150-165).  General path, same arithmetic as the Neumann branch of
+// smooth_kernel: per axis the transform pair and eigenvalues follow the two closures (axis_kind), dense 32 x 32
+// transforms with the matrices of DftPatchSolver.h:237-289 (mats), eigenvalue sums formed on the fly (lam), zero mode
+// removed on an all-Neumann patch.  One CTA per patch, the patch lives in a CTA-private 256 KB block of `scratch`
+// (L2-resident: the block is reused for every patch of the CTA); the variant switches are run-time arguments.
+// Correctness path, not a fast one: 6 x 1024 multiply-adds per cell.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TGPU_THREADS)
+smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
+                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ uc,
+                   const double *__restrict__ mats, const double *__restrict__ lam, double *__restrict__ scratch, int zero_guess,
+                   int emit, int prolong, int write_u)
+{
+	constexpr int N = 32, M = N * N, NC = M * N;
+	const int     t = threadIdx.x;
+	double *      W = scratch + (size_t) blockIdx.x * NC;
+	pdl_launch_dependents();
+	pdl_wait();
+	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
+		const int        p    = p0 + g;
+		const PatchMeta &pm   = meta[p];
+		const int        neu  = pm.neumann;
+		const double     cfac = 2.0 * pm.inv_h2, h2 = pm.h2;
+		for (int i = t; i < NC; i += TGPU_THREADS) W[i] = __ldg(f + (size_t) p * NC + i);
+		__syncthreads();
+		if (!zero_guess) { // f - (2/h^2) E^T gamma, side by side (edge cells belong to several sides)
+			for (int s = 0; s < 6; s++) {
+				if (pm.nbr_type[s] != NBR_NONE) {
+					for (int m = t; m < M; m += TGPU_THREADS) {
+						const double gm = prolong ? gamma_entry32<true>(meta, p, s, m, Fin, uc) : gamma_entry32<false>(meta, p, s, m, Fin, uc);
+						int          c[3];
+						face_cell<3, N>(s, m, c);
+						W[(c[2] * N + c[1]) * N + c[0]] -= cfac * gm;
+					}
+				}
+				__syncthreads();
+			}
+		}
+		double v[N];
+		// forward along z, y, x; then inverse along x, y, z (pass 2 also divides by the eigenvalue sums first)
+		for (int pass = 0; pass < 6; pass++) {
+			const int      axis = pass < 3 ? 2 - pass : pass - 3;
+			const AxisKind ak   = axis_kind(neu, axis);
+			const double * T    = mats + (size_t) (pass < 3 ? ak.fwd : ak.inv) * N * N;
+			const int      step = axis == 0 ? 1 : (axis == 1 ? N : M);
+			if (pass == 3) {
+				const AxisKind kx = axis_kind(neu, 0), ky = axis_kind(neu, 1), kz = axis_kind(neu, 2);
+				const double   scale = h2 * (2.0 / N) * (2.0 / N) * (2.0 / N);
+				const bool     singular = neu == 63;
+				for (int i = t; i < NC; i += TGPU_THREADS) {
+					const double sum = __ldg(lam + kx.lam * N + i % N) + (__ldg(lam + ky.lam * N + (i / N) % N) + __ldg(lam + kz.lam * N + i / M));
+					W[i]             = (singular && i == 0) ? 0.0 : W[i] * scale / sum;
+				}
+				__syncthreads();
+			}
+			for (int q = t; q < M; q += TGPU_THREADS) {
+				const int base = axis == 0 ? q * N : (axis == 1 ? (q % N) + (q / N) * M : q);
+#pragma unroll
+				for (int j = 0; j < N; j++) v[j] = W[base + j * step];
+#pragma unroll 1
+				for (int k = 0; k < N; k++) {
+					double acc = 0.0;
+#pragma unroll
+					for (int j = 0; j < N; j++) acc = fma(__ldg(T + k * N + j), v[j], acc);
+					W[base + k * step] = acc;
+				}
+			}
+			__syncthreads();
+		}
+		if (write_u)
+			for (int i = t; i < NC; i += TGPU_THREADS) u[(size_t) p * NC + i] = W[i];
+		if (emit)
+			for (int i = t; i < 6 * M; i += TGPU_THREADS) {
+				int c[3];
+				face_cell<3, N>(i / M, i % M, c);
+				Fout[(size_t) p * 6 * M + i] = W[(c[2] * N + c[1]) * N + c[0]];
+			}
+		__syncthreads(); // the block is refilled next
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // operator apply / residual for 32^3 patches: one (patch, z slab) item per iteration.  Tile with a
 // ghost layer [10][34][36] (interior rows start 16-byte aligned at column 2).  MODE 0: out = A u,
 // MODE 1: out = f - A u.  Ghost = 2 gamma - a (neighbour), -a (Dirichlet), +a (Neumann), StarPatchOp.h:46-64.

@@ -212,6 +212,7 @@ struct tgpu_hier {
 	int                   D = 0, N = 0;
 	std::vector<LevelDev> levels;
 	double *              eig = nullptr; // [N^D]
+	double *              scratch32 = nullptr; // smooth3d32n_kernel (32^3 levels with Neumann sides): one 256 KB block per CTA
 	double *              cycle_faces = nullptr; // boundary slices of the last cycle's result (level 0), if it was asked to emit them
 	double *              tri = nullptr; // [N/2 + 1][N^(D-1)] tridiagonal multipliers (TriSolve)
 	double *              mats = nullptr, *lam = nullptr; // Neumann patches: transform matrices [6][N][N], 1-D eigenvalues [3][N]
@@ -390,6 +391,8 @@ static int setup_3d32(tgpu_hier *h)
 	CU(cudaFuncSetAttribute(apply3d32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
+	for (const LevelDev &L : h->levels)
+		if (L.has_neumann && !h->scratch32) CU(cudaMalloc(&h->scratch32, (size_t) h->ctx->sm_count * 2 * 32768 * sizeof(double)));
 	return TGPU_OK;
 }
 template <int D, int N> static int set_smem_attrs()
@@ -1175,6 +1178,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	cudaFree(h->mats);
 	cudaFree(h->lam);
 	cudaFree(h->eig);
+	cudaFree(h->scratch32);
 	cudaFree(h->tri);
 	delete h;
 	return TGPU_OK;
@@ -1356,8 +1360,7 @@ static int check_level_vec(const tgpu_hier *h, int level, const tgpu_vec *v, con
 }
 static int need_smoother(const tgpu_hier *h, int level)
 {
-	if (h->levels[level].has_neumann && is_3d32(h))
-		return fail(TGPU_ERR_UNSUPPORTED, "patch solver: Neumann domain sides are not implemented for 32^3 patches yet");
+	(void) h, (void) level; // every (D, n, closure) combination has a kernel
 	return TGPU_OK;
 }
 
@@ -1427,6 +1430,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
+	if (is_3d32(h) && L.has_neumann) { // general transform path through an L2-resident scratch block
+		const int nblk = std::min(p1 - p0, h->ctx->sm_count * 2);
+		if (!h->scratch32) return fail(TGPU_ERR_ARG, "k_smooth: scratch for 32^3 Neumann levels missing");
+		return launch(h->ctx, smooth3d32n_kernel, dim3(nblk), dim3(TGPU_THREADS), 0, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, uc,
+		              (const double *) h->mats, (const double *) h->lam, h->scratch32, (int) zero_guess, (int) emit, (int) (uc != nullptr), (int) write_u);
+	}
 	if (is_3d32(h)) {
 		// one cluster of two CTAs (two SMs) per patch, see smooth3d32c_kernel
 		const dim3   grid(2 * std::min(p1 - p0, h->ctx->sm_count / 2)), block(C32_THREADS);
