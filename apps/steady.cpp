@@ -4,6 +4,9 @@
 // mirrored plugin surface in include/tgpu_plugin.hpp.  Every numerical step runs on the GPU.
 //
 // usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--out u.bin]
+//               [--neumann] [--problem trig|gauss]
+//   --neumann Neumann domain boundaries (ThundereggDomGen(..., neumann = true), Init::initNeumann, right-hand-side mean
+//             removed as in apps/3d/steady.cpp:301,316-334; 3D); --problem gauss: the app's second manufactured problem
 //   --plugin  drive the cycle through the virtual Level/Smoother/Operator/Restrictor/Interpolator
 //             objects (one ABI call per step, like the reference) instead of the fused tgpu_vcycle
 #include <chrono>
@@ -21,23 +24,34 @@ template <size_t D> static int run(int argc, char **argv)
 	const std::string mesh_file = argv[2];
 	const int         divide = atoi(argv[3]), n = atoi(argv[4]);
 	GMG::CycleOpts    copts;
-	bool              plugin = false;
-	std::string       out;
+	bool              plugin = false, neumann = false;
+	std::string       out, problem = "trig";
 	for (int a = 5; a < argc; a++) {
 		if (!strcmp(argv[a], "--cycle") && a + 1 < argc) copts.cycle_type = argv[++a];
 		else if (!strcmp(argv[a], "--pre") && a + 1 < argc) copts.pre_sweeps = atoi(argv[++a]);
 		else if (!strcmp(argv[a], "--post") && a + 1 < argc) copts.post_sweeps = atoi(argv[++a]);
 		else if (!strcmp(argv[a], "--plugin")) plugin = true;
+		else if (!strcmp(argv[a], "--neumann")) neumann = true;
+		else if (!strcmp(argv[a], "--problem") && a + 1 < argc) problem = argv[++a];
 		else if (!strcmp(argv[a], "--out") && a + 1 < argc) out = argv[++a];
 	}
 	auto ctx = std::make_shared<Context>(0);
 	Mesh mesh(mesh_file, (int) D);
 	for (int i = 0; i < divide; i++) mesh.refineLeaves();
+	if (neumann) mesh.setNeumann(true);
 	auto h = std::make_shared<Hierarchy>(ctx, mesh, n);
 
 	std::shared_ptr<VectorGenerator<D>> vg(new DeviceVG<D>(h, 0));
 	auto u = vg->getNewVector(), exact = vg->getNewVector(), f = vg->getNewVector(), au = vg->getNewVector();
-	check(tgpu_init_trig_rhs(h->p, DeviceVector<D>::raw(f), DeviceVector<D>::raw(exact)));
+	if (neumann) {
+		check(tgpu_init_neumann_rhs(h->p, problem == "gauss" ? 1 : 0, DeviceVector<D>::raw(f), DeviceVector<D>::raw(exact)));
+		double integral = 0, volume = 1;
+		check(tgpu_vec_integrate(h->p, DeviceVector<D>::raw(f), &integral, &volume));
+		std::cout << "Fdiff: " << integral / volume << "\n";
+		f->shift(-integral / volume);
+	} else {
+		check(tgpu_init_trig_rhs(h->p, DeviceVector<D>::raw(f), DeviceVector<D>::raw(exact)));
+	}
 
 	std::shared_ptr<Operator<D>> A(new DeviceOperator<D>(h, 0));
 	std::shared_ptr<Operator<D>> M;
@@ -54,6 +68,11 @@ template <size_t D> static int run(int argc, char **argv)
 	auto resid = vg->getNewVector(), error = vg->getNewVector();
 	resid->addScaled(-1, au, 1, f);
 	error->addScaled(-1, exact, 1, u);
+	if (neumann) { // the solution is determined up to a constant (apps/3d/steady.cpp:539-548 shifts the error by the difference of the two averages)
+		double ie = 0, vol = 1;
+		check(tgpu_vec_integrate(h->p, DeviceVector<D>::raw(error), &ie, &vol));
+		error->shift(-ie / vol);
+	}
 	std::cout.precision(13);
 	std::cout << "Iterations: " << its << "\n";
 	std::cout << "Error (2-norm):   " << error->twoNorm() / exact->twoNorm() << "\n";
@@ -73,7 +92,7 @@ template <size_t D> static int run(int argc, char **argv)
 int main(int argc, char **argv)
 {
 	if (argc < 5) {
-		std::cerr << "usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--out u.bin]\n";
+		std::cerr << "usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--out u.bin] [--neumann] [--problem trig|gauss]\n";
 		return 2;
 	}
 	try {

@@ -12,6 +12,7 @@
  *
  * usage: ref_gmg D mesh.bin divide n dft|fftw[-neumann] cmd [cmd...]
  *   (suffix -neumann: ThundereggDomGen(tree, ns, neumann = true), apps/3d/steady.cpp:301)
+ *   cmd rhsn:trig|gauss:f.bin:exact.bin  (3D) the reference's Init::initNeumann on the app's manufactured problems
  *   meta:OUT                         hierarchy metadata (format: see dump_meta)
  *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
  *   apply:L:U_IN:OUT                 OUT = A_L U                (level 0 = finest)
@@ -110,6 +111,45 @@ template <> struct Traits<3> {
 		};
 		Init::initDirichlet(d, f, e, ffun, gfun);
 	}
+	/* Init::initNeumann with the manufactured problems of apps/3d/steady.cpp:230-282 ("gauss", default trig) */
+	static void rhs_neumann(Domain<3> &d, Vec f, Vec e, const string &problem)
+	{
+		function<double(double, double, double)> ffun, gfun, nfunx, nfuny, nfunz;
+		if (problem == "gauss") {
+			gfun = [](double x, double y, double z) { return exp(cos(10 * M_PI * x)) - exp(cos(11 * M_PI * y)) + exp(cos(12 * M_PI * z)); };
+			ffun = [](double x, double y, double z) {
+				return -M_PI * M_PI
+				       * (100 * exp(cos(10 * M_PI * x)) * cos(10 * M_PI * x) - 100 * exp(cos(10 * M_PI * x)) * pow(sin(10 * M_PI * x), 2)
+				          - 121 * exp(cos(11 * M_PI * y)) * cos(11 * M_PI * y) + 121 * exp(cos(11 * M_PI * y)) * pow(sin(11 * M_PI * y), 2)
+				          + 144 * exp(cos(12 * M_PI * z)) * cos(12 * M_PI * z) - 144 * exp(cos(12 * M_PI * z)) * pow(sin(12 * M_PI * z), 2));
+			};
+			nfunx = [](double x, double y, double z) { return -10 * M_PI * sin(10 * M_PI * x) * exp(cos(10 * M_PI * x)); };
+			nfuny = [](double x, double y, double z) { return 11 * M_PI * sin(11 * M_PI * y) * exp(cos(11 * M_PI * y)); };
+			nfunz = [](double x, double y, double z) { return -12 * M_PI * sin(12 * M_PI * z) * exp(cos(12 * M_PI * z)); };
+		} else {
+			ffun = [](double x, double y, double z) {
+				x += .3; y += .3; z += .3;
+				return -77.0 / 36 * M_PI * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+			};
+			gfun = [](double x, double y, double z) {
+				x += .3; y += .3; z += .3;
+				return sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+			};
+			nfunx = [](double x, double y, double z) {
+				x += .3; y += .3; z += .3;
+				return M_PI * cos(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+			};
+			nfuny = [](double x, double y, double z) {
+				x += .3; y += .3; z += .3;
+				return -2.0 / 3 * M_PI * sin(M_PI * x) * sin(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+			};
+			nfunz = [](double x, double y, double z) {
+				x += .3; y += .3; z += .3;
+				return 5.0 / 6 * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * cos(5.0 / 6 * M_PI * z);
+			};
+		}
+		Init::initNeumann(d, f, e, ffun, gfun, nfunx, nfuny, nfunz);
+	}
 };
 template <> struct Traits<2> {
 	using Factory = GMG::CycleFactory2d;
@@ -120,6 +160,7 @@ template <> struct Traits<2> {
 		auto gfun = [](double x, double y) { return (double) (sinl(M_PI * y) * cosl(2 * M_PI * x)); };
 		Init::initDirichlet2d(d, f, e, ffun, gfun);
 	}
+	static void rhs_neumann(Domain<2> &, Vec, Vec, const string &) { cerr << "rhsn: 3D only\n"; exit(2); }
 };
 
 template <size_t D> struct Ctx {
@@ -247,6 +288,12 @@ template <size_t D> static int run(int argc, char **argv)
 			Traits<D>::rhs(*c.domains[0], f->vec, e->vec);
 			write_from(p[1], f->vec);
 			write_from(p[2], e->vec);
+		} else if (cmd == "rhsn") { /* rhsn:problem:f:exact  -> Init::initNeumann, then prints integrate(f) / volume (apps/3d/steady.cpp:330-334) */
+			auto f = newvec(0), e = newvec(0);
+			Traits<D>::rhs_neumann(*c.domains[0], f->vec, e->vec, p[1]);
+			write_from(p[2], f->vec);
+			write_from(p[3], e->vec);
+			printf("{\"fdiff\": %.17g, \"volume\": %.17g}\n", c.domains[0]->integrate(f) / c.domains[0]->volume(), c.domains[0]->volume());
 		} else if (cmd == "apply") {
 			int  l = stoi(p[1]);
 			auto u = newvec(l), o = newvec(l);

@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "tgpu_vec_scale_then_add_scaled2", "tgpu_vec_two_norm", "tgpu_vec_inf_norm", "tgpu_vec_dot", "tgpu_apply",
     "tgpu_residual", "tgpu_smooth", "tgpu_smooth_jacobi", "tgpu_restrict", "tgpu_prolong_add",
     "tgpu_residual_restrict", "tgpu_cycle_opts_default", "tgpu_vcycle", "tgpu_bicgstab", "tgpu_vcycle_host",
-    "tgpu_init_trig_rhs", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
+    "tgpu_init_trig_rhs", "tgpu_init_neumann_rhs", "tgpu_vec_integrate", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
     "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann", "tgpu_vcycle_host_async", "tgpu_vcycle_host_wait",
 ]
@@ -120,6 +120,8 @@ for _name, _args in {
                       C.POINTER(C.c_double)],
     "tgpu_vcycle_host": [_vp, C.POINTER(CycleOpts), _vp, _vp],
     "tgpu_init_trig_rhs": [_vp, _vp, _vp],
+    "tgpu_init_neumann_rhs": [_vp, C.c_int, _vp, _vp],
+    "tgpu_vec_integrate": [_vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "tgpu_mesh_partition": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)], "tgpu_part_destroy": [_vp],
     "tgpu_part_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "tgpu_part_level": [_vp, C.c_int, C.POINTER(LevelDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -457,6 +459,16 @@ class Hierarchy:
 
     def init_trig_rhs(self, f, exact=None):
         check(lib.tgpu_init_trig_rhs(self._p, f._p, exact._p if exact is not None else None))
+
+    def init_neumann_rhs(self, f, exact=None, problem="trig"):
+        """Init::initNeumann (apps/shared/Init.cpp:57-151) on the 3D manufactured problems `trig` / `gauss`"""
+        check(lib.tgpu_init_neumann_rhs(self._p, {"trig": 0, "gauss": 1}[problem], f._p, exact._p if exact is not None else None))
+
+    def integrate(self, v):
+        """(Domain::integrate(v), Domain::volume()), Domain.h:237-278"""
+        a, b = C.c_double(), C.c_double()
+        check(lib.tgpu_vec_integrate(self._p, v._p, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def close(self):
         if self._p:

@@ -1591,6 +1591,97 @@ __global__ void init_trig_kernel(const PatchMeta *__restrict__ meta, int P, cons
 		if (exact) exact[i] = trig_exact<D>(x[0], x[1], x[2]);
 	}
 }
+// Neumann form of the right-hand side (Init::initNeumann, apps/shared/Init.cpp:57-151) for the 3D manufactured problems
+// of apps/3d/steady.cpp:230-282: problem 0 = trig (the one above), 1 = "gauss".  On a domain side without a neighbour the
+// boundary cell gets +dg/dx_a (lower side) / -dg/dx_a (upper side), evaluated on the face, divided by h_a.
+struct Problem3 {
+	int kind;
+	__device__ __forceinline__ double g(double x, double y, double z) const
+	{
+		if (kind == 1) return exp(cos(10 * M_PI * x)) - exp(cos(11 * M_PI * y)) + exp(cos(12 * M_PI * z));
+		return trig_exact<3>(x, y, z);
+	}
+	__device__ __forceinline__ double f(double x, double y, double z) const
+	{
+		if (kind == 1)
+			return -M_PI * M_PI
+			       * (100 * exp(cos(10 * M_PI * x)) * cos(10 * M_PI * x) - 100 * exp(cos(10 * M_PI * x)) * pow(sin(10 * M_PI * x), 2)
+			          - 121 * exp(cos(11 * M_PI * y)) * cos(11 * M_PI * y) + 121 * exp(cos(11 * M_PI * y)) * pow(sin(11 * M_PI * y), 2)
+			          + 144 * exp(cos(12 * M_PI * z)) * cos(12 * M_PI * z) - 144 * exp(cos(12 * M_PI * z)) * pow(sin(12 * M_PI * z), 2));
+		return trig_rhs<3>(x, y, z);
+	}
+	__device__ __forceinline__ double dg(int axis, double x, double y, double z) const
+	{
+		if (kind == 1) {
+			if (axis == 0) return -10 * M_PI * sin(10 * M_PI * x) * exp(cos(10 * M_PI * x));
+			if (axis == 1) return 11 * M_PI * sin(11 * M_PI * y) * exp(cos(11 * M_PI * y));
+			return -12 * M_PI * sin(12 * M_PI * z) * exp(cos(12 * M_PI * z));
+		}
+		x += .3, y += .3, z += .3;
+		if (axis == 0) return M_PI * cos(M_PI * x) * cos(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+		if (axis == 1) return -2.0 / 3 * M_PI * sin(M_PI * x) * sin(2.0 / 3 * M_PI * y) * sin(5.0 / 6 * M_PI * z);
+		return 5.0 / 6 * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * cos(5.0 / 6 * M_PI * z);
+	}
+};
+template <int N>
+__global__ void init_neumann3_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ starts,
+                                     const double *__restrict__ spacing, double *__restrict__ f, double *__restrict__ exact, int problem)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	using G            = Geo<3, N>;
+	const Problem3 pr{problem};
+	const size_t   total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int        ci = (int) (i % G::NC);
+		const size_t     p  = i / G::NC;
+		const PatchMeta &pm = meta[p];
+		const int        c[3] = {ci % N, (ci / N) % N, ci / (N * N)};
+		double           h[3], st[3], x[3];
+		for (int a = 0; a < 3; a++) {
+			h[a]  = spacing[p * 3 + a];
+			st[a] = starts[p * 3 + a];
+			x[a]  = st[a] + h[a] / 2.0 + h[a] * c[a];
+		}
+		double val = pr.f(x[0], x[1], x[2]);
+		for (int a = 0; a < 3; a++) { // west, east, south, north, bottom, top (the order of Init.cpp:90-148)
+			double xb[3] = {x[0], x[1], x[2]};
+			if (c[a] == 0 && pm.nbr_type[2 * a] == NBR_NONE) {
+				xb[a] = st[a];
+				val += pr.dg(a, xb[0], xb[1], xb[2]) / h[a];
+			}
+			if (c[a] == N - 1 && pm.nbr_type[2 * a + 1] == NBR_NONE) {
+				xb[a] = st[a] + h[a] * N;
+				val -= pr.dg(a, xb[0], xb[1], xb[2]) / h[a];
+			}
+		}
+		f[i] = val;
+		if (exact) exact[i] = pr.g(x[0], x[1], x[2]);
+	}
+}
+// per-patch sums times the cell volume (Domain::integrate, Domain.h:258-278): out[p] = prod_a h_a * sum of the patch
+template <int D, int N>
+__global__ void patch_integrals_kernel(int P, const double *__restrict__ spacing, const double *__restrict__ v, double *__restrict__ out)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	using G = Geo<D, N>;
+	__shared__ double part[8];
+	for (int p = blockIdx.x; p < P; p += gridDim.x) {
+		double acc = 0.0;
+		for (int i = threadIdx.x; i < G::NC; i += blockDim.x) acc += v[(size_t) p * G::NC + i];
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double s = 0.0;
+			for (int w = 0; w < (int) (blockDim.x >> 5); w++) s += part[w];
+			for (int a = 0; a < D; a++) s *= spacing[(size_t) p * D + a];
+			out[p] = s;
+		}
+		__syncthreads();
+	}
+}
 } // namespace tgpu
 #include "smooth3d16.cuh"
 #include "patch3d32.cuh"

@@ -2225,6 +2225,70 @@ extern "C" int tgpu_bicgstab(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu
 	API_END
 }
 
+extern "C" int tgpu_init_neumann_rhs(tgpu_hier *h, int problem, tgpu_vec *f, tgpu_vec *exact)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, f, "tgpu_init_neumann_rhs"));
+	if (exact) TRY(check_level_vec(h, 0, exact, "tgpu_init_neumann_rhs"));
+	if (h->D != 3) return fail(TGPU_ERR_UNSUPPORTED, "tgpu_init_neumann_rhs: 3D only");
+	if (problem != 0 && problem != 1) return fail(TGPU_ERR_ARG, "tgpu_init_neumann_rhs: problem must be 0 (trig) or 1 (gauss)");
+	LevelDev &L = h->levels[0];
+	if (!L.starts) return fail(TGPU_ERR_ARG, "tgpu_init_neumann_rhs: hierarchy was created without patch starts");
+	const dim3 grid(grid_for(h->ctx, L.ncells)), block(256);
+	double *   ex = exact ? exact->d : (double *) nullptr;
+	switch (h->N) {
+#define NCASE(NN) \
+	case NN: return launch(h->ctx, init_neumann3_kernel<NN>, grid, block, 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, ex, problem);
+		NCASE(4) NCASE(8) NCASE(16) NCASE(32)
+#undef NCASE
+	default: return fail(TGPU_ERR_UNSUPPORTED, "tgpu_init_neumann_rhs: patch size");
+	}
+	API_END
+}
+extern "C" int tgpu_vec_integrate(tgpu_hier *h, const tgpu_vec *v, double *integral, double *volume)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, v, "tgpu_vec_integrate"));
+	if (!integral && !volume) return fail(TGPU_ERR_ARG, "tgpu_vec_integrate: nothing asked for");
+	LevelDev &L      = h->levels[0];
+	const int owned  = L.P; // owned patches come first
+	double *  d_part = nullptr;
+	CU(cudaMalloc(&d_part, sizeof(double) * (size_t) std::max(owned, 1)));
+	int rc = TGPU_OK;
+	{
+		Tag tg(h->ctx, "patch_integrals", 0);
+		DISPATCH_DN_ALL(h->D, h->N, rc = launch(h->ctx, patch_integrals_kernel<DD, NN>, dim3(std::min(std::max(owned, 1), h->ctx->sm_count * 8)), dim3(256), 0, owned, (const double *) L.spacing, (const double *) v->d, d_part));
+	}
+	std::vector<double> part((size_t) owned), sp((size_t) owned * h->D);
+	if (rc == TGPU_OK && cudaMemcpyAsync(part.data(), d_part, sizeof(double) * owned, cudaMemcpyDeviceToHost, h->ctx->stream) != cudaSuccess) rc = TGPU_ERR_CUDA;
+	if (rc == TGPU_OK && cudaMemcpyAsync(sp.data(), L.spacing, sizeof(double) * owned * h->D, cudaMemcpyDeviceToHost, h->ctx->stream) != cudaSuccess) rc = TGPU_ERR_CUDA;
+	if (rc == TGPU_OK && cudaStreamSynchronize(h->ctx->stream) != cudaSuccess) rc = TGPU_ERR_CUDA;
+	cudaFree(d_part);
+	if (rc != TGPU_OK) return rc == TGPU_ERR_CUDA ? fail(TGPU_ERR_CUDA, "tgpu_vec_integrate: copy failed") : rc;
+	double res[2] = {0.0, 0.0};
+	for (int p = 0; p < owned; p++) {
+		res[0] += part[p];
+		double vol = 1.0;
+		for (int a = 0; a < h->D; a++) vol *= sp[(size_t) p * h->D + a] * h->N;
+		res[1] += vol;
+	}
+	if (h->ctx->nranks > 1) {
+		double *d2 = nullptr;
+		CU(cudaMalloc(&d2, 2 * sizeof(double)));
+		CU(cudaMemcpyAsync(d2, res, 2 * sizeof(double), cudaMemcpyHostToDevice, h->ctx->stream));
+		rc = k_allreduce_sum(h, d2, 2);
+		if (rc == TGPU_OK) {
+			CU(cudaMemcpyAsync(res, d2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->ctx->stream));
+			CU(cudaStreamSynchronize(h->ctx->stream));
+		}
+		cudaFree(d2);
+		TRY(rc);
+	}
+	if (integral) *integral = res[0];
+	if (volume) *volume = res[1];
+	return TGPU_OK;
+	API_END
+}
 extern "C" int tgpu_init_trig_rhs(tgpu_hier *h, tgpu_vec *f, tgpu_vec *exact)
 {
 	API_BEGIN

@@ -9,6 +9,7 @@ The mesh files under tests/golden/meshes/ are byte copies of the reference's oct
 (test/*.bin, apps/{2d,3d}/meshes/*.bin: data, not source) so that nothing reads /root/reference
 at test time.
 """
+import json
 import os
 import subprocess
 import sys
@@ -78,9 +79,30 @@ def neumann_cases():
             print(name, [L.P for L in levels])
 
 
+def neumann_init_case():
+    """Init::initNeumann (apps/shared/Init.cpp:57-151) on the manufactured problems of apps/3d/steady.cpp:230-282 and the
+    right-hand-side mean the app removes (apps/3d/steady.cpp:330-334), on the refined octree with 8^3 patches"""
+    out = {"mesh": "2refine.bin", "D": 3, "n": 8, "divide": 0}
+    with tempfile.TemporaryDirectory() as tmp:
+        t = lambda k: os.path.join(tmp, k + ".bin")  # noqa: E731
+        for prob in ("trig", "gauss"):
+            txt = subprocess.check_output([REF, "3", os.path.join(HERE, "meshes", "2refine.bin"), "0", "8", "dft-neumann",
+                                           "rhsn:%s:%s:%s" % (prob, t("f"), t("e"))], text=True)
+            info = json.loads(txt.strip().splitlines()[-1])
+            out["f_" + prob] = np.fromfile(t("f"))
+            out["exact_" + prob] = np.fromfile(t("e"))
+            out["fdiff_" + prob] = info["fdiff"]
+            out["volume"] = info["volume"]
+    np.savez_compressed(os.path.join(HERE, "3d_2refine_n8_neumann_init.npz"), **out)
+    print("3d_2refine_n8_neumann_init", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 def main():
+    if "--neumann-init-only" in sys.argv:
+        return neumann_init_case()
     if "--neumann-only" in sys.argv:
         return neumann_cases()
+    neumann_init_case()
     neumann_cases()
     for name, D, mesh, div, n in CASES:
         with tempfile.TemporaryDirectory() as tmp:

@@ -238,6 +238,34 @@ def test_neumann_vs_oracle_seeded(ctx):
         mesh.close()
 
 
+def test_neumann_rhs_initialiser_vs_reference(ctx):
+    """tgpu_init_neumann_rhs / tgpu_vec_integrate against the reference's own Init::initNeumann and Domain::integrate
+    (golden 3d_2refine_n8_neumann_init: trig and gauss problems of apps/3d/steady.cpp on the refined octree)"""
+    g = load_golden("3d_2refine_n8_neumann_init")
+    mesh = pps.Mesh.load(os.path.join(MESHES, str(g["mesh"])), 3).set_neumann(True)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, int(g["n"]))
+    f, e = h.new_vec(0), h.new_vec(0)
+    for prob in ("trig", "gauss"):
+        h.init_neumann_rhs(f, e, prob)
+        assert rel_l2(f.download(), g["f_" + prob]) < 1e-13
+        assert rel_l2(e.download(), g["exact_" + prob]) < 1e-14
+        integral, volume = h.integrate(f)
+        assert abs(volume - float(g["volume"])) < 1e-14
+        assert abs(integral / volume - float(g["fdiff_" + prob])) < 1e-11 * max(1.0, abs(float(g["fdiff_" + prob])))
+    # the app's Neumann solve: remove the mean, BiCGStab + V-cycle, compare with the exact solution up to a constant
+    h.init_neumann_rhs(f, e, "trig")
+    integral, volume = h.integrate(f)
+    f.shift(-integral / volume)
+    u = h.new_vec(0)
+    its, rel = h.bicgstab(f, u, tol=1e-10, max_it=100)
+    assert rel < 1e-10
+    d = u.download() - e.download()
+    d -= d.mean()
+    assert np.linalg.norm(d) / np.linalg.norm(e.download()) < 0.05  # second-order discretisation error on 8^3 patches
+    h.close()
+    mesh.close()
+
+
 def test_coarse_rhs_from_fine_faces_variant():
     """TGPU_FINE_SOURCE=1 (opt-in schedule: the coarse level's first sweep assembles its right-hand side from the
     finer level's faces) must give the default schedule's result; run in a fresh process because the switch is
