@@ -49,6 +49,7 @@ def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret):
     h.vcycle(f, ug, g)
     out["vcycle_graph"] = ug.download().reshape(-1, nc)
     out["fnorm"] = f.two_norm()
+    out["integral"] = h.integrate(f)  # (Domain::integrate(f), Domain::volume()) summed over the ranks
     h.apply(0, f, r)
     out["apply"] = r.download().reshape(-1, nc)
     x = h.new_vec(0)
@@ -90,6 +91,8 @@ def test_distributed_cycle_matches_reference(name):
     assert rel_l2(gather("vcycle"), g["vcycle"]) < 1e-12
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
     assert abs(ret[0]["fnorm"] / np.linalg.norm(g["rhs_f"]) - 1) < 1e-13
+    # unit square / cube; every rank holds the same global sums
+    assert abs(ret[0]["integral"][1] - 1.0) < 1e-12 and all(ret[r]["integral"] == ret[0]["integral"] for r in range(world))
     assert ret[0]["its"] == int(g["bicgstab_info"][0])
     assert rel_l2(gather("x"), g["bicgstab_u"]) < 1e-10
 
