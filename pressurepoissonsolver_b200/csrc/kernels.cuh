@@ -5,13 +5,20 @@
 //                        interface interpolation (TriLinInterp.cpp:60-172 / BilinearInterpolator.cpp:61-117)
 //                        + StarPatchOp::addInterfaceToRHS (StarPatchOp.h:185-203)
 //                        + patch solve (PatchSolvers/FftwPatchSolver.h:174-206, DftPatchSolver.h:173-216)
+//                        size-generic form (and the path for patches with Neumann sides); specialised forms with the same
+//                        arithmetic: smooth3d16_kernel (smooth3d16.cuh), smooth3d32c_kernel / smooth3d32n_kernel
+//                        (patch3d32.cuh), smooth2d32_kernel (smooth2d32.cuh).  Patch solve = Dst2 / Dst3 transforms on
+//                        D - 1 axes (dense halves: generated dst4_fast.cuh) + TriSolve on the remaining axis
+//   face_residual_restrict_kernel / face_residual_restrict16_kernel   r = f - A u right after a sweep, from face data,
+//                        fused with AvgRstr::restrict (GMG/Cycle.h:59-66, GMG/AvgRstr.h:78-113)
 //   apply_kernel         SchurHelper::apply (SchurHelper.h:361-376) + StarPatchOp::applyWithInterface
 //                        (StarPatchOp.h:28-184), optionally fused with r = f - Au (GMG/Cycle.h:59-61)
 //                        and AvgRstr::restrict (GMG/AvgRstr.h:78-113)
 //   extract_faces_kernel the boundary-cell slices LocalData::getSliceOnSide yields (Vector.h:153-177)
 //   prolong_faces_kernel / prolong_add_kernel   DrctIntp::interpolate (GMG/DrctIntp.h:80-113)
 //   restrict_kernel      AvgRstr::restrict (GMG/AvgRstr.h:78-113)
-//   blas1 / reduce       Vector<D> ops (Vector.h:190-321)
+//   blas1 / reduce       Vector<D> ops (Vector.h:190-321); bicg_* fused passes of BiCGStab.h:45-106
+//   init_trig_kernel / init_neumann3_kernel / patch_integrals_kernel   apps/shared/Init.cpp, Domain::integrate
 //
 // Ghost fill: the reference couples patches through interface values gamma.
 // Here every kernel that produces a level vector also emits the 2D boundary-cell slices of each

@@ -1,18 +1,20 @@
 // patch3d32.cuh - kernels for D = 3, N = 32 patches (BASELINE config D).  Included by kernels.cuh.
 //
 // A 32^3 patch is 256 KB of fp64: more than one SM's shared memory, so the one-CTA-one-tile scheme of the
-// smaller sizes does not apply.  Here one CTA still owns a whole patch but walks it in four slabs of
-// eight z planes (64 KB tile):
-//   smooth3d32_kernel   phase A  per z slab: f -> tile, subtract (2/h^2) gamma on the boundary cells,
-//                                DST-II along x and y, result -> a CTA-private 256 KB scratch block
-//                       phase B  DST-II along z, eigenvalue division, DST-III along z: register-only,
-//                                pencils read/written in place in the scratch block (coalesced)
-//                       phase C  per z slab: DST-III along y and x, u and its boundary slices -> global
-//                       The scratch block is reused for every patch the persistent CTA processes, so it
-//                       lives in L2 (296 CTAs x 256 KB = 78 MB of the 126 MB): HBM sees f once and u once,
-//                       exactly like the single-tile kernels.
+// smaller sizes does not apply.
+//   smooth3d32c_kernel  the smoother the library uses: a thread-block cluster of two CTAs holds the whole patch in the
+//                       shared memory of two SMs; x and y are transformed, z is a two-sided tridiagonal elimination split
+//                       over the pair (see the comment above the kernel)
+//   smooth3d32n_kernel  levels with Neumann domain sides: general dense-transform path through an L2-resident scratch block
+//   smooth3d32_kernel   the first version (PR 1), kept as the cross-check of tools/smooth32_bench.cu: one CTA walks the
+//                       patch in four slabs of eight z planes (64 KB tile)
+//                         phase A  per z slab: f -> tile, subtract (2/h^2) gamma on the boundary cells,
+//                                  DST-II along x and y, result -> a CTA-private 256 KB scratch block
+//                         phase B  tridiagonal solve along z, register-only, pencils in place in the scratch block
+//                         phase C  per z slab: DST-III along y and x, u and its boundary slices -> global
+//                       (the scratch block is reused for every patch of the persistent CTA, so it lives in L2)
 //   apply3d32_kernel    operator / residual with fused ghost fill, one (patch, z slab) item at a time
-//   face_residual_restrict32_kernel   residual + restriction from face data (see kernels.cuh)
+//   face_residual_restrict_big_kernel   residual + restriction from face data (see kernels.cuh)
 // Reference functions replaced: same as smooth_kernel / apply_kernel / face_residual_restrict_kernel.
 #pragma once
 
