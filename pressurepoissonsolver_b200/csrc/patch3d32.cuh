@@ -422,7 +422,7 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			if (WRITE_U) {
 				double *up = u + (size_t) p * NC + (size_t) z * M + lane;
 #pragma unroll
-				for (int k = 0; k < N; k++) up[k * N] = v[k];
+				for (int k = 0; k < N; k++) __stcs(up + k * N, v[k]);
 			}
 			if (EMIT) {
 				double *Fp = Fout + (size_t) p * 6 * M;

@@ -166,7 +166,7 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			if (WRITE_U) {
 				double *up = u + (size_t) p * NC + lane;
 #pragma unroll
-				for (int k = 0; k < N; k++) up[k * N] = v[k];
+				for (int k = 0; k < N; k++) __stcs(up + k * N, v[k]);
 			}
 			if (EMIT) {
 				double *Fp = Fout + (size_t) p * 4 * N;

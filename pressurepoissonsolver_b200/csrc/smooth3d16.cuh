@@ -429,7 +429,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			dst3_inverse<N>(v, mg);
 			double *up = u + (size_t) p * G::NC + t;
 #pragma unroll
-			for (int k = 0; k < N; k++) up[k * G::M] = v[k];
+			for (int k = 0; k < N; k++) __stcs(up + k * G::M, v[k]); // streaming store: u is not read again soon, the face buffers should stay in L2
 			if (EMIT) {
 				double *Fp       = Fout + (size_t) p * G::S * G::M;
 				Fp[4 * G::M + t] = v[0];
