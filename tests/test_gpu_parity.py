@@ -238,6 +238,23 @@ def test_neumann_vs_oracle_seeded(ctx):
         mesh.close()
 
 
+@pytest.mark.parametrize("mesh_file,D,n,divide", [("2refine.bin", 3, 16, 1), ("2uni.bin", 3, 32, 0), ("2d2ref.bin", 2, 32, 1)])
+def test_cycle_is_bitwise_reproducible(ctx, mesh_file, D, n, divide):
+    """the specialised kernels hand data between warps, CTAs of a cluster and kernels through shared memory, distributed
+    shared memory and face buffers: a missing barrier would show up as bits that change from run to run"""
+    h, mesh = build(ctx, mesh_file, D, n, divide)
+    fn = np.random.default_rng(21).standard_normal(h.ncells(0))
+    f, u = h.new_vec(0, fn), h.new_vec(0)
+    ref_bits = None
+    for rep in range(12):
+        h.vcycle(f, u, pps.CycleOpts.default(use_graph=rep & 1))
+        bits = u.download().tobytes()
+        ref_bits = ref_bits or bits
+        assert bits == ref_bits, rep
+    h.close()
+    mesh.close()
+
+
 def test_neumann_rhs_initialiser_vs_reference(ctx):
     """tgpu_init_neumann_rhs / tgpu_vec_integrate against the reference's own Init::initNeumann and Domain::integrate
     (golden 3d_2refine_n8_neumann_init: trig and gauss problems of apps/3d/steady.cpp on the refined octree)"""
