@@ -189,9 +189,10 @@ int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part *part, tgpu
 /* ---- manufactured problem (apps/3d/steady.cpp:253-265, apps/2d/steady.cpp:314-316,
  *      apps/shared/Init.cpp:152-245,305-361): f with Dirichlet data folded in, exact solution ---- */
 int tgpu_init_trig_rhs(tgpu_hier *h, tgpu_vec *f, tgpu_vec *exact);
-/* Neumann form (Init::initNeumann, apps/shared/Init.cpp:57-151) of the 3D manufactured problems of
- * apps/3d/steady.cpp:230-282: problem 0 = trig, 1 = "gauss"; every domain side without a neighbour gets the normal
- * derivative of the exact solution folded into f.  3D only (TGPU_ERR_UNSUPPORTED otherwise). */
+/* Neumann form (Init::initNeumann / initNeumann2d, apps/shared/Init.cpp:57-151,246-303) of the manufactured problems of
+ * apps/3d/steady.cpp:230-282 (problem 0 = trig, 1 = "gauss") and apps/2d/steady.cpp:314-318 (2D: trig only, otherwise
+ * TGPU_ERR_UNSUPPORTED); every domain side without a neighbour gets the normal derivative of the exact solution folded
+ * into f. */
 int tgpu_init_neumann_rhs(tgpu_hier *h, int problem, tgpu_vec *f, tgpu_vec *exact);
 /* Domain::integrate (Domain.h:258-278) and Domain::volume (Domain.h:237-256) of a finest-level vector: the app removes
  * integral / volume from a Neumann right-hand side (apps/3d/steady.cpp:330-334).  Sums over all ranks. */

@@ -12,7 +12,7 @@
  *
  * usage: ref_gmg D mesh.bin divide n dft|fftw[-neumann] cmd [cmd...]
  *   (suffix -neumann: ThundereggDomGen(tree, ns, neumann = true), apps/3d/steady.cpp:301)
- *   cmd rhsn:trig|gauss:f.bin:exact.bin  (3D) the reference's Init::initNeumann on the app's manufactured problems
+ *   cmd rhsn:trig|gauss:f.bin:exact.bin  the reference's Init::initNeumann / initNeumann2d on the app's manufactured problems
  *   meta:OUT                         hierarchy metadata (format: see dump_meta)
  *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
  *   apply:L:U_IN:OUT                 OUT = A_L U                (level 0 = finest)
@@ -160,7 +160,16 @@ template <> struct Traits<2> {
 		auto gfun = [](double x, double y) { return (double) (sinl(M_PI * y) * cosl(2 * M_PI * x)); };
 		Init::initDirichlet2d(d, f, e, ffun, gfun);
 	}
-	static void rhs_neumann(Domain<2> &, Vec, Vec, const string &) { cerr << "rhsn: 3D only\n"; exit(2); }
+	/* Init::initNeumann2d with the trig problem of apps/2d/steady.cpp:314-318 */
+	static void rhs_neumann(Domain<2> &d, Vec f, Vec e, const string &problem)
+	{
+		if (problem != "trig") { cerr << "rhsn: 2D has the trig problem only\n"; exit(2); }
+		auto ffun  = [](double x, double y) { return (double) (-5 * M_PI * M_PI * sinl(M_PI * y) * cosl(2 * M_PI * x)); };
+		auto gfun  = [](double x, double y) { return (double) (sinl(M_PI * y) * cosl(2 * M_PI * x)); };
+		auto nfun  = [](double x, double y) { return (double) (-2 * M_PI * sinl(M_PI * y) * sinl(2 * M_PI * x)); };
+		auto nfuny = [](double x, double y) { return (double) (M_PI * cosl(M_PI * y) * cosl(2 * M_PI * x)); };
+		Init::initNeumann2d(d, f, e, ffun, gfun, nfun, nfuny);
+	}
 };
 
 template <size_t D> struct Ctx {

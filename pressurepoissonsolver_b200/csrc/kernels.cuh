@@ -18,7 +18,7 @@
 //   prolong_faces_kernel / prolong_add_kernel   DrctIntp::interpolate (GMG/DrctIntp.h:80-113)
 //   restrict_kernel      AvgRstr::restrict (GMG/AvgRstr.h:78-113)
 //   blas1 / reduce       Vector<D> ops (Vector.h:190-321); bicg_* fused passes of BiCGStab.h:45-106
-//   init_trig_kernel / init_neumann3_kernel / patch_integrals_kernel   apps/shared/Init.cpp, Domain::integrate
+//   init_trig_kernel / init_neumann_kernel / patch_integrals_kernel   apps/shared/Init.cpp, Domain::integrate
 //
 // Ghost fill: the reference couples patches through interface values gamma.
 // Here every kernel that produces a level vector also emits the 2D boundary-cell slices of each
@@ -1630,40 +1630,45 @@ struct Problem3 {
 		return 5.0 / 6 * M_PI * sin(M_PI * x) * cos(2.0 / 3 * M_PI * y) * cos(5.0 / 6 * M_PI * z);
 	}
 };
-template <int N>
-__global__ void init_neumann3_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ starts,
-                                     const double *__restrict__ spacing, double *__restrict__ f, double *__restrict__ exact, int problem)
+// 2D: the trig problem of apps/2d/steady.cpp:314-318 (Init::initNeumann2d, apps/shared/Init.cpp:246-303)
+__device__ __forceinline__ double trig2_dg(int axis, double x, double y)
+{
+	return axis == 0 ? -2 * M_PI * sin(M_PI * y) * sin(2 * M_PI * x) : M_PI * cos(M_PI * y) * cos(2 * M_PI * x);
+}
+template <int D, int N>
+__global__ void init_neumann_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ starts,
+                                    const double *__restrict__ spacing, double *__restrict__ f, double *__restrict__ exact, int problem)
 {
 	pdl_launch_dependents();
 	pdl_wait();
-	using G            = Geo<3, N>;
+	using G            = Geo<D, N>;
 	const Problem3 pr{problem};
 	const size_t   total = (size_t) P * G::NC;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
 		const int        ci = (int) (i % G::NC);
 		const size_t     p  = i / G::NC;
 		const PatchMeta &pm = meta[p];
-		const int        c[3] = {ci % N, (ci / N) % N, ci / (N * N)};
-		double           h[3], st[3], x[3];
-		for (int a = 0; a < 3; a++) {
-			h[a]  = spacing[p * 3 + a];
-			st[a] = starts[p * 3 + a];
+		const int        c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
+		double           h[3] = {0, 0, 0}, st[3] = {0, 0, 0}, x[3] = {0, 0, 0};
+		for (int a = 0; a < D; a++) {
+			h[a]  = spacing[p * D + a];
+			st[a] = starts[p * D + a];
 			x[a]  = st[a] + h[a] / 2.0 + h[a] * c[a];
 		}
-		double val = pr.f(x[0], x[1], x[2]);
-		for (int a = 0; a < 3; a++) { // west, east, south, north, bottom, top (the order of Init.cpp:90-148)
+		double val = (D == 2) ? trig_rhs<2>(x[0], x[1], 0.0) : pr.f(x[0], x[1], x[2]);
+		for (int a = 0; a < D; a++) { // west, east, south, north, bottom, top (the order of Init.cpp:90-148, 270-299)
 			double xb[3] = {x[0], x[1], x[2]};
 			if (c[a] == 0 && pm.nbr_type[2 * a] == NBR_NONE) {
 				xb[a] = st[a];
-				val += pr.dg(a, xb[0], xb[1], xb[2]) / h[a];
+				val += ((D == 2) ? trig2_dg(a, xb[0], xb[1]) : pr.dg(a, xb[0], xb[1], xb[2])) / h[a];
 			}
 			if (c[a] == N - 1 && pm.nbr_type[2 * a + 1] == NBR_NONE) {
 				xb[a] = st[a] + h[a] * N;
-				val -= pr.dg(a, xb[0], xb[1], xb[2]) / h[a];
+				val -= ((D == 2) ? trig2_dg(a, xb[0], xb[1]) : pr.dg(a, xb[0], xb[1], xb[2])) / h[a];
 			}
 		}
 		f[i] = val;
-		if (exact) exact[i] = pr.g(x[0], x[1], x[2]);
+		if (exact) exact[i] = (D == 2) ? trig_exact<2>(x[0], x[1], 0.0) : pr.g(x[0], x[1], x[2]);
 	}
 }
 // per-patch sums times the cell volume (Domain::integrate, Domain.h:258-278): out[p] = prod_a h_a * sum of the patch

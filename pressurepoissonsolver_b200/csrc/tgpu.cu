@@ -2230,19 +2230,11 @@ extern "C" int tgpu_init_neumann_rhs(tgpu_hier *h, int problem, tgpu_vec *f, tgp
 	API_BEGIN
 	TRY(check_level_vec(h, 0, f, "tgpu_init_neumann_rhs"));
 	if (exact) TRY(check_level_vec(h, 0, exact, "tgpu_init_neumann_rhs"));
-	if (h->D != 3) return fail(TGPU_ERR_UNSUPPORTED, "tgpu_init_neumann_rhs: 3D only");
 	if (problem != 0 && problem != 1) return fail(TGPU_ERR_ARG, "tgpu_init_neumann_rhs: problem must be 0 (trig) or 1 (gauss)");
+	if (h->D == 2 && problem != 0) return fail(TGPU_ERR_UNSUPPORTED, "tgpu_init_neumann_rhs: 2D has the trig problem only");
 	LevelDev &L = h->levels[0];
 	if (!L.starts) return fail(TGPU_ERR_ARG, "tgpu_init_neumann_rhs: hierarchy was created without patch starts");
-	const dim3 grid(grid_for(h->ctx, L.ncells)), block(256);
-	double *   ex = exact ? exact->d : (double *) nullptr;
-	switch (h->N) {
-#define NCASE(NN) \
-	case NN: return launch(h->ctx, init_neumann3_kernel<NN>, grid, block, 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, ex, problem);
-		NCASE(4) NCASE(8) NCASE(16) NCASE(32)
-#undef NCASE
-	default: return fail(TGPU_ERR_UNSUPPORTED, "tgpu_init_neumann_rhs: patch size");
-	}
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, init_neumann_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.starts, (const double *) L.spacing, f->d, exact ? exact->d : (double *) nullptr, problem));
 	API_END
 }
 extern "C" int tgpu_vec_integrate(tgpu_hier *h, const tgpu_vec *v, double *integral, double *volume)

@@ -95,6 +95,17 @@ def neumann_init_case():
             out["volume"] = info["volume"]
     np.savez_compressed(os.path.join(HERE, "3d_2refine_n8_neumann_init.npz"), **out)
     print("3d_2refine_n8_neumann_init", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+    # 2D: Init::initNeumann2d, trig problem of apps/2d/steady.cpp:314-318, refined quadtree
+    out = {"mesh": "2d2ref.bin", "D": 2, "n": 8, "divide": 1}
+    with tempfile.TemporaryDirectory() as tmp:
+        t = lambda k: os.path.join(tmp, k + ".bin")  # noqa: E731
+        txt = subprocess.check_output([REF, "2", os.path.join(HERE, "meshes", "2d2ref.bin"), "1", "8", "dft-neumann",
+                                       "rhsn:trig:%s:%s" % (t("f"), t("e"))], text=True)
+        info = json.loads(txt.strip().splitlines()[-1])
+        out["f_trig"], out["exact_trig"] = np.fromfile(t("f")), np.fromfile(t("e"))
+        out["fdiff_trig"], out["volume"] = info["fdiff"], info["volume"]
+    np.savez_compressed(os.path.join(HERE, "2d_2d2ref_d1_n8_neumann_init.npz"), **out)
+    print("2d_2d2ref_d1_n8_neumann_init", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
 def main():

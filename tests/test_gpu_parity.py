@@ -269,7 +269,25 @@ def test_neumann_rhs_initialiser_vs_reference(ctx):
         integral, volume = h.integrate(f)
         assert abs(volume - float(g["volume"])) < 1e-14
         assert abs(integral / volume - float(g["fdiff_" + prob])) < 1e-11 * max(1.0, abs(float(g["fdiff_" + prob])))
+    h.close()
+    mesh.close()
+    # 2D: Init::initNeumann2d, trig problem
+    g2 = load_golden("2d_2d2ref_d1_n8_neumann_init")
+    mesh2 = pps.Mesh.load(os.path.join(MESHES, str(g2["mesh"])), 2).set_neumann(True)
+    mesh2.refine_leaves(int(g2["divide"]))
+    h2 = pps.Hierarchy.from_mesh(ctx, mesh2, int(g2["n"]))
+    f2, e2 = h2.new_vec(0), h2.new_vec(0)
+    h2.init_neumann_rhs(f2, e2, "trig")
+    assert rel_l2(f2.download(), g2["f_trig"]) < 1e-13
+    assert rel_l2(e2.download(), g2["exact_trig"]) < 1e-14
+    integral, volume = h2.integrate(f2)
+    assert abs(volume - 1.0) < 1e-14 and abs(integral / volume - float(g2["fdiff_trig"])) < 1e-11
+    h2.close()
+    mesh2.close()
     # the app's Neumann solve: remove the mean, BiCGStab + V-cycle, compare with the exact solution up to a constant
+    mesh = pps.Mesh.load(os.path.join(MESHES, str(g["mesh"])), 3).set_neumann(True)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, int(g["n"]))
+    f, e = h.new_vec(0), h.new_vec(0)
     h.init_neumann_rhs(f, e, "trig")
     integral, volume = h.integrate(f)
     f.shift(-integral / volume)
