@@ -9,7 +9,8 @@
 //     stores it into the warp's private 32 x 34 tile; lane k_y then reads row k_y (128-bit), eliminates along x,
 //     writes it back; lane x reads column x, transforms back and stores u (and the boundary slices) to memory;
 //   * the eight warps of a CTA drift apart freely, so the fp64, shared-memory and load phases of different
-//     patches overlap on the SM (the lock step of barrier-coupled warps is what limits the 3D kernels);
+//     patches overlap on the SM; with 4 shared-memory accesses and 20 fp64 operations per cell (16^3 kernel: 8 and
+//     33) the kernel ends up bound by HBM;
 //   * the interface values of the warp's next patch are gathered in two batches of two sides, issued before a
 //     transform and combined after it; x-face values (needed by lanes 0 and 31 for every y) pass through a
 //     64-double staging row, y-face values stay in two registers.
