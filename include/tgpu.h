@@ -61,6 +61,13 @@ typedef struct TgpuCycleOpts {
 	int32_t fused;         /* 1 (default) = fused kernel schedule (face-only residual), 2 = fused schedule with the residual
 	                          evaluated from u and f, 0 = API-granular sequence as GMG/Cycle.h */
 	int32_t use_graph;     /* 1 (default) = replay the cycle as a CUDA graph */
+	int32_t max_levels;    /* GMG/CycleOpts.h:55: the cycle uses at most this many levels, counted from the finest; 0 = all */
+	int32_t interpolator;  /* 0 (default) = piecewise constant, GMG::DrctIntp (the one CycleFactory builds, GMG/CycleFactory3d.cpp:60);
+	                          1 = piecewise (bi/tri)linear (GMG/TriLinIntp.cpp, unused upstream); cycles with 1 run the
+	                          API-granular schedule */
+	int32_t reserved_;     /* keeps the struct free of implicit padding; must be 0 */
+	double  patches_per_proc; /* GMG/CycleOpts.h:59: coarsening stops before a level with fewer patches per rank than this
+	                             (GMG/CycleFactory3d.cpp:101-104); 0 = never */
 } TgpuCycleOpts;
 
 const char *tgpu_last_error(void);
@@ -109,7 +116,13 @@ int tgpu_mesh_level_ids(const tgpu_mesh *mesh, int level, const int32_t **ids, c
 int tgpu_hierarchy_create(tgpu_ctx *ctx, int D, int n, int nlevels, const TgpuLevelDesc *levels, tgpu_hier **h);
 int tgpu_hierarchy_destroy(tgpu_hier *h);
 int tgpu_hierarchy_info(const tgpu_hier *h, int *D, int *n, int *nlevels);
+/* frees what earlier calls allocated lazily (Krylov work vectors, host-buffer slots, cached cycle graphs, pooled vector
+ * storage); tables, face buffers and per-level cycle vectors stay */
+int tgpu_hierarchy_trim(tgpu_hier *h);
 int tgpu_level_npatch(const tgpu_hier *h, int level, int64_t *npatch, int64_t *ncells);
+/* the patch solver's shift, FftwPatchSolver(domain, lambda) (PatchSolvers/FftwPatchSolver.h:66,170): block-Jacobi patch
+ * problems (Laplacian + lambda) u = rhs; default 0.  Non-zero values take the general (dense-transform) patch solve. */
+int tgpu_hierarchy_set_lambda(tgpu_hier *h, double lambda);
 /* test hook: on != 0 routes every smoother launch through the size-generic kernel even where a
  * specialised one exists (D = 3, n = 16), so that the two can be compared */
 int tgpu_hierarchy_force_generic_kernels(tgpu_hier *h, int on);
@@ -147,6 +160,7 @@ int tgpu_smooth(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec *u);       
 int tgpu_smooth_jacobi(tgpu_hier *h, int level, const tgpu_vec *f, tgpu_vec *u, double omega); /* weighted point Jacobi */
 int tgpu_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *fine, tgpu_vec *coarse);
 int tgpu_prolong_add(tgpu_hier *h, int fine_level, const tgpu_vec *coarse, tgpu_vec *fine); /* fine += P coarse */
+int tgpu_prolong_add_linear(tgpu_hier *h, int fine_level, const tgpu_vec *coarse, tgpu_vec *fine); /* fine += P_linear coarse */
 int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *f, const tgpu_vec *u, tgpu_vec *coarse_f);
 
 /* ---- cycle / Krylov ---- */

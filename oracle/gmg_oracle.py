@@ -496,9 +496,10 @@ def patch_solve(L, rhs, lam=0.0):
     return out
 
 
-def smooth(L, f, u):
+def smooth(L, f, u, lam=0.0):
     """SchurHelper<D>::solveWithSolution (src/Thunderegg/SchurHelper.h:319-331): gamma from the
-    current u, StarPatchOp::addInterfaceToRHS (StarPatchOp.h:185-203), exact patch solves."""
+    current u, StarPatchOp::addInterfaceToRHS (StarPatchOp.h:185-203), exact patch solves
+    (lam: the patch solver's shift, DftPatchSolver.h:78,168)."""
     D = L.D
     gamma = interface_values(L, u)
     rhs = f.copy()
@@ -507,7 +508,28 @@ def smooth(L, f, u):
         h2 = (L.spacings[:, s // 2] ** 2).reshape((-1,) + (1,) * (D - 1))
         fs = face(rhs, D, s)
         fs[has] -= (2.0 / h2 * gamma[:, s])[has]
-    return patch_solve(L, rhs)
+    return patch_solve(L, rhs, lam)
+
+
+def jacobi(L, f, u, omega):
+    """Weighted point-Jacobi sweep u <- u + omega D^-1 (f - A u) on the ghost-eliminated composite operator (the
+    "weighted-Jacobi option" of BASELINE.json's north star; the reference has no such smoother, its operator is
+    StarPatchOp.h:28-184).  D = diagonal of A: -(2 D)/h^2 per cell plus, for every patch side the cell touches, the
+    coefficient of the cell itself in the ghost value 2 gamma - u (StarPatchOp.h:46-64 with the interface weights of
+    SURVEY App. A.2): domain side -1 (Dirichlet) / +1 (Neumann); same-level neighbour 0; coarse neighbour 2 * 11/12 - 1 =
+    5/6 (3D), 2 * 5/6 - 1 = 2/3 (2D); fine neighbours 2 * 1/3 - 1 = -1/3."""
+    D, n = L.D, L.n
+    diag = np.full(L.shape, -2.0 * D)
+    for s in range(2 * D):
+        ty = L.nbr_type[:, s]
+        neu = _is_neumann(L, s)
+        add = np.where(ty == NBR_NONE, np.where(neu, 1.0, -1.0), 0.0)
+        add = np.where(ty == NBR_COARSE, 5.0 / 6.0 if D == 3 else 2.0 / 3.0, add)
+        add = np.where(ty == NBR_FINE, -1.0 / 3.0, add)
+        face(diag, D, s)[...] += add.reshape((-1,) + (1,) * (D - 1))
+    h2 = (L.spacings[:, 0] ** 2).reshape((-1,) + (1,) * D)
+    r = -1 * apply_op(L, u) + f
+    return u + omega * r / (diag / h2)
 
 
 def _child_view(a, D, n, orth):
@@ -587,6 +609,90 @@ def vcycle(levels, f, pre=1, post=1, coarse_sweeps=1, lvl=0, u=None):
     for _ in range(post):
         u = smooth(L, f, u)
     return u
+
+
+def active_levels(levels, max_levels=0, patches_per_proc=0.0, nranks=1):
+    """The level list GMG::CycleFactory3d::getCycle builds (GMG/CycleFactory3d.cpp:99-104): at most max_levels levels
+    (0 = all), stopping before a level with fewer than patches_per_proc patches per rank."""
+    out = [levels[0]]
+    for L in levels[1:]:
+        if max_levels > 0 and len(out) >= max_levels:
+            break
+        if L.P / nranks < patches_per_proc:
+            break
+        out.append(L)
+    return out
+
+
+def cycle(levels, f, cycle_type="V", pre=1, post=1, mid=1, coarse_sweeps=1, max_levels=0, patches_per_proc=0.0,
+          lam=0.0, interp=None):
+    """GMG::Cycle<D>::apply (GMG/Cycle.h:116-126) with VCycle::visit (GMG/VCycle.h:44-62) or WCycle::visit
+    (GMG/WCycle.h:45-68): prepCoarser = residual + restriction into fresh zero vectors (Cycle.h:56-68), prepFiner =
+    interpolation of the coarse correction at the END of the coarser visit (Cycle.h:74-80, WCycle.h:66)."""
+    lv = active_levels(levels, max_levels, patches_per_proc)
+    interp = interp or interpolate
+
+    def visit(l, fl, u):
+        L = lv[l]
+        if l == len(lv) - 1:
+            for _ in range(coarse_sweeps):
+                u = smooth(L, fl, u, lam)
+            return u
+
+        def coarse_correction(u):
+            r = -1 * apply_op(L, u) + fl
+            fc = restrict(L, lv[l + 1], r)
+            uc = visit(l + 1, fc, np.zeros(lv[l + 1].shape))
+            return interp(L, lv[l + 1], uc, u)
+
+        for _ in range(pre):
+            u = smooth(L, fl, u, lam)
+        u = coarse_correction(u)
+        if cycle_type == "W":
+            for _ in range(mid):
+                u = smooth(L, fl, u, lam)
+            u = coarse_correction(u)
+        for _ in range(post):
+            u = smooth(L, fl, u, lam)
+        return u
+
+    return visit(0, f, np.zeros(lv[0].shape))
+
+
+def interpolate_trilinear(fine, coarse, uc, uf):
+    """Piecewise (bi/tri)linear prolongation uf += P uc: the interpolator the dead GMG/TriLinIntp.cpp:110-181 restates
+    with coefficient tables (interior 27/9/9/3/9/3/3/1 over 64; on the parent patch's own boundary the one-sided
+    45/15/15/5/-9/-3/-3/-1 over 64, TriLinIntp.cpp:185-190), i.e. the tensor product of the 1-D rule
+        fine cell i -> coarse cell c = (i + offset)/2, partner c -/+ 1 towards the fine cell:  3/4 u_c + 1/4 u_partner,
+        partner outside the parent patch: linear extrapolation 5/4 u_c - 1/4 u_(c +/- 1 on the other side).
+    Patches present on both levels are copied (TriLinIntp.cpp:634-642).  Reproduces linear fields exactly
+    (test/GMG.cpp:465-600)."""
+    D, n = fine.D, fine.n
+    out = uf.copy()
+    copy = fine.orth_on_parent < 0
+    out[copy] += uc[fine.parent_idx[copy]]
+    i = np.arange(n)
+    for p in np.nonzero(~copy)[0]:
+        src = uc[fine.parent_idx[p]]
+        orth = int(fine.orth_on_parent[p])
+        val = src
+        for ax in range(D):  # ax 0 = x = last numpy axis
+            off = ((orth >> ax) & 1) * (n // 2)
+            c = off + i // 2
+            partner = np.where(i % 2 == 1, c + 1, c - 1)
+            inside = (partner >= 0) & (partner < n)
+            other = np.where(i % 2 == 1, c - 1, c + 1)
+            wc = np.where(inside, 0.75, 1.25)
+            wp = np.where(inside, 0.25, -0.25)
+            q = np.where(inside, partner, other)
+            npax = val.ndim - 1 - ax
+            a = np.take(val, c, axis=npax)
+            b = np.take(val, q, axis=npax)
+            shp = [1] * val.ndim
+            shp[npax] = n
+            val = a * wc.reshape(shp) + b * wp.reshape(shp)
+        out[p] += val
+    return out
 
 
 def vcycle_history(levels, f, ncyc):

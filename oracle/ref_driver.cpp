@@ -10,8 +10,10 @@
  * the RHS follows apps/3d/steady.cpp:253-265 / apps/2d/steady.cpp:314-316 through
  * Init::initDirichlet{,2d}.
  *
- * usage: ref_gmg D mesh.bin divide n dft|fftw[-neumann] cmd [cmd...]
+ * usage: ref_gmg D mesh.bin divide n dft|fftw[-neumann][@opt,opt...] cmd [cmd...]
  *   (suffix -neumann: ThundereggDomGen(tree, ns, neumann = true), apps/3d/steady.cpp:301)
+ *   (@ options fill GMG::CycleOpts, GMG/CycleOpts.h:51-80, and the patch solver's shift: W | V | pre=K | post=K | mid=K |
+ *    coarse=K | max_levels=K | ppp=X (patches_per_proc) | lambda=X (FftwPatchSolver / DftPatchSolver(domain, lambda)))
  *   cmd rhsn:trig|gauss:f.bin:exact.bin  the reference's Init::initNeumann / initNeumann2d on the app's manufactured problems
  *   meta:OUT                         hierarchy metadata (format: see dump_meta)
  *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
@@ -22,7 +24,7 @@
  *   vcycle:F_IN:OUT                  OUT = Cycle::apply(F)
  *   vhist:F_IN:NCYC:U_OUT:HIST_OUT   u += V(f - A u), NCYC times from u = 0; HIST = ||f-Au||_2/||f||_2
  *   bicgstab:F_IN:TOL:MAXIT:U_OUT:INFO_OUT   BiCGStab<D>::solve with Mr = V-cycle; INFO = its, relres
- *   time:REPS                        times Cycle::apply on the trig RHS, prints one JSON line
+ *   time:REPS[:WARMUP]               times Cycle::apply on the trig RHS, prints one JSON line
  */
 #include <algorithm>
 #include <array>
@@ -253,6 +255,25 @@ template <size_t D> static int run(int argc, char **argv)
 	int    divide = atoi(argv[3]);
 	int    n      = atoi(argv[4]);
 	string solver = argv[5];
+	GMG::CycleOpts opts; /* defaults: V, 1 pre, 1 post, 1 coarse sweep, all levels */
+	double         lambda = 0;
+	{
+		size_t at = solver.find('@');
+		if (at != string::npos) {
+			for (const string &o : split(solver.substr(at + 1), ',')) {
+				if (o == "W" || o == "V") opts.cycle_type = o;
+				else if (o.rfind("pre=", 0) == 0) opts.pre_sweeps = stoi(o.substr(4));
+				else if (o.rfind("post=", 0) == 0) opts.post_sweeps = stoi(o.substr(5));
+				else if (o.rfind("mid=", 0) == 0) opts.mid_sweeps = stoi(o.substr(4));
+				else if (o.rfind("coarse=", 0) == 0) opts.coarse_sweeps = stoi(o.substr(7));
+				else if (o.rfind("max_levels=", 0) == 0) opts.max_levels = stoi(o.substr(11));
+				else if (o.rfind("ppp=", 0) == 0) opts.patches_per_proc = stod(o.substr(4));
+				else if (o.rfind("lambda=", 0) == 0) lambda = stod(o.substr(7));
+				else { cerr << "unknown option " << o << "\n"; return 2; }
+			}
+			solver = solver.substr(0, at);
+		}
+	}
 	bool   neumann = false;
 	if (solver.size() > 8 && solver.substr(solver.size() - 8) == "-neumann") {
 		neumann = true;
@@ -271,11 +292,10 @@ template <size_t D> static int run(int argc, char **argv)
 	shared_ptr<PatchOperator<D>> p_op(new StarPatchOp<D>());
 	shared_ptr<IfaceInterp<D>>   p_interp(new typename Traits<D>::Interp());
 	shared_ptr<PatchSolver<D>>   p_solver;
-	if (solver == "fftw") p_solver.reset(new FftwPatchSolver<D>(*finest));
-	else                  p_solver.reset(new DftPatchSolver<D>(*finest));
+	if (solver == "fftw") p_solver.reset(new FftwPatchSolver<D>(*finest, lambda));
+	else                  p_solver.reset(new DftPatchSolver<D>(*finest, lambda));
 	shared_ptr<SchurHelper<D>> sch(new SchurHelper<D>(finest, p_solver, p_op, p_interp));
 	c.A.reset(new DomainWrapOp<D>(sch));
-	GMG::CycleOpts opts; /* defaults: V, 1 pre, 1 post, 1 coarse sweep, all levels */
 	c.cycle = Traits<D>::Factory::getCycle(opts, c.dcg, p_solver, p_op, p_interp);
 	for (auto &d : c.dcg->domain_list) c.domains.push_back(d);
 	{
@@ -283,7 +303,8 @@ template <size_t D> static int run(int argc, char **argv)
 		while (l) { c.levels.push_back(l); l = l->coarser; }
 	}
 	double setup_s = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
-	if (c.levels.size() != c.domains.size()) { cerr << "level/domain count mismatch\n"; return 3; }
+	if (c.levels.size() > c.domains.size()) { cerr << "level/domain count mismatch\n"; return 3; }
+	if (c.levels.size() != c.domains.size() && opts.max_levels == 0 && opts.patches_per_proc == 0) { cerr << "level/domain count mismatch\n"; return 3; }
 
 	auto newvec = [&](int l) { return c.domains[l]->getNewDomainVec(); };
 
@@ -367,10 +388,10 @@ template <size_t D> static int run(int argc, char **argv)
 			ofstream out(p[5], ios::binary);
 			out.write((const char *) info, sizeof(info));
 		} else if (cmd == "time") {
-			int  reps = stoi(p[1]);
+			int  reps = stoi(p[1]), warm = p.size() > 2 ? stoi(p[2]) : 1;
 			auto f = newvec(0), e = newvec(0), u = newvec(0);
 			Traits<D>::rhs(*c.domains[0], f->vec, e->vec);
-			c.cycle->apply(f, u); /* warm-up */
+			for (int k = 0; k < warm; k++) c.cycle->apply(f, u); /* warm-up */
 			vector<double> secs;
 			for (int k = 0; k < reps; k++) {
 				auto t1 = chrono::steady_clock::now();

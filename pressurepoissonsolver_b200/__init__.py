@@ -48,7 +48,8 @@ class ProfileEntry(C.Structure):
 class CycleOpts(C.Structure):
     _fields_ = [("pre_sweeps", C.c_int32), ("post_sweeps", C.c_int32), ("mid_sweeps", C.c_int32),
                 ("coarse_sweeps", C.c_int32), ("cycle_type", C.c_int32), ("fused", C.c_int32),
-                ("use_graph", C.c_int32)]
+                ("use_graph", C.c_int32), ("max_levels", C.c_int32), ("interpolator", C.c_int32),
+                ("reserved_", C.c_int32), ("patches_per_proc", C.c_double)]
 
     @classmethod
     def default(cls, **kw):
@@ -77,6 +78,7 @@ ABI_SYMBOLS = [
     "tgpu_init_trig_rhs", "tgpu_init_neumann_rhs", "tgpu_vec_integrate", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
     "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann", "tgpu_vcycle_host_async", "tgpu_vcycle_host_wait",
+    "tgpu_hierarchy_trim", "tgpu_hierarchy_set_lambda", "tgpu_prolong_add_linear",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -95,7 +97,7 @@ for _name, _args in {
     "tgpu_mesh_level_ids": [_vp, C.c_int, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)),
                             C.POINTER(C.POINTER(C.c_int32))],
     "tgpu_hierarchy_create": [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(LevelDesc), C.POINTER(_vp)],
-    "tgpu_hierarchy_destroy": [_vp],
+    "tgpu_hierarchy_destroy": [_vp], "tgpu_hierarchy_trim": [_vp],
     "tgpu_hierarchy_info": [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "tgpu_level_npatch": [_vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "tgpu_vec_create": [_vp, C.c_int, C.POINTER(_vp)], "tgpu_vec_destroy": [_vp],
@@ -114,7 +116,7 @@ for _name, _args in {
     "tgpu_apply": [_vp, C.c_int, _vp, _vp], "tgpu_residual": [_vp, C.c_int, _vp, _vp, _vp],
     "tgpu_smooth": [_vp, C.c_int, _vp, _vp], "tgpu_smooth_jacobi": [_vp, C.c_int, _vp, _vp, C.c_double],
     "tgpu_restrict": [_vp, C.c_int, _vp, _vp], "tgpu_prolong_add": [_vp, C.c_int, _vp, _vp],
-    "tgpu_residual_restrict": [_vp, C.c_int, _vp, _vp, _vp],
+    "tgpu_residual_restrict": [_vp, C.c_int, _vp, _vp, _vp], "tgpu_prolong_add_linear": [_vp, C.c_int, _vp, _vp],
     "tgpu_cycle_opts_default": [C.POINTER(CycleOpts)], "tgpu_vcycle": [_vp, C.POINTER(CycleOpts), _vp, _vp],
     "tgpu_bicgstab": [_vp, C.POINTER(CycleOpts), _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_int),
                       C.POINTER(C.c_double)],
@@ -133,7 +135,7 @@ for _name, _args in {
     "tgpu_part_level_interior": [_vp, C.c_int, C.POINTER(C.c_int32)],
     "tgpu_comm_unique_id": [_vp], "tgpu_comm_init": [_vp, _vp, C.c_int, C.c_int],
     "tgpu_hierarchy_create_distributed": [_vp, _vp, C.POINTER(_vp)],
-    "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int],
+    "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int], "tgpu_hierarchy_set_lambda": [_vp, C.c_double],
     "tgpu_mesh_set_neumann": [_vp, C.c_int],
     "tgpu_vcycle_host_async": [_vp, C.POINTER(CycleOpts), _vp, _vp], "tgpu_vcycle_host_wait": [_vp],
 }.items():
@@ -407,6 +409,14 @@ class Hierarchy:
         check(lib.tgpu_hierarchy_create_distributed(ctx._p, part._p, C.byref(self._p)))
         return self
 
+    def trim(self):
+        """free lazily allocated work space (Krylov vectors, host-buffer slots, cached graphs, pooled vector storage)"""
+        check(lib.tgpu_hierarchy_trim(self._p))
+
+    def set_lambda(self, lam):
+        """the patch solver's shift (FftwPatchSolver(domain, lambda), PatchSolvers/FftwPatchSolver.h:66,170)"""
+        check(lib.tgpu_hierarchy_set_lambda(self._p, lam))
+
     def force_generic_kernels(self, on=True):
         check(lib.tgpu_hierarchy_force_generic_kernels(self._p, 1 if on else 0))
 
@@ -432,6 +442,9 @@ class Hierarchy:
     def smooth_jacobi(self, level, f, u, omega): check(lib.tgpu_smooth_jacobi(self._p, level, f._p, u._p, omega))
     def restrict(self, fine_level, fine, coarse): check(lib.tgpu_restrict(self._p, fine_level, fine._p, coarse._p))
     def prolong_add(self, fine_level, coarse, fine): check(lib.tgpu_prolong_add(self._p, fine_level, coarse._p, fine._p))
+
+    def prolong_add_linear(self, fine_level, coarse, fine):
+        check(lib.tgpu_prolong_add_linear(self._p, fine_level, coarse._p, fine._p))
 
     def residual_restrict(self, fine_level, f, u, coarse_f):
         check(lib.tgpu_residual_restrict(self._p, fine_level, f._p, u._p, coarse_f._p))

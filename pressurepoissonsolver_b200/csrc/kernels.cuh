@@ -538,8 +538,11 @@ template <int D, int N, bool ZERO_GUESS, bool EMIT, bool PROLONG>
 __global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
 smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
               const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-              const double *__restrict__ uc, const double *__restrict__ mats, const double *__restrict__ lam)
+              const double *__restrict__ uc, const double *__restrict__ mats, const double *__restrict__ lam, double lam_shift)
 {
+	// lam_shift: the patch solver's "lambda" (FftwPatchSolver.h:66,170, DftPatchSolver.h:78,168): the patch problems are
+	// (Laplacian + lambda) u = rhs; != 0 sends every patch through the general transform path, whose eigenvalue sums are
+	// formed on the fly
 	// works on patches [p0, P) (multi-GPU: interior and boundary patches are separate launches)
 	// Persistent CTAs: each loops over groups of PPB patches (group g = blockIdx.x + k gridDim.x).
 	// The right-hand side of the NEXT group streams into the second shared-memory buffer with
@@ -592,6 +595,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 		double *S = Sall + pp * G::SP;
 		double  cfac = 0.0, h2 = 0.0;
 		int     neu  = 0; // Neumann domain sides of this patch: != 0 takes the general transform path
+		bool    general = false;
 		int8_t  ntype[6] = {-1, -1, -1, -1, -1, -1};
 		double  gam[6]   = {0, 0, 0, 0, 0, 0}; // (2/h^2) gamma of entry m on each side
 		if (valid) {
@@ -599,6 +603,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			cfac                = 2.0 * pm.inv_h2;
 			h2                  = pm.h2;
 			neu                 = pm.neumann;
+			general             = neu != 0 || lam_shift != 0.0;
 			if (!ZERO_GUESS) {
 				// entry m of every side is both produced and consumed by thread m: no staging needed
 				int    ty[G::S];
@@ -640,7 +645,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				if (ntype[G::S - 2] != NBR_NONE) v[0] -= gam[G::S - 2];
 				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= gam[G::S - 1];
 			}
-			if (neu) {
+			if (general) {
 				dense_to_smem<N>(mats + axis_kind(neu, D - 1).fwd * N * N, v, S + base, step);
 			} else {
 				dst2_forward<N>(v, mg);
@@ -653,7 +658,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-			if (neu) {
+			if (general) {
 				dense_to_smem<N>(mats + axis_kind(neu, 1).fwd * N * N, v, S + base, G::ROW);
 			} else {
 				dst2_forward<N>(v, mg);
@@ -666,7 +671,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 		{
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
-			if (neu) {
+			if (general) {
 				const AxisKind kx = axis_kind(neu, 0), ky = axis_kind(neu, 1), kz = axis_kind(neu, 2);
 				dense_to_smem<N>(mats + kx.fwd * N * N, v, S + m * G::ROW, 1);
 				// eigenvalue sum of row m = (k_y, k_z) (2D: k_y) on the fly; scale (2/N)^D as in DftPatchSolver.h:214
@@ -677,7 +682,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				const bool singular = neu == (1 << (2 * D)) - 1;
 #pragma unroll
 				for (int k = 0; k < N; k++) {
-					const double sum = __ldg(lam + kx.lam * N + k) + rest;
+					const double sum = __ldg(lam + kx.lam * N + k) + rest + lam_shift * h2;
 					v[k]             = (singular && k == 0 && m == 0) ? 0.0 : S[m * G::ROW + k] * scale / sum;
 				}
 				dense_to_smem<N>(mats + kx.inv * N * N, v, S + m * G::ROW, 1);
@@ -703,7 +708,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			const int base = (m / N) * N * G::ROW + (m % N);
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
-			if (neu) {
+			if (general) {
 				dense_to_smem<N>(mats + axis_kind(neu, 1).inv * N * N, v, S + base, G::ROW);
 			} else {
 				dst3_inverse<N>(v, mg);
@@ -718,13 +723,13 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			const int step = (D == 2) ? G::ROW : N * G::ROW;
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
-			if (neu) { // general path: transform through the pencil's own slots, then pick the result up again
+			if (general) { // general path: transform through the pencil's own slots, then pick the result up again
 				dense_to_smem<N>(mats + axis_kind(neu, D - 1).inv * N * N, v, S + base, step);
 #pragma unroll
 				for (int k = 0; k < N; k++) v[k] = S[base + k * step];
 			}
 			__syncthreads(); // all reads of this buffer are done: the next iteration may refill it
-			if (!neu) dst3_inverse<N>(v, mg);
+			if (!general) dst3_inverse<N>(v, mg);
 			if (valid) {
 				double *up = u + (size_t) p * G::NC + m;
 #pragma unroll
@@ -1158,6 +1163,48 @@ __global__ void prolong_add_kernel(const PatchMeta *__restrict__ meta, int P, co
 		uf[i] += __ldg(uc + (size_t) pm.parent_idx * G::NC + parent_cell<D, N>(pm.orth_on_parent, c));
 	}
 }
+// uf += P uc with the piecewise (bi/tri)linear interpolator (the intent of the reference's GMG/TriLinIntp.cpp:110-190, dead
+// code upstream; known answer test/GMG.cpp:465-600: linear fields are reproduced exactly): tensor product of the 1-D rule
+//   fine cell i -> coarse cell c = (i + offset) / 2 and its neighbour towards the fine cell: 3/4 u_c + 1/4 u_nbr
+//   (3D interior weights 27/9/9/3/9/3/3/1 over 64); where that neighbour lies outside the parent patch the value is
+//   extrapolated from inside, 5/4 u_c - 1/4 u_(neighbour on the other side) (face weights 45/15/15/5/-9/-3/-3/-1 over 64).
+// Patches present on both levels are copied.  Evaluated axis by axis (x, y, z) like oracle/gmg_oracle.py.
+template <int D, int N>
+__global__ void prolong_linear_add_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ uc,
+                                          double *__restrict__ uf)
+{
+	pdl_launch_dependents();
+	pdl_wait();
+	using G            = Geo<D, N>;
+	const size_t total = (size_t) P * G::NC;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int        ci = (int) (i % G::NC);
+		const size_t     p  = i / G::NC;
+		const PatchMeta &pm = meta[p];
+		const double *   src = uc + (size_t) pm.parent_idx * G::NC;
+		const int        orth = pm.orth_on_parent;
+		if (orth < 0) {
+			uf[i] += __ldg(src + ci);
+			continue;
+		}
+		const int c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
+		int       cc[3] = {0, 0, 0}, cq[3] = {0, 0, 0};
+		double    wc[3] = {1, 1, 1}, wq[3] = {0, 0, 0};
+		for (int a = 0; a < D; a++) {
+			const int  off = ((orth >> a) & 1) * (N / 2), k = off + c[a] / 2, odd = c[a] & 1;
+			const int  nb = odd ? k + 1 : k - 1;
+			const bool in = nb >= 0 && nb < N;
+			cc[a] = k;
+			cq[a] = in ? nb : (odd ? k - 1 : k + 1);
+			wc[a] = in ? 0.75 : 1.25;
+			wq[a] = in ? 0.25 : -0.25;
+		}
+		auto at = [&](int x, int y, int z) { return __ldg(src + (z * N + y) * N + x); };
+		auto line = [&](int y, int z) { return at(cc[0], y, z) * wc[0] + at(cq[0], y, z) * wq[0]; };
+		auto plane = [&](int z) { return line(cc[1], z) * wc[1] + line(cq[1], z) * wq[1]; };
+		uf[i] += (D == 2) ? plane(0) : plane(cc[2]) * wc[2] + plane(cq[2]) * wq[2];
+	}
+}
 // thread per destination (coarse-resolution) cell of every fine patch; bit-exact w.r.t. AvgRstr.h:88-107
 template <int D, int N>
 __global__ void restrict_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ fine,
@@ -1191,9 +1238,11 @@ __global__ void restrict_kernel(const PatchMeta *__restrict__ meta, int P, const
 	}
 }
 
-// weighted point-Jacobi sweep u <- u + omega D^-1 (f - A u); the residual comes from apply_kernel MODE 1
-// and the diagonal of the ghost-eliminated operator is -(2D + #closed sides)/h^2 per cell; provided as
-// the "weighted-Jacobi option" of the north star (no reference counterpart).
+// weighted point-Jacobi sweep u <- u + omega D^-1 (f - A u); the residual comes from apply_kernel MODE 1.  D is the
+// diagonal of the ghost-eliminated composite operator: -(2 D)/h^2 per cell plus, per patch side the cell touches, the
+// cell's own coefficient in the ghost value 2 gamma - u (StarPatchOp.h:46-64, interface weights SURVEY App. A.2):
+// domain side -1 (Dirichlet) / +1 (Neumann), same-level neighbour 0, coarse neighbour 5/6 (3D) or 2/3 (2D), fine
+// neighbours -1/3.  The "weighted-Jacobi option" of the north star (no reference counterpart; oracle: gmg_oracle.jacobi).
 template <int D, int N>
 __global__ void jacobi_update_kernel(const PatchMeta *__restrict__ meta, int P, const double *__restrict__ r,
                                      double *__restrict__ u, double omega)
@@ -1208,10 +1257,16 @@ __global__ void jacobi_update_kernel(const PatchMeta *__restrict__ meta, int P, 
 		const PatchMeta &pm = meta[p];
 		const int        c[3] = {ci % N, (ci / N) % N, (D == 2) ? 0 : ci / (N * N)};
 		double           diag = -2.0 * D;
+		auto side = [&](int s) {
+			const int ty = pm.nbr_type[s];
+			if (ty == NBR_NONE) return ((pm.neumann >> s) & 1) ? 1.0 : -1.0;
+			if (ty == NBR_COARSE) return (D == 3) ? 5.0 / 6.0 : 2.0 / 3.0;
+			if (ty == NBR_FINE) return -1.0 / 3.0;
+			return 0.0;
+		};
 		for (int a = 0; a < D; a++) {
-			if (c[a] == 0) diag += (pm.nbr_type[2 * a] == NBR_NONE) ? (((pm.neumann >> (2 * a)) & 1) ? 1.0 : -1.0) : 0.0;
-			if (c[a] == N - 1)
-				diag += (pm.nbr_type[2 * a + 1] == NBR_NONE) ? (((pm.neumann >> (2 * a + 1)) & 1) ? 1.0 : -1.0) : 0.0;
+			if (c[a] == 0) diag += side(2 * a);
+			if (c[a] == N - 1) diag += side(2 * a + 1);
 		}
 		u[i] += omega * r[i] / (diag * pm.inv_h2);
 	}
@@ -1303,37 +1358,46 @@ __global__ void p2p_signal_kernel(uint64_t *const *__restrict__ remote_flags, in
 	pdl_wait();
 	const uint64_t v = *counter + 1;
 	__syncthreads();
-	if ((int) threadIdx.x < npeers) {
+	for (int k = threadIdx.x; k < npeers; k += blockDim.x) {
 		__threadfence_system();
-		st_release_sys(remote_flags[threadIdx.x], v);
+		st_release_sys(remote_flags[k], v);
 	}
 	if (threadIdx.x == 0) *counter = v;
 }
 // waits until every peer's flag has reached generation counter + 1 - lag, then counter += 1.
-// A peer that never arrives (crashed rank) trips the timeout instead of hanging the GPU: *err is set.
+// A peer that never arrives (crashed rank) trips the timeout instead of hanging the GPU: the generation counter is NOT
+// advanced (the protocol stays where it broke), *abort (device) makes every later wait of the hierarchy return at
+// once, and *host_err (mapped host memory, read by the host after its next synchronisation, see check_comm in tgpu.cu)
+// receives the rank that was waited for + 1.
 __global__ void p2p_wait_kernel(const uint64_t *__restrict__ local_flags, const int32_t *__restrict__ peer_rank, int npeers,
-                                uint64_t *__restrict__ counter, int lag, int *__restrict__ err)
+                                uint64_t *__restrict__ counter, int lag, int *__restrict__ abort, int *__restrict__ host_err)
 {
 	pdl_launch_dependents();
 	pdl_wait();
+	__shared__ int failed;
+	if (threadIdx.x == 0) failed = *abort;
 	const uint64_t expected = *counter + 1 - lag;
 	__syncthreads();
-	if ((int) threadIdx.x < npeers) {
-		const uint64_t *f = local_flags + peer_rank[threadIdx.x];
+	if (failed) return;
+	for (int k = threadIdx.x; k < npeers; k += blockDim.x) {
+		const uint64_t *f = local_flags + peer_rank[k];
 		unsigned long long t0;
 		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 		while (ld_acquire_sys(f) < expected) {
 			unsigned long long t1;
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
 			if (t1 - t0 > 20000000000ull) { // 20 s
-				atomicExch(err, 1);
+				failed = 1;
+				atomicExch(abort, 1);
+				*(volatile int *) host_err = peer_rank[k] + 1;
+				__threadfence_system();
 				break;
 			}
 			__nanosleep(200);
 		}
 	}
 	__syncthreads();
-	if (threadIdx.x == 0) *counter += 1;
+	if (threadIdx.x == 0 && !failed) *counter += 1;
 }
 
 // ---------------------------------------------------------------------------------------------

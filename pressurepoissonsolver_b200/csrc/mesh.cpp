@@ -61,6 +61,17 @@ Mesh Mesh::load(const std::string &path, int D)
 	int32_t hdr[2];
 	in.read((char *) hdr, 8);
 	if (!in || hdr[0] <= 0) throw std::runtime_error("mesh: bad header in " + path);
+	{
+		// the record count must agree with the file size for this D (a 3D file opened with D = 2, or a truncated
+		// file, is rejected before any record is interpreted)
+		const std::streamoff rec = 12 + 16 * D + 8 * D + 4 * (1 << D);
+		in.seekg(0, std::ios::end);
+		const std::streamoff size = in.tellg();
+		in.seekg(8, std::ios::beg);
+		if (size != 8 + rec * (std::streamoff) hdr[0])
+			throw std::runtime_error("mesh: " + path + " does not hold " + std::to_string(hdr[0]) + " records of a " + std::to_string(D)
+			                         + "D tree (wrong D or truncated file)");
+	}
 	for (int i = 0; i < hdr[0]; i++) {
 		MeshNode n;
 		int32_t  ilp[3];
@@ -72,10 +83,56 @@ Mesh Mesh::load(const std::string &path, int D)
 		in.read((char *) n.child, 4 * (1 << D));
 		if (!in) throw std::runtime_error("mesh: truncated file " + path);
 		if (i == 0) m.root = n.id;
+		if (n.level < 1 || n.level > 30) throw std::runtime_error("mesh: node level out of range in " + path);
+		if (n.id >= 0 && (size_t) n.id < m.nodes.size() && m.nodes[n.id].id >= 0) throw std::runtime_error("mesh: duplicate node id in " + path);
 		m.put(n);
 		m.num_levels = std::max(m.num_levels, n.level);
 	}
+	m.validate(path);
 	return m;
+}
+
+// Every id stored in a record is used as a raw index later (refineNode, extractLevels): check them all once, and the
+// parent/child/neighbour back-links with them, so that a corrupt file is an I/O error instead of an out-of-bounds access
+// (the reference keeps nodes in a std::map and cannot index out of range).
+void Mesh::validate(const std::string &path) const
+{
+	auto bad = [&](const char *what, int id) { throw std::runtime_error("mesh: " + std::string(what) + " (node " + std::to_string(id) + ") in " + path); };
+	auto ok  = [&](int id) { return id == -1 || (id >= 0 && (size_t) id < nodes.size() && nodes[id].id == id); };
+	const int no = 1 << D;
+	for (const MeshNode &n : nodes) {
+		if (n.id < 0) continue;
+		if (!ok(n.parent)) bad("dangling parent id", n.id);
+		for (int a = 0; a < D; a++)
+			if (!(n.lengths[a] > 0.0)) bad("non-positive patch length", n.id);
+		for (int s = 0; s < 2 * D; s++) {
+			if (!ok(n.nbr[s])) bad("dangling neighbour id", n.id);
+			if (n.nbr[s] != -1) {
+				const MeshNode &b = nodes[n.nbr[s]];
+				if (b.nbr[s ^ 1] != n.id) bad("neighbour link is not mutual", n.id);
+				if (b.level != n.level) bad("neighbour on a different tree level", n.id);
+			}
+		}
+		int nchild = 0;
+		for (int o = 0; o < no; o++) {
+			if (!ok(n.child[o])) bad("dangling child id", n.id);
+			if (n.child[o] != -1) {
+				nchild++;
+				const MeshNode &c = nodes[n.child[o]];
+				if (c.parent != n.id || c.level != n.level + 1) bad("child does not point back to its parent", n.id);
+			}
+		}
+		if (nchild != 0 && nchild != no) bad("partially refined node", n.id);
+		if (n.parent != -1) {
+			const MeshNode &p     = nodes[n.parent];
+			bool            found = false;
+			for (int o = 0; o < no; o++) found = found || p.child[o] == n.id;
+			if (!found) bad("parent does not list the node as a child", n.id);
+		} else if (n.id != root) {
+			bad("second root node", n.id);
+		}
+	}
+	if (root < 0 || nodes[root].parent != -1) bad("first record is not the root", root);
 }
 
 Mesh Mesh::uniform(int D, int num_levels)
@@ -197,7 +254,8 @@ std::vector<HostLevel> Mesh::extractLevels(int n) const
 					const MeshNode &parent = nodes[nd.parent];
 					int             octs[4], quad = 0;
 					orthantsOnSide(D, s, octs);
-					while (parent.child[octs[quad]] != nd.id) quad++;
+					while (quad < Q && parent.child[octs[quad]] != nd.id) quad++;
+					if (quad == Q) throw std::runtime_error("mesh: node without a sibling link on an interior side (corrupt tree)");
 					r.type[s]   = TGPU_NBR_COARSE;
 					r.orth[s]   = (int8_t) quad;
 					r.ids[s][0] = parent.nbr[s];
@@ -270,7 +328,8 @@ std::vector<HostLevel> Mesh::extractLevels(int n) const
 				L.parent_ids[k] = nd.parent;
 				if (nd.parent != -1) {
 					int o = 0;
-					while (nodes[nd.parent].child[o] != nd.id) o++;
+					while (o < (1 << D) && nodes[nd.parent].child[o] != nd.id) o++;
+					if (o == (1 << D)) throw std::runtime_error("mesh: parent does not list the node as a child");
 					L.orth_on_parent[k] = (int8_t) o;
 				}
 			}

@@ -54,6 +54,7 @@ class Mesh
 	std::vector<HostLevel> extractLevels(int n) const;
 
 	private:
+	void      validate(const std::string &path) const;
 	void      refineNode(int id);
 	MeshNode &at(int id) { return nodes[id]; }
 	void      put(const MeshNode &n);

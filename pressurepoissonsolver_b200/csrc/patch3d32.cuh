@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(TGPU_THREADS)
 smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                    const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ uc,
                    const double *__restrict__ mats, const double *__restrict__ lam, double *__restrict__ scratch, int zero_guess,
-                   int emit, int prolong, int write_u)
+                   int emit, int prolong, int write_u, double lam_shift)
 {
 	constexpr int N = 32, M = N * N, NC = M * N;
 	const int     t = threadIdx.x;
@@ -501,7 +501,7 @@ smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 				const double   scale = h2 * (2.0 / N) * (2.0 / N) * (2.0 / N);
 				const bool     singular = neu == 63;
 				for (int i = t; i < NC; i += TGPU_THREADS) {
-					const double sum = __ldg(lam + kx.lam * N + i % N) + (__ldg(lam + ky.lam * N + (i / N) % N) + __ldg(lam + kz.lam * N + i / M));
+					const double sum = __ldg(lam + kx.lam * N + i % N) + (__ldg(lam + ky.lam * N + (i / N) % N) + __ldg(lam + kz.lam * N + i / M)) + lam_shift * h2;
 					W[i]             = (singular && i == 0) ? 0.0 : W[i] * scale / sum;
 				}
 				__syncthreads();

@@ -131,6 +131,9 @@ struct tgpu_ctx {
 	int          rank        = 0;
 	int          nranks      = 1;
 	cudaStream_t comm_stream = nullptr; // halo exchanges run here, concurrently with interior sweeps
+	// set by p2p_wait_kernel when a peer's flag never arrives (pinned, mapped host memory: the kernel writes it, the host
+	// reads it after every synchronisation point, see check_comm)
+	volatile int *p2p_err = nullptr;
 	// per-launch profiling
 	bool                          profiling = false;
 	const char *                  tag_name  = "kernel";
@@ -154,6 +157,15 @@ struct Tag {
 	}
 };
 static constexpr int MAX_PARTIAL = 2048;
+// Called after every host synchronisation point of a multi-GPU context: a halo exchange whose peer never signalled
+// (crashed or stalled rank) has consumed stale faces, so everything computed since is invalid.
+static int check_comm(tgpu_ctx *ctx)
+{
+	if (ctx->p2p_err && *ctx->p2p_err)
+		return fail(TGPU_ERR_COMM, "peer-to-peer halo exchange timed out waiting for rank " + std::to_string(*ctx->p2p_err - 1)
+		                           + " (results since the last successful synchronisation are invalid; the context must be torn down)");
+	return TGPU_OK;
+}
 
 struct tgpu_mesh {
 	Mesh                       mesh;
@@ -172,6 +184,7 @@ struct PeerDev {
 };
 struct LevelDev {
 	int        P      = 0; // owned patches (kernel loop bound, vector length)
+	int64_t    global_P = 0; // patches of the level over all ranks (Domain::getNumGlobalPatches)
 	int        slots  = 0; // owned + halo face slots
 	bool       distributed = false;
 	int        n_interior  = 0;
@@ -226,10 +239,12 @@ struct tgpu_hier {
 	cudaEvent_t           ev_in[2] = {nullptr, nullptr}, ev_cyc[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 	uint64_t              pipe_count = 0;
 	bool                  generic_kernels = false; // test hook: force the size-generic smoother
+	double                lambda = 0.0;            // the patch solver's shift (tgpu_hierarchy_set_lambda)
+	int                   last_level = 0;          // coarsest level the running cycle visits (CycleOpts max_levels / patches_per_proc)
 	// peer-to-peer arena: flag rows + the face buffers of the distributed levels, one IPC-exported allocation
 	void *                arena = nullptr;
 	std::vector<void *>   ipc_opened;
-	int *                 p2p_err = nullptr;
+	int *                 p2p_abort = nullptr; // device flag: a wait of this hierarchy has timed out (p2p_wait_kernel)
 };
 
 struct tgpu_vec {
@@ -474,6 +489,12 @@ extern "C" int tgpu_init(int device, tgpu_ctx **out)
 	CU(cudaMallocHost(&ctx->h_result, 8 * sizeof(double)));
 	CU(cudaEventCreate(&ctx->ev0));
 	CU(cudaEventCreate(&ctx->ev1));
+	{ // vector storage pool (tgpu_vec_create): keep freed blocks across synchronisations; tgpu_hierarchy_trim releases them
+		cudaMemPool_t pool = nullptr;
+		CU(cudaDeviceGetDefaultMemPool(&pool, device));
+		uint64_t keep = ~0ull;
+		CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
 	TRY(init_constant_tables());
 	*out = ctx.release();
 	return TGPU_OK;
@@ -486,6 +507,7 @@ extern "C" int tgpu_finalize(tgpu_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
 	if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+	if (ctx->p2p_err) cudaFreeHost((void *) ctx->p2p_err);
 	cudaFree(ctx->d_partial);
 	cudaFree(ctx->d_result);
 	cudaFreeHost(ctx->h_result);
@@ -508,7 +530,7 @@ extern "C" int tgpu_sync(tgpu_ctx *ctx)
 {
 	if (!ctx) return fail(TGPU_ERR_ARG, "null context");
 	CU(cudaStreamSynchronize(ctx->stream));
-	return TGPU_OK;
+	return check_comm(ctx);
 }
 extern "C" int tgpu_kernel_launches(tgpu_ctx *ctx, int64_t *count)
 {
@@ -530,7 +552,7 @@ extern "C" int tgpu_timer_stop(tgpu_ctx *ctx, double *ms)
 	float f = 0;
 	CU(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
 	*ms = f;
-	return TGPU_OK;
+	return check_comm(ctx);
 }
 
 extern "C" int tgpu_profile_begin(tgpu_ctx *ctx)
@@ -673,10 +695,15 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 		if (d.npatch < 1) return fail(TGPU_ERR_ARG, "level without patches");
 		LevelDev L;
 		L.P      = n_owned ? n_owned[l] : d.npatch;
+		L.global_P = L.P;
 		L.slots  = d.npatch;
 		L.ncells = (size_t) L.P * NC;
 		L.nface  = (size_t) d.npatch * S * M;
 		if (L.P < 0 || L.P > d.npatch) return fail(TGPU_ERR_ARG, "owned patch count out of range");
+		// the 16^3 smoother's gather descriptors (GDesc16, smooth3d16.cuh) hold 32-bit element offsets into the face
+		// buffer ((slot * 6 + side) * 256) and into the coarser level's vector (parent * 4096)
+		if (D == 3 && n == 16 && ((uint64_t) d.npatch * 6 * 256 > 0xffffffffull || (l > 0 && (uint64_t) d.npatch * 4096 > 0xffffffffull)))
+			return fail(TGPU_ERR_UNSUPPORTED, "tgpu_hierarchy_create: more than 2.7 M patches of 16^3 on one level of one GPU (1 M on a coarser level) exceed the 32-bit gather offsets");
 		std::vector<PatchMeta> meta(d.npatch);
 		const int              Pc = (l + 1 < nlevels) ? levels[l + 1].npatch : 0;
 		for (int p = 0; p < d.npatch; p++) {
@@ -910,6 +937,12 @@ extern "C" int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nr
 	memcpy(&id, id128, sizeof(id));
 	NC(g_nccl.CommInitRank(&ctx->comm, nranks, id, rank));
 	if (!ctx->comm_stream) CU(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+	if (!ctx->p2p_err) {
+		int *e = nullptr;
+		CU(cudaHostAlloc(&e, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+		*e           = 0;
+		ctx->p2p_err = e;
+	}
 	ctx->rank   = rank;
 	ctx->nranks = nranks;
 	return TGPU_OK;
@@ -923,6 +956,7 @@ extern "C" int tgpu_comm_init(tgpu_ctx *ctx, const void *id128, int rank, int nr
 // ------------------------------------------------------------------------------------------
 struct P2PPack {
 	cudaIpcMemHandle_t handle;
+	int32_t            ok;                 // this rank could allocate and export its arena
 	uint64_t           base_off;           // arena - allocation base
 	uint64_t           flags_off;          // flag rows: [level][kind: data, ack][rank]
 	uint64_t           fa_off[16], fb_off[16];
@@ -961,14 +995,29 @@ static int setup_p2p(tgpu_hier *h, const Partition &pt)
 		mine.fa_off[l] = off, off += align256(L.nface * sizeof(double));
 		mine.fb_off[l] = off, off += align256(L.nface * sizeof(double));
 	}
-	CU(cudaMalloc(&h->arena, off));
-	CU(cudaMemset(h->arena, 0, off));
-	void *base = nullptr;
-	TRY(alloc_base_of(h->arena, &base));
-	mine.base_off = (uint64_t) ((char *) h->arena - (char *) base);
-	CU(cudaIpcGetMemHandle(&mine.handle, base));
-	CU(cudaMalloc(&h->p2p_err, sizeof(int)));
-	CU(cudaMemset(h->p2p_err, 0, sizeof(int)));
+	// Everything that can fail on ONE rank only (allocation, IPC export, mapping a peer) is recorded in `ok` instead of
+	// returned: the ranks then agree on the outcome with an all-reduce, and if any of them cannot map its peers every
+	// rank keeps the NCCL send/recv exchange (k_exchange), so nobody is left waiting in a collective.
+	int         ok = 1;
+	std::string why;
+	auto        soft = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && ok) {
+            ok  = 0;
+            why = std::string(what) + ": " + cudaGetErrorString(e);
+            cudaGetLastError();
+        }
+	};
+	soft(cudaMalloc(&h->arena, off), "cudaMalloc(arena)");
+	if (ok) soft(cudaMemset(h->arena, 0, off), "cudaMemset(arena)");
+	if (ok) {
+		void *base = nullptr;
+		if (alloc_base_of(h->arena, &base) != TGPU_OK) ok = 0, why = "cuMemGetAddressRange failed";
+		else {
+			mine.base_off = (uint64_t) ((char *) h->arena - (char *) base);
+			soft(cudaIpcGetMemHandle(&mine.handle, base), "cudaIpcGetMemHandle");
+		}
+	}
+	mine.ok = ok;
 	// ---- all-gather the packs ----
 	std::vector<P2PPack> all(nr);
 	{
@@ -982,17 +1031,43 @@ static int setup_p2p(tgpu_hier *h, const Partition &pt)
 		cudaFree(d_mine);
 		cudaFree(d_all);
 	}
+	for (int r = 0; r < nr; r++)
+		if (!all[r].ok && ok) ok = 0, why = "rank " + std::to_string(r) + " could not export its arena";
 	// ---- map the arenas of the ranks I exchange with ----
 	std::vector<char *> rarena(nr, nullptr);
 	rarena[me] = (char *) h->arena;
-	for (int l = 0; l < nl; l++)
+	for (int l = 0; l < nl && ok; l++)
 		for (const PeerDev &pd : h->levels[l].peers) {
-			if (rarena[pd.peer]) continue;
+			if (rarena[pd.peer] || !ok) continue;
 			void *rb = nullptr;
-			CU(cudaIpcOpenMemHandle(&rb, all[pd.peer].handle, cudaIpcMemLazyEnablePeerAccess));
+			soft(cudaIpcOpenMemHandle(&rb, all[pd.peer].handle, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+			if (!ok) break;
 			h->ipc_opened.push_back(rb);
 			rarena[pd.peer] = (char *) rb + all[pd.peer].base_off;
 		}
+	if (ok) soft(cudaMalloc(&h->p2p_abort, sizeof(int)), "cudaMalloc(abort flag)");
+	if (ok) soft(cudaMemset(h->p2p_abort, 0, sizeof(int)), "cudaMemset(abort flag)");
+	{ // agreement: peer-to-peer only if every rank mapped everything it needs
+		int *d = nullptr;
+		CU(cudaMalloc(&d, sizeof(int)));
+		CU(cudaMemcpy(d, &ok, sizeof(int), cudaMemcpyHostToDevice));
+		NC(g_nccl.AllReduce(d, d, 1, ncclInt32, ncclMin, ctx->comm, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		int all_ok = 0;
+		CU(cudaMemcpy(&all_ok, d, sizeof(int), cudaMemcpyDeviceToHost));
+		cudaFree(d);
+		if (!all_ok) {
+			if (!ok) fprintf(stderr, "tgpu: rank %d cannot use the peer-to-peer halo exchange (%s)\n", me, why.c_str());
+			if (me == 0) fprintf(stderr, "tgpu: peer-to-peer mapping unavailable on at least one rank: using the NCCL send/recv halo exchange\n");
+			for (void *b : h->ipc_opened) cudaIpcCloseMemHandle(b);
+			h->ipc_opened.clear();
+			cudaFree(h->arena);
+			cudaFree(h->p2p_abort);
+			h->arena     = nullptr;
+			h->p2p_abort = nullptr;
+			return TGPU_OK; // L.p2p stays false on every level
+		}
+	}
 	// ---- per level: move the face buffers into the arena, exchange the halo-slot numbering, build the tables ----
 	for (int l = 0; l < nl; l++) {
 		LevelDev &       L  = h->levels[l];
@@ -1076,6 +1151,7 @@ extern "C" int tgpu_hierarchy_create_distributed(tgpu_ctx *ctx, const tgpu_part 
 		LevelDev &       L  = h->levels[l];
 		L.distributed       = PL.distributed;
 		L.n_interior        = PL.n_interior;
+		if (PL.distributed && l < pt.owner.size()) L.global_P = (int64_t) pt.owner[l].size();
 		for (int e = 0; e < 4; e++) CU(cudaEventCreateWithFlags(&L.ev[e], cudaEventDisableTiming));
 		std::vector<int32_t> sp, ss, rs, rsd;
 		for (const PeerExchange &x : PL.peers) {
@@ -1173,7 +1249,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	}
 	for (void *b : h->ipc_opened) cudaIpcCloseMemHandle(b);
 	cudaFree(h->arena);
-	cudaFree(h->p2p_err);
+	cudaFree(h->p2p_abort);
 	cudaFree(h->krylov_sc);
 	cudaFree(h->mats);
 	cudaFree(h->lam);
@@ -1183,12 +1259,53 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	delete h;
 	return TGPU_OK;
 }
+// Gives the memory of everything the library allocated lazily on behalf of earlier calls back to the device: Krylov work
+// vectors, the host-buffer slots of tgpu_vcycle_host / _async, cached cycle graphs, the vector pool's free blocks.  The
+// neighbour tables, face buffers and per-level cycle vectors stay.
+extern "C" int tgpu_hierarchy_trim(tgpu_hier *h)
+{
+	API_BEGIN
+	if (!h) return fail(TGPU_ERR_ARG, "null hierarchy");
+	tgpu_ctx *ctx = h->ctx;
+	CU(cudaSetDevice(ctx->device));
+	if (h->s_in) CU(cudaStreamSynchronize(h->s_in));
+	if (h->s_out) CU(cudaStreamSynchronize(h->s_out));
+	CU(cudaStreamSynchronize(ctx->stream));
+	free_graphs(h);
+	for (tgpu_vec *v : h->krylov_ws) tgpu_vec_destroy(v);
+	h->krylov_ws.clear();
+	tgpu_vec_destroy(h->host_f), h->host_f = nullptr;
+	tgpu_vec_destroy(h->host_u), h->host_u = nullptr;
+	for (int k = 0; k < 2; k++) {
+		tgpu_vec_destroy(h->pipe_f[k]), h->pipe_f[k] = nullptr;
+		tgpu_vec_destroy(h->pipe_u[k]), h->pipe_u[k] = nullptr;
+	}
+	h->pipe_count = 0;
+	CU(cudaStreamSynchronize(ctx->stream));
+	cudaMemPool_t pool = nullptr;
+	CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+	CU(cudaMemPoolTrimTo(pool, 0));
+	return TGPU_OK;
+	API_END
+}
 extern "C" int tgpu_hierarchy_info(const tgpu_hier *h, int *D, int *n, int *nlevels)
 {
 	if (!h) return fail(TGPU_ERR_ARG, "null hierarchy");
 	if (D) *D = h->D;
 	if (n) *n = h->N;
 	if (nlevels) *nlevels = (int) h->levels.size();
+	return TGPU_OK;
+}
+// FftwPatchSolver(domain, lambda) / DftPatchSolver(domain, lambda) (PatchSolvers/FftwPatchSolver.h:66,170,
+// DftPatchSolver.h:78,168): the block-Jacobi patch problems become (Laplacian + lambda) u = rhs.  As in the reference the
+// shift lives in the patch solver only; the operator (StarPatchOp) is unchanged.
+extern "C" int tgpu_hierarchy_set_lambda(tgpu_hier *h, double lambda)
+{
+	if (!h) return fail(TGPU_ERR_ARG, "null argument");
+	if (!(lambda == lambda)) return fail(TGPU_ERR_ARG, "tgpu_hierarchy_set_lambda: lambda is NaN");
+	h->lambda = lambda;
+	if (lambda != 0.0 && is_3d32(h) && !h->scratch32) CU(cudaMalloc(&h->scratch32, (size_t) h->ctx->sm_count * 2 * 32768 * sizeof(double)));
+	free_graphs(h);
 	return TGPU_OK;
 }
 extern "C" int tgpu_hierarchy_force_generic_kernels(tgpu_hier *h, int on)
@@ -1209,6 +1326,10 @@ extern "C" int tgpu_level_npatch(const tgpu_hier *h, int level, int64_t *npatch,
 // ------------------------------------------------------------------------------------------
 // vectors
 // ------------------------------------------------------------------------------------------
+// Vector storage comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the library's stream):
+// creating and destroying temporaries - the reference allocates three vectors per level per cycle (GMG/Cycle.h:59-64)
+// and a caller driving the API-granular plugin classes does the same - costs neither a device synchronisation nor a
+// trip to the driver's allocator once the pool is warm.
 extern "C" int tgpu_vec_create(tgpu_hier *h, int level, tgpu_vec **out)
 {
 	if (!h || !out || level < 0 || level >= (int) h->levels.size()) return fail(TGPU_ERR_ARG, "tgpu_vec_create: bad argument");
@@ -1217,7 +1338,7 @@ extern "C" int tgpu_vec_create(tgpu_hier *h, int level, tgpu_vec **out)
 	v->h     = h;
 	v->level = level;
 	v->n     = h->levels[level].ncells;
-	CU(cudaMalloc(&v->d, v->n * sizeof(double)));
+	CU(cudaMallocAsync(&v->d, std::max<size_t>(1, v->n) * sizeof(double), h->ctx->stream));
 	CU(cudaMemsetAsync(v->d, 0, v->n * sizeof(double), h->ctx->stream));
 	*out = v.release();
 	return TGPU_OK;
@@ -1225,10 +1346,17 @@ extern "C" int tgpu_vec_create(tgpu_hier *h, int level, tgpu_vec **out)
 extern "C" int tgpu_vec_destroy(tgpu_vec *v)
 {
 	if (!v) return TGPU_OK;
-	cudaStreamSynchronize(v->h->ctx->stream);
-	// cached graphs may reference this storage
-	free_graphs(v->h);
-	cudaFree(v->d);
+	tgpu_hier *h = v->h;
+	// cached cycle graphs that were captured on this storage are dropped; graphs of other vectors stay
+	for (size_t i = 0; i < h->graphs.size();) {
+		if (h->graphs[i].f == v->d || h->graphs[i].u == v->d) {
+			cudaGraphExecDestroy(h->graphs[i].exec);
+			h->graphs.erase(h->graphs.begin() + i);
+		} else {
+			i++;
+		}
+	}
+	cudaFreeAsync(v->d, h->ctx->stream); // stream-ordered: work already queued on the vector completes first
 	delete v;
 	return TGPU_OK;
 }
@@ -1244,7 +1372,7 @@ extern "C" int tgpu_vec_download(const tgpu_vec *v, double *host)
 	if (!v || !host) return fail(TGPU_ERR_ARG, "null argument");
 	CU(cudaMemcpyAsync(host, v->d, v->n * sizeof(double), cudaMemcpyDeviceToHost, v->h->ctx->stream));
 	CU(cudaStreamSynchronize(v->h->ctx->stream));
-	return TGPU_OK;
+	return check_comm(v->h->ctx);
 }
 extern "C" int tgpu_vec_upload_async(tgpu_vec *v, const double *host)
 {
@@ -1336,7 +1464,7 @@ template <int OP> static int reduce(const tgpu_vec *a, const tgpu_vec *b, double
 	CU(cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	*result = ctx->h_result[0];
-	return TGPU_OK;
+	return check_comm(ctx);
 }
 extern "C" int tgpu_vec_dot(const tgpu_vec *v, const tgpu_vec *b, double *result) { return reduce<0>(v, b, result); }
 extern "C" int tgpu_vec_two_norm(const tgpu_vec *v, double *result)
@@ -1430,11 +1558,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
-	if (is_3d32(h) && L.has_neumann) { // general transform path through an L2-resident scratch block
+	const bool general = L.has_neumann || h->lambda != 0.0; // patch solves that are not the plain Dirichlet Poisson solve
+	if (is_3d32(h) && general) { // general transform path through an L2-resident scratch block
 		const int nblk = std::min(p1 - p0, h->ctx->sm_count * 2);
-		if (!h->scratch32) return fail(TGPU_ERR_ARG, "k_smooth: scratch for 32^3 Neumann levels missing");
+		if (!h->scratch32) return fail(TGPU_ERR_ARG, "k_smooth: scratch for the general 32^3 patch solve missing");
 		return launch(h->ctx, smooth3d32n_kernel, dim3(nblk), dim3(TGPU_THREADS), 0, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, uc,
-		              (const double *) h->mats, (const double *) h->lam, h->scratch32, (int) zero_guess, (int) emit, (int) (uc != nullptr), (int) write_u);
+		              (const double *) h->mats, (const double *) h->lam, h->scratch32, (int) zero_guess, (int) emit, (int) (uc != nullptr), (int) write_u, h->lambda);
 	}
 	if (is_3d32(h)) {
 		// one cluster of two CTAs (two SMs) per patch, see smooth3d32c_kernel
@@ -1465,7 +1594,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		if (emit) return launch_smooth3d16<true, true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
 		return launch_smooth3d16<true, false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
 	}
-	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !L.has_neumann) { // the generic kernel has the Neumann path
+	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !general) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		switch (key) {
 		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
@@ -1480,7 +1609,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
 		}
 	}
-	if (h->D == 2 && h->N == 32 && !h->generic_kernels && !L.has_neumann) { // one warp per patch, see smooth2d32.cuh
+	if (h->D == 2 && h->N == 32 && !h->generic_kernels && !general) { // one warp per patch, see smooth2d32.cuh
 		const int    nblk = (p1 - p0 + Q32_WARPS - 1) / Q32_WARPS;
 		const dim3   grid(std::min(nblk, h->ctx->sm_count * 2)), block(TGPU_THREADS);
 		const size_t sm  = smooth2d32_smem_bytes();
@@ -1508,12 +1637,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = TGPU_S16_TRIDIAG ? h->tri : h->eig;
-		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
-		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
-		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
-		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
-		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
-		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam);
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
 	});
 }
 // coarse = R (f - A u) for a u that a block-Jacobi sweep has just produced: needs only the faces of the new
@@ -1554,6 +1683,12 @@ static int k_prolong_add(tgpu_hier *h, int l, const double *coarse, double *fine
 	Tag       tg(h->ctx, "prolong_add", l);
 	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, prolong_add_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, fine));
 }
+static int k_prolong_linear_add(tgpu_hier *h, int l, const double *coarse, double *fine)
+{
+	LevelDev &L = h->levels[l];
+	Tag       tg(h->ctx, "prolong_linear_add", l);
+	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, prolong_linear_add_kernel<DD, NN>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, coarse, fine));
+}
 static int k_prolong_faces(tgpu_hier *h, int l, const double *coarse, double *F)
 {
 	LevelDev &L = h->levels[l];
@@ -1584,7 +1719,7 @@ static int p2p_wait(tgpu_hier *h, int l, int kind, int lag)
 	LevelDev &L = h->levels[l];
 	Tag       tg(h->ctx, kind == P2P_DATA ? "p2p_wait_data" : "p2p_wait_ack", l);
 	return launch(h->ctx, p2p_wait_kernel, dim3(1), dim3(32), 0, (const uint64_t *) (kind == P2P_DATA ? L.data_flags : L.ack_flags),
-	              (const int32_t *) L.peer_rank, (int) L.peers.size(), L.cnt + (kind == P2P_DATA ? 1 : 3), lag, h->p2p_err);
+	              (const int32_t *) L.peer_rank, (int) L.peers.size(), L.cnt + (kind == P2P_DATA ? 1 : 3), lag, h->p2p_abort, (int *) h->ctx->p2p_err);
 }
 // store my boundary faces (F, or F + P uc on the boundary cells) into the peers' halo slots and publish them
 static int p2p_push(tgpu_hier *h, int l, double *F, const double *uc)
@@ -1749,6 +1884,14 @@ extern "C" int tgpu_prolong_add(tgpu_hier *h, int fine_level, const tgpu_vec *co
 	return k_prolong_add(h, fine_level, coarse->d, fine->d);
 	API_END
 }
+extern "C" int tgpu_prolong_add_linear(tgpu_hier *h, int fine_level, const tgpu_vec *coarse, tgpu_vec *fine)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, fine_level, fine, "tgpu_prolong_add_linear"));
+	TRY(check_level_vec(h, fine_level + 1, coarse, "tgpu_prolong_add_linear"));
+	return k_prolong_linear_add(h, fine_level, coarse->d, fine->d);
+	API_END
+}
 extern "C" int tgpu_residual_restrict(tgpu_hier *h, int fine_level, const tgpu_vec *f, const tgpu_vec *u, tgpu_vec *coarse_f)
 {
 	API_BEGIN
@@ -1776,6 +1919,10 @@ extern "C" int tgpu_cycle_opts_default(TgpuCycleOpts *o)
 	o->cycle_type                                                   = 0;
 	o->fused                                                        = 1;
 	o->use_graph                                                    = 1;
+	o->max_levels                                                   = 0;
+	o->interpolator                                                 = 0;
+	o->reserved_                                                    = 0;
+	o->patches_per_proc                                             = 0.0;
 	return TGPU_OK;
 }
 
@@ -1802,20 +1949,21 @@ static int generic_prep_coarser(tgpu_hier *h, int l, const double *f, const doub
 }
 static int generic_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u)
 {
-	const int last = (int) h->levels.size() - 1;
+	const int last = h->last_level;
 	if (l == last) {
 		for (int i = 0; i < o.coarse_sweeps; i++) TRY(generic_smooth(h, l, f, u));
 	} else {
 		LevelDev &C = h->levels[l + 1];
 		for (int i = 0; i < o.pre_sweeps; i++) TRY(generic_smooth(h, l, f, u));
 		TRY(generic_prep_coarser(h, l, f, u));
+		auto prolong = [&]() { return o.interpolator == 1 ? k_prolong_linear_add(h, l, C.u, u) : k_prolong_add(h, l, C.u, u); };
 		TRY(generic_visit(h, o, l + 1, C.f, C.u));
-		TRY(k_prolong_add(h, l, C.u, u));
+		TRY(prolong());
 		if (o.cycle_type == 1) {
 			for (int i = 0; i < o.mid_sweeps; i++) TRY(generic_smooth(h, l, f, u));
 			TRY(generic_prep_coarser(h, l, f, u));
 			TRY(generic_visit(h, o, l + 1, C.f, C.u));
-			TRY(k_prolong_add(h, l, C.u, u));
+			TRY(prolong());
 		}
 		for (int i = 0; i < o.post_sweeps; i++) TRY(generic_smooth(h, l, f, u));
 	}
@@ -1849,7 +1997,7 @@ static int exchange_async(tgpu_hier *h, int l, double *F, const double *uc, cuda
 static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double *f, double *u, bool want_faces,
                        const double *fine_faces = nullptr)
 {
-	const int last = (int) h->levels.size() - 1;
+	const int last = h->last_level;
 	LevelDev &L    = h->levels[l];
 	double *  Fcur = L.Fa, *Falt = L.Fb;
 	if (l == last) {
@@ -1926,13 +2074,18 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	if (l == 0 && want_faces) h->cycle_faces = Fcur; // the last sweep emitted the slices of u here
 	return TGPU_OK;
 }
+// the fused schedule covers V cycles with at least one sweep everywhere and the piecewise-constant interpolator
+static bool fused_schedule(const TgpuCycleOpts &o)
+{
+	return o.fused && o.cycle_type == 0 && o.interpolator == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+}
 // want_faces: the caller applies the operator to the result next (BiCGStab: v = A M^-1 p), so the last sweep also
 // writes the result's boundary slices (h->cycle_faces != nullptr afterwards) and no extraction pass is needed
 static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u, bool want_faces = false)
 {
-	const bool fused = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+	const bool fused = fused_schedule(o);
 	h->cycle_faces   = nullptr;
-	if (fused) return fused_visit(h, o, 0, f, u, want_faces && h->levels.size() > 1);
+	if (fused) return fused_visit(h, o, 0, f, u, want_faces && h->last_level > 0);
 	TRY(k_set(h, u, h->levels[0].ncells, 0.0)); // Cycle::apply: u->set(0)
 	return generic_visit(h, o, 0, f, u);
 }
@@ -1943,12 +2096,22 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	TgpuCycleOpts o;
 	if (opts) o = *opts;
 	else tgpu_cycle_opts_default(&o);
-	if (o.pre_sweeps < 0 || o.post_sweeps < 0 || o.coarse_sweeps < 0 || o.mid_sweeps < 0 || (o.cycle_type != 0 && o.cycle_type != 1))
+	o.reserved_ = 0;
+	if (o.pre_sweeps < 0 || o.post_sweeps < 0 || o.coarse_sweeps < 0 || o.mid_sweeps < 0 || (o.cycle_type != 0 && o.cycle_type != 1)
+	    || (o.interpolator != 0 && o.interpolator != 1))
 		return fail(TGPU_ERR_ARG, "tgpu_vcycle: bad cycle options"); /* reference: throw 3, GMG/CycleFactory3d.cpp:131 */
 	tgpu_ctx *ctx = h->ctx;
-	for (size_t l = 0; l < h->levels.size(); l++) {
+	// the level list the reference's factory would build for these options (GMG/CycleFactory3d.cpp:99-104): at most
+	// max_levels levels (0 = no limit), and no level with fewer than patches_per_proc patches per rank
+	if (o.max_levels < 0 || !(o.patches_per_proc >= 0.0)) return fail(TGPU_ERR_ARG, "tgpu_vcycle: bad max_levels / patches_per_proc");
+	h->last_level = 0;
+	for (int l = 1; l < (int) h->levels.size() && (o.max_levels <= 0 || l < o.max_levels); l++) {
+		if ((double) h->levels[l].global_P / ctx->nranks < o.patches_per_proc) break;
+		h->last_level = l;
+	}
+	for (size_t l = 0; l <= (size_t) h->last_level; l++) {
 		TRY(need_smoother(h, (int) l));
-		const bool fused_sched = o.fused && o.cycle_type == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+		const bool fused_sched = fused_schedule(o);
 		TRY(ensure_work(h, (int) l, !fused_sched || (o.fused == 2 && is_3d32(h))));
 	}
 	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u, want_faces);
@@ -2005,7 +2168,7 @@ extern "C" int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const d
 	TRY(cycle_ptr(h, opts, h->host_f->d, h->host_u->d));
 	TRY(tgpu_vec_download_async(h->host_u, u_host));
 	CU(cudaStreamSynchronize(h->ctx->stream));
-	return TGPU_OK;
+	return check_comm(h->ctx);
 	API_END
 }
 
@@ -2022,11 +2185,15 @@ extern "C" int tgpu_vcycle_host_async(tgpu_hier *h, const TgpuCycleOpts *opts, c
 		CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
 		CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
 		for (int k = 0; k < 2; k++) {
-			TRY(tgpu_vec_create(h, 0, &h->pipe_f[k]));
-			TRY(tgpu_vec_create(h, 0, &h->pipe_u[k]));
 			CU(cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
 			CU(cudaEventCreateWithFlags(&h->ev_cyc[k], cudaEventDisableTiming));
 			CU(cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming));
+		}
+	}
+	if (!h->pipe_f[0]) { // first call, or the first one after tgpu_hierarchy_trim
+		for (int k = 0; k < 2; k++) {
+			TRY(tgpu_vec_create(h, 0, &h->pipe_f[k]));
+			TRY(tgpu_vec_create(h, 0, &h->pipe_u[k]));
 		}
 		CU(cudaStreamSynchronize(ctx->stream)); // the zero fills of the new vectors
 	}
@@ -2056,7 +2223,7 @@ extern "C" int tgpu_vcycle_host_wait(tgpu_hier *h)
 	if (!h) return fail(TGPU_ERR_ARG, "null hierarchy");
 	if (h->s_out) CU(cudaStreamSynchronize(h->s_out));
 	CU(cudaStreamSynchronize(h->ctx->stream));
-	return TGPU_OK;
+	return check_comm(h->ctx);
 	API_END
 }
 
@@ -2108,7 +2275,7 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 		CU(cudaMemcpyAsync(ctx->h_result, sc + SC_RNORM, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 		*out = ctx->h_result[0];
-		return (int) TGPU_OK;
+		return check_comm(ctx);
 	};
 	TRY(A(x, resid));
 	TRY(tgpu_vec_scale_then_add(resid, -1, b));
@@ -2264,7 +2431,7 @@ extern "C" int tgpu_vec_integrate(tgpu_hier *h, const tgpu_vec *v, double *integ
 		for (int a = 0; a < h->D; a++) vol *= sp[(size_t) p * h->D + a] * h->N;
 		res[1] += vol;
 	}
-	if (h->ctx->nranks > 1) {
+	if (h->ctx->nranks > 1 && h->levels[0].distributed) { // a replicated level: every rank already holds the global sums
 		double *d2 = nullptr;
 		CU(cudaMalloc(&d2, 2 * sizeof(double)));
 		CU(cudaMemcpyAsync(d2, res, 2 * sizeof(double), cudaMemcpyHostToDevice, h->ctx->stream));

@@ -108,13 +108,58 @@ def neumann_init_case():
     print("2d_2d2ref_d1_n8_neumann_init", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+# Cycle variants and the patch solver's shift, from the reference's own WCycle / CycleFactory / DftPatchSolver:
+# name -> "@" option string of ref_gmg (oracle/ref_driver.cpp)
+CYCLE_VARIANTS = {
+    "W": "W", "W_p2m2c2": "W,pre=2,mid=2,post=1,coarse=2", "V_max_levels2": "max_levels=2", "V_ppp2": "ppp=2",
+    "W_max_levels2": "W,max_levels=2", "V_lambda": "lambda=-3.5",
+}
+CYCLE_CASES = [("3d_2refine_n8", 3, "2refine.bin", 0, 8), ("2d_2d2ref_d1_n8", 2, "2d2ref.bin", 1, 8),
+               ("3d_multi_refine_n4", 3, "multi_refine.bin", 0, 4)]
+
+
+def cycle_variant_cases():
+    for name, D, mesh, div, n in CYCLE_CASES:
+        base = np.load(os.path.join(HERE, name + ".npz"))
+        f = base["rhs_f"]
+        out = {"D": D, "n": n, "divide": div, "mesh": mesh}
+        with tempfile.TemporaryDirectory() as tmp:
+            t = lambda k: os.path.join(tmp, k)  # noqa: E731
+            f.tofile(t("f"))
+            for key, opt in CYCLE_VARIANTS.items():
+                ref(D, mesh, div, n, "vcycle:%s:%s" % (t("f"), t("v")), solver="dft@" + opt)
+                out["cycle_" + key] = np.fromfile(t("v"))
+            # one block-Jacobi sweep with the shifted patch solver on every level, both solver implementations
+            rng = np.random.default_rng(777)
+            for l in range(int(base["nlevels"])):
+                cells = base["L%d_in_u" % l].size
+                u, ff = rng.standard_normal(cells), rng.standard_normal(cells)
+                u.tofile(t("u"))
+                ff.tofile(t("ff"))
+                ref(D, mesh, div, n, "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("s1")), solver="dft@lambda=-3.5")
+                ref(D, mesh, div, n, "smooth:%d:%s:%s:%s" % (l, t("ff"), t("u"), t("s2")), solver="fftw@lambda=-3.5")
+                out["L%d_in_u" % l], out["L%d_in_f" % l] = u, ff
+                out["L%d_smooth_lambda" % l] = np.fromfile(t("s1"))
+                out["L%d_smooth_lambda_fftw" % l] = np.fromfile(t("s2"))
+        out["lambda"] = -3.5
+        np.savez_compressed(os.path.join(HERE, name + "_cycles.npz"), **out)
+        print(name + "_cycles", sorted(k for k in out if k.startswith("cycle_")))
+
+
 def main():
+    if "--cycles-only" in sys.argv:
+        return cycle_variant_cases()
     if "--neumann-init-only" in sys.argv:
         return neumann_init_case()
     if "--neumann-only" in sys.argv:
         return neumann_cases()
     neumann_init_case()
     neumann_cases()
+    _base_cases()
+    cycle_variant_cases()
+
+
+def _base_cases():
     for name, D, mesh, div, n in CASES:
         with tempfile.TemporaryDirectory() as tmp:
             t = lambda f: os.path.join(tmp, f)  # noqa: E731

@@ -144,10 +144,9 @@ def test_vs_oracle_seeded(ctx, mesh_file, D, n, divide):
                  dict(pre_sweeps=3, post_sweeps=2, coarse_sweeps=3, fused=2), dict(pre_sweeps=3, post_sweeps=3),
                  dict(cycle_type=1), dict(pre_sweeps=0, post_sweeps=2)):
         h.vcycle(f, u, pps.CycleOpts.default(**opts))
-        if opts.get("cycle_type", 0) == 0:
-            ref = go.vcycle(levels, fn, pre=opts.get("pre_sweeps", 1), post=opts.get("post_sweeps", 1),
-                            coarse_sweeps=opts.get("coarse_sweeps", 1))
-            assert rel_l2(u.download(), ref) < TOL, opts
+        ref = go.cycle(levels, fn, cycle_type="W" if opts.get("cycle_type", 0) == 1 else "V", pre=opts.get("pre_sweeps", 1),
+                       post=opts.get("post_sweeps", 1), coarse_sweeps=opts.get("coarse_sweeps", 1))
+        assert rel_l2(u.download(), ref) < TOL, opts
     h.close()
     mesh.close()
 
@@ -369,6 +368,195 @@ def test_error_behaviour(ctx):
         pps.Hierarchy.from_mesh(ctx, mesh, 6)  # unsupported patch size
     with pytest.raises(pps.TgpuError):
         pps.Hierarchy.from_mesh(ctx, mesh, 64)
+    h.close()
+    mesh.close()
+
+
+CYCLE_GOLDENS = ["3d_2refine_n8", "2d_2d2ref_d1_n8", "3d_multi_refine_n4"]
+CYCLE_VARIANT_OPTS = {
+    "W": dict(cycle_type=1), "W_p2m2c2": dict(cycle_type=1, pre_sweeps=2, mid_sweeps=2, post_sweeps=1, coarse_sweeps=2),
+    "V_max_levels2": dict(max_levels=2), "V_ppp2": dict(patches_per_proc=2.0), "W_max_levels2": dict(cycle_type=1, max_levels=2),
+}
+
+
+@pytest.mark.parametrize("name", CYCLE_GOLDENS)
+def test_cycle_variants_vs_reference(ctx, name):
+    """W cycles (GMG/WCycle.h:45-68), the level truncation of the factory (CycleOpts max_levels / patches_per_proc,
+    GMG/CycleFactory3d.cpp:99-104) and the patch solver's lambda (FftwPatchSolver.h:66,170) against golden vectors the
+    reference itself produced (tests/golden/*_cycles.npz), on every schedule and with / without graph replay."""
+    g, c = load_golden(name), load_golden(name + "_cycles")
+    h, mesh = build(ctx, str(g["mesh"]), int(g["D"]), int(g["n"]), int(g["divide"]))
+    f, u = h.new_vec(0, g["rhs_f"]), h.new_vec(0)
+    for key, kw in CYCLE_VARIANT_OPTS.items():
+        for fused in (1, 0):
+            for graph in (1, 0):
+                h.vcycle(f, u, pps.CycleOpts.default(fused=fused, use_graph=graph, **kw))
+                assert rel_l2(u.download(), c["cycle_" + key]) < TOL, (key, fused, graph)
+    # the plain cycle still comes out after truncated ones (the level limit is per call, not sticky)
+    h.vcycle(f, u)
+    assert rel_l2(u.download(), g["vcycle"]) < TOL
+    # BiCGStab preconditioned with a W cycle converges in no more iterations than with the V cycle
+    x = h.new_vec(0)
+    its_w, rel = h.bicgstab(f, x, pps.CycleOpts.default(cycle_type=1), tol=1e-12, max_it=100)
+    assert rel <= 1e-12 and its_w <= int(g["bicgstab_info"][0])
+    lam = float(c["lambda"])
+    h.set_lambda(lam)
+    for l in range(h.nlevels):
+        ul, fl = h.new_vec(l, c["L%d_in_u" % l]), h.new_vec(l, c["L%d_in_f" % l])
+        h.smooth(l, fl, ul)
+        assert rel_l2(ul.download(), c["L%d_smooth_lambda" % l]) < TOL, l
+    for fused in (1, 2, 0):
+        h.vcycle(f, u, pps.CycleOpts.default(fused=fused))
+        assert rel_l2(u.download(), c["cycle_V_lambda"]) < 1e-11, fused
+    h.set_lambda(0.0)
+    h.vcycle(f, u)
+    assert rel_l2(u.download(), g["vcycle"]) < TOL
+    h.close()
+    mesh.close()
+
+
+@pytest.mark.parametrize("mesh_file,D,n,divide", [("2refine.bin", 3, 16, 0), ("2uni.bin", 3, 32, 0), ("2d2ref.bin", 2, 32, 1)])
+def test_lambda_on_specialised_sizes_vs_oracle(ctx, mesh_file, D, n, divide):
+    """a non-zero lambda must leave the specialised Dirichlet kernels (16^3, 32^3, 2D 32^2) for the general patch solve"""
+    h, mesh = build(ctx, mesh_file, D, n, divide)
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), D, n, divide)
+    rng = np.random.default_rng(5)
+    h.set_lambda(-7.25)
+    for l, L in enumerate(levels):
+        un, fn = rng.standard_normal(L.shape), rng.standard_normal(L.shape)
+        u, f = h.new_vec(l, un), h.new_vec(l, fn)
+        h.smooth(l, f, u)
+        assert rel_l2(u.download(), go.smooth(L, fn, un, -7.25)) < 1e-11
+    fn = rng.standard_normal(levels[0].shape)
+    f, u = h.new_vec(0, fn), h.new_vec(0)
+    h.vcycle(f, u)
+    assert rel_l2(u.download(), go.cycle(levels, fn, lam=-7.25)) < 1e-11
+    h.close()
+    mesh.close()
+
+
+def test_config_e_kernel_path_vs_oracle(ctx):
+    """BASELINE config E's kernel path: the deeply refined quadtree multi_refine_8 with 32 x 32 patches and Dirichlet
+    boundaries runs smooth2d32_kernel with coarse/fine faces on every level; per-level operators, the cycle (all
+    schedules) and the Krylov solve against the oracle."""
+    h, mesh = build(ctx, "2d_multi_refine_8.bin", 2, 32, 0)
+    levels = go.build_hierarchy(os.path.join(MESHES, "2d_multi_refine_8.bin"), 2, 32, 0)
+    assert [L.P for L in levels] == [h.npatch(l) for l in range(h.nlevels)] and levels[0].P == 160
+    rng = np.random.default_rng(2718)
+    for l, L in enumerate(levels):
+        un, fn = rng.standard_normal(L.shape), rng.standard_normal(L.shape)
+        u, f, out = h.new_vec(l, un), h.new_vec(l, fn), h.new_vec(l)
+        h.apply(l, u, out)
+        assert rel_l2(out.download(), go.apply_op(L, un)) < TOL
+        h.smooth(l, f, u)
+        assert rel_l2(u.download(), go.smooth(L, fn, un)) < TOL
+        if l + 1 < len(levels):
+            c = h.new_vec(l + 1)
+            h.residual_restrict(l, f, u, c)
+            r = -1 * go.apply_op(L, u.download().reshape(L.shape)) + fn
+            assert rel_l2(c.download(), go.restrict(L, levels[l + 1], r)) < 1e-11
+    fn = rng.standard_normal(levels[0].shape)
+    f, u = h.new_vec(0, fn), h.new_vec(0)
+    ref = go.vcycle(levels, fn)
+    for fused in (1, 2, 0):
+        for graph in (1, 0):
+            h.vcycle(f, u, pps.CycleOpts.default(fused=fused, use_graph=graph))
+            assert rel_l2(u.download(), ref) < TOL, (fused, graph)
+    h.vcycle(f, u, pps.CycleOpts.default(pre_sweeps=2, post_sweeps=2, coarse_sweeps=2))
+    assert rel_l2(u.download(), go.vcycle(levels, fn, pre=2, post=2, coarse_sweeps=2)) < TOL
+    ft, et = go.trig_rhs(levels[0])
+    f.upload(ft)
+    x = h.new_vec(0)
+    its, rel = h.bicgstab(f, x, tol=1e-12, max_it=100)
+    xo, its_o = go.bicgstab(levels, ft)
+    assert its == its_o and rel_l2(x.download(), xo) < 1e-10
+    h.close()
+    mesh.close()
+
+
+@pytest.mark.parametrize("mesh_file,D,n,divide,neumann", [("2refine.bin", 3, 8, 0, False), ("2refine.bin", 3, 16, 0, False),
+                                                          ("2d_multi_refine_8.bin", 2, 16, 0, False), ("2d2ref.bin", 2, 32, 1, True),
+                                                          ("2uni.bin", 3, 32, 0, False), ("multi_refine.bin", 3, 4, 0, True)])
+def test_weighted_jacobi_vs_oracle(ctx, mesh_file, D, n, divide, neumann):
+    """the weighted-Jacobi option of the north star against oracle/gmg_oracle.jacobi (whose diagonal is pinned to the
+    reference's operator by tests/test_oracle_vs_reference.py), three sweeps on every level"""
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).set_neumann(neumann)
+    mesh.refine_leaves(divide)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), D, n, divide, neumann=neumann)
+    rng = np.random.default_rng(31)
+    for l, L in enumerate(levels):
+        un, fn = rng.standard_normal(L.shape), rng.standard_normal(L.shape)
+        u, f = h.new_vec(l, un), h.new_vec(l, fn)
+        for omega in (0.8, 2.0 / 3.0, 1.0):
+            h.smooth_jacobi(l, f, u, omega)
+            un = go.jacobi(L, fn, un, omega)
+        assert rel_l2(u.download(), un) < TOL, l
+    h.close()
+    mesh.close()
+
+
+@pytest.mark.parametrize("mesh_file,D,n,divide", [("2refine.bin", 3, 8, 0), ("3uni.bin", 3, 16, 0), ("2d2ref.bin", 2, 32, 1),
+                                                  ("2uni.bin", 3, 32, 0), ("multi_refine.bin", 3, 4, 0)])
+def test_linear_interpolator(ctx, mesh_file, D, n, divide):
+    """the piecewise (tri)linear interpolator: known answer of test/GMG.cpp:465-600 (linear fields are reproduced),
+    agreement with the oracle's restatement of the TriLinIntp.cpp coefficient tables, and cycles that use it"""
+    h, mesh = build(ctx, mesh_file, D, n, divide)
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), D, n, divide)
+    rng = np.random.default_rng(8)
+
+    def field(L):
+        out = np.zeros(L.shape)
+        for p in range(L.P):
+            c = [L.starts[p, a] + L.spacings[p, a] * (np.arange(n) + 0.5) for a in range(D)]
+            out[p] = (c[0][None, None, :] + 0.5 * c[1][None, :, None] - c[2][:, None, None]) if D == 3 else (c[0][None, :] + 0.5 * c[1][:, None])
+        return out
+
+    for l in range(len(levels) - 1):
+        fine, coarse = levels[l], levels[l + 1]
+        uc, uf = h.new_vec(l + 1, field(coarse)), h.new_vec(l)
+        h.prolong_add_linear(l, uc, uf)
+        assert rel_l2(uf.download(), field(fine)) < 1e-14
+        ucn, ufn = rng.standard_normal(coarse.shape), rng.standard_normal(fine.shape)
+        uc.upload(ucn)
+        uf.upload(ufn)
+        h.prolong_add_linear(l, uc, uf)
+        assert rel_l2(uf.download(), go.interpolate_trilinear(fine, coarse, ucn, ufn)) < 1e-14
+    fn = rng.standard_normal(levels[0].shape)
+    f, u = h.new_vec(0, fn), h.new_vec(0)
+    for kw, okw in ((dict(), dict()), (dict(cycle_type=1, pre_sweeps=2), dict(cycle_type="W", pre=2))):
+        h.vcycle(f, u, pps.CycleOpts.default(interpolator=1, **kw))
+        assert rel_l2(u.download(), go.cycle(levels, fn, interp=go.interpolate_trilinear, **okw)) < TOL
+    with pytest.raises(pps.TgpuError):
+        h.vcycle(f, u, pps.CycleOpts.default(interpolator=5))
+    h.close()
+    mesh.close()
+
+
+def test_vector_temporaries_keep_cached_graphs(ctx):
+    """creating and destroying temporaries (what the API-granular plugin classes do every cycle, GMG/Cycle.h:59-64) neither
+    invalidates the cycle graphs of other vectors nor changes results; tgpu_hierarchy_trim releases lazily allocated
+    work space and everything still works afterwards"""
+    h, mesh = build(ctx, "2refine.bin", 3, 16, 0)
+    fn = np.random.default_rng(4).standard_normal(h.ncells(0))
+    f, u = h.new_vec(0, fn), h.new_vec(0)
+    h.vcycle(f, u)
+    ref = u.download()
+    n0 = ctx.kernel_launches()
+    for _ in range(5):
+        tmp = [h.new_vec(l) for l in range(h.nlevels)]
+        for t in tmp:
+            t.close()
+        h.vcycle(f, u)
+        assert np.array_equal(u.download(), ref)
+    x = h.new_vec(0)
+    its, _ = h.bicgstab(f, x, tol=1e-10, max_it=50)
+    h.trim()
+    x2 = h.new_vec(0)
+    its2, _ = h.bicgstab(f, x2, tol=1e-10, max_it=50)
+    assert its == its2 and np.array_equal(x.download(), x2.download())
+    h.vcycle(f, u)
+    assert np.array_equal(u.download(), ref) and ctx.kernel_launches() > n0
     h.close()
     mesh.close()
 

@@ -74,3 +74,20 @@ def test_bad_arguments_report_errors():
         pps.Mesh.load("/nonexistent/mesh.bin", 3)
     with pytest.raises(pps.TgpuError):
         pps.Mesh.uniform(3, 2).extract_levels(5)  # odd n
+def test_corrupt_mesh_files_are_rejected(tmp_path):
+    """a truncated file, a 3D file opened as 2D and dangling ids are I/O errors, not out-of-bounds accesses"""
+    src = open(os.path.join(MESHES, "2refine.bin"), "rb").read()
+    bad = tmp_path / "trunc.bin"
+    bad.write_bytes(src[:len(src) - 40])
+    with pytest.raises(pps.TgpuError):
+        pps.Mesh.load(str(bad), 3)
+    with pytest.raises(pps.TgpuError):
+        pps.Mesh.load(os.path.join(MESHES, "2refine.bin"), 2)
+    b = bytearray(src)
+    b[8 + 8:8 + 12] = (123456).to_bytes(4, "little")  # the root's parent id -> dangling
+    bad2 = tmp_path / "dangling.bin"
+    bad2.write_bytes(bytes(b))
+    with pytest.raises(pps.TgpuError):
+        pps.Mesh.load(str(bad2), 3)
+
+

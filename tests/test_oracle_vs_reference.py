@@ -117,3 +117,82 @@ def test_second_order_convergence():
         x, _ = go.bicgstab(levels, f)
         errs.append(np.max(np.abs(x - exact)))
     assert 3.0 < errs[0] / errs[1] < 5.0
+
+
+CYCLE_GOLDENS = ["3d_2refine_n8", "2d_2d2ref_d1_n8", "3d_multi_refine_n4"]
+# key in *_cycles.npz -> arguments of go.cycle (the "@" options of ref_gmg that produced it, tests/golden/make_golden.py)
+CYCLE_VARIANT_ARGS = {
+    "W": dict(cycle_type="W"), "W_p2m2c2": dict(cycle_type="W", pre=2, mid=2, post=1, coarse_sweeps=2),
+    "V_max_levels2": dict(max_levels=2), "V_ppp2": dict(patches_per_proc=2.0), "W_max_levels2": dict(cycle_type="W", max_levels=2),
+    "V_lambda": dict(lam=-3.5),
+}
+
+
+@pytest.mark.parametrize("name", CYCLE_GOLDENS)
+def test_cycle_variants_vs_reference(name):
+    """GMG::WCycle (GMG/WCycle.h:45-68), the level truncation of GMG::CycleFactory (GMG/CycleFactory3d.cpp:99-104) and the
+    patch solver's lambda (DftPatchSolver.h:78,168), all against runs of the reference itself."""
+    g = load_golden(name)
+    c = load_golden(name + "_cycles")
+    levels = go.build_hierarchy(os.path.join(MESHES, str(g["mesh"])), int(g["D"]), int(g["n"]), int(g["divide"]))
+    f = g["rhs_f"].reshape(levels[0].shape)
+    assert rel_l2(go.cycle(levels, f), g["vcycle"]) < 1e-12
+    for key, kw in CYCLE_VARIANT_ARGS.items():
+        assert rel_l2(go.cycle(levels, f, **kw), c["cycle_" + key]) < 1e-12, key
+    # the truncated and W cycles really differ from the plain V cycle (the fixtures are not vacuous)
+    assert rel_l2(c["cycle_W"], g["vcycle"]) > 1e-6 and rel_l2(c["cycle_V_max_levels2"], g["vcycle"]) > 1e-6
+    lam = float(c["lambda"])
+    for l, L in enumerate(levels):
+        u, ff = c["L%d_in_u" % l].reshape(L.shape), c["L%d_in_f" % l].reshape(L.shape)
+        assert rel_l2(go.smooth(L, ff, u, lam), c["L%d_smooth_lambda" % l]) < TOL
+        assert rel_l2(c["L%d_smooth_lambda_fftw" % l], c["L%d_smooth_lambda" % l]) < TOL
+
+
+def test_jacobi_is_a_sweep_on_the_assembled_diagonal():
+    """jacobi(): the diagonal used must be the diagonal of the operator the reference applies (apply_op, pinned above):
+    probe A with unit vectors on a small refined mesh, Dirichlet and Neumann."""
+    for neumann in (False, True):
+        levels = go.build_hierarchy(os.path.join(MESHES, "2d2ref.bin"), 2, 4, 0, neumann=neumann)
+        L = levels[0]
+        diag = np.zeros(L.shape)
+        for idx in np.ndindex(*L.shape):
+            e = np.zeros(L.shape)
+            e[idx] = 1.0
+            diag[idx] = go.apply_op(L, e)[idx]
+        rng = np.random.default_rng(3)
+        u, f = rng.standard_normal(L.shape), rng.standard_normal(L.shape)
+        expect = u + 0.8 * (f - go.apply_op(L, u)) / diag
+        assert rel_l2(go.jacobi(L, f, u, 0.8), expect) < 1e-14
+
+
+@pytest.mark.parametrize("mesh,D,n,divide", [("2refine.bin", 3, 8, 0), ("3uni.bin", 3, 4, 0), ("2d2ref.bin", 2, 8, 1)])
+def test_trilinear_interpolation_known_answer(mesh, D, n, divide):
+    """test/GMG.cpp:465-600 (disabled upstream): the (tri)linear interpolator reproduces the linear field x + y/2 - z
+    on uniform and refined two-level meshes; and its weights are the tables of GMG/TriLinIntp.cpp:110-190."""
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh), D, n, divide)
+    fine, coarse = levels[0], levels[1]
+
+    def field(L):
+        out = np.zeros(L.shape)
+        for p in range(L.P):
+            c = [L.starts[p, a] + L.spacings[p, a] * (np.arange(n) + 0.5) for a in range(D)]
+            if D == 3:
+                out[p] = c[0][None, None, :] + 0.5 * c[1][None, :, None] - c[2][:, None, None]
+            else:
+                out[p] = c[0][None, :] + 0.5 * c[1][:, None]
+        return out
+
+    got = go.interpolate_trilinear(fine, coarse, field(coarse), np.zeros(fine.shape))
+    assert rel_l2(got, field(fine)) < 1e-14
+    if D == 3:
+        # interior fine cell (1, 1, 1) of orthant 0 mixes the coarse cube (0..1)^3 with 27/9/9/3/9/3/3/1 over 64; the
+        # corner cell (0, 0, 0) extrapolates with 125, -25, -25, 5, -25, 5, 5, -1 over 64
+        p = int(np.nonzero(fine.orth_on_parent == 0)[0][0])
+        uc = np.zeros(coarse.shape)
+        cube = np.arange(1.0, 9.0).reshape(2, 2, 2)  # [z][y][x]
+        uc[fine.parent_idx[p], :2, :2, :2] = cube
+        uf = go.interpolate_trilinear(fine, coarse, uc, np.zeros(fine.shape))[p]
+        w = np.array([27, 9, 9, 3, 9, 3, 3, 1]) / 64.0  # order x fastest: (0,0,0), (1,0,0), (0,1,0), ...
+        assert abs(uf[1, 1, 1] - float(np.dot(w, cube.ravel()))) < 1e-14
+        wc = np.array([125, -25, -25, 5, -25, 5, 5, -1]) / 64.0
+        assert abs(uf[0, 0, 0] - float(np.dot(wc, cube.ravel()))) < 1e-14
