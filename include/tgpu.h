@@ -176,6 +176,9 @@ int tgpu_vcycle_host(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_pi
  * u_pinned of a call is valid after tgpu_vcycle_host_wait. */
 int tgpu_vcycle_host_async(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f_pinned, double *u_pinned);
 int tgpu_vcycle_host_wait(tgpu_hier *h);
+/* the two copies of one pipelined step alone (host -> dst_dev and src_dev -> host concurrently, then waited for): the
+ * host-link ceiling of the e2e path */
+int tgpu_vec_transfer_pair(tgpu_hier *h, tgpu_vec *dst_dev, const double *src_pinned, const tgpu_vec *src_dev, double *dst_pinned);
 
 /* ---- multi-GPU (one process per GPU): Morton partition of the patches + NCCL halo exchange ----
  * Replaces the reference's Zoltan partition / migration (ThundereggDomGen.h:223-648), the interface

@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "tgpu_init_trig_rhs", "tgpu_init_neumann_rhs", "tgpu_vec_integrate", "tgpu_mesh_partition", "tgpu_part_destroy", "tgpu_part_info", "tgpu_part_level", "tgpu_part_peer", "tgpu_part_level_interior",
     "tgpu_comm_unique_id", "tgpu_comm_init", "tgpu_hierarchy_create_distributed",
     "tgpu_hierarchy_force_generic_kernels", "tgpu_mesh_set_neumann", "tgpu_vcycle_host_async", "tgpu_vcycle_host_wait",
-    "tgpu_hierarchy_trim", "tgpu_hierarchy_set_lambda", "tgpu_prolong_add_linear",
+    "tgpu_hierarchy_trim", "tgpu_hierarchy_set_lambda", "tgpu_prolong_add_linear", "tgpu_vec_transfer_pair",
 ]
 
 lib.tgpu_last_error.restype = C.c_char_p
@@ -138,6 +138,7 @@ for _name, _args in {
     "tgpu_hierarchy_force_generic_kernels": [_vp, C.c_int], "tgpu_hierarchy_set_lambda": [_vp, C.c_double],
     "tgpu_mesh_set_neumann": [_vp, C.c_int],
     "tgpu_vcycle_host_async": [_vp, C.POINTER(CycleOpts), _vp, _vp], "tgpu_vcycle_host_wait": [_vp],
+    "tgpu_vec_transfer_pair": [_vp, _vp, _vp, _vp, _vp],
 }.items():
     getattr(lib, _name).argtypes = _args
     getattr(lib, _name).restype = C.c_int
@@ -458,6 +459,10 @@ class Hierarchy:
     def vcycle_host_async(self, f_pinned, u_pinned, opts=None):
         """pipelined form for a stream of independent right-hand sides; results are valid after vcycle_host_wait()"""
         check(lib.tgpu_vcycle_host_async(self._p, C.byref(opts) if opts is not None else None, f_pinned._p, u_pinned._p))
+
+    def copy_pair(self, dst_dev, src_pinned, src_dev, dst_pinned):
+        """host -> dst_dev and src_dev -> host concurrently (the copies of one pipelined e2e step, nothing else)"""
+        check(lib.tgpu_vec_transfer_pair(self._p, dst_dev._p, src_pinned._p, src_dev._p, dst_pinned._p))
 
     def vcycle_host_wait(self):
         check(lib.tgpu_vcycle_host_wait(self._p))

@@ -2097,6 +2097,9 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	if (opts) o = *opts;
 	else tgpu_cycle_opts_default(&o);
 	o.reserved_ = 0;
+	// With a shifted patch solver the sweep solves (A_p + lambda) u = ..., so the residual of the unshifted operator
+	// right after a sweep is no longer supported on the patch boundaries: the face-only residual schedule does not apply
+	if (h->lambda != 0.0 && o.fused == 1) o.fused = 2;
 	if (o.pre_sweeps < 0 || o.post_sweeps < 0 || o.coarse_sweeps < 0 || o.mid_sweeps < 0 || (o.cycle_type != 0 && o.cycle_type != 1)
 	    || (o.interpolator != 0 && o.interpolator != 1))
 		return fail(TGPU_ERR_ARG, "tgpu_vcycle: bad cycle options"); /* reference: throw 3, GMG/CycleFactory3d.cpp:131 */
@@ -2214,6 +2217,31 @@ extern "C" int tgpu_vcycle_host_async(tgpu_hier *h, const TgpuCycleOpts *opts, c
 	CU(cudaStreamWaitEvent(h->s_out, h->ev_cyc[k], 0));
 	CU(cudaMemcpyAsync(u_host, h->pipe_u[k]->d, bytes, cudaMemcpyDeviceToHost, h->s_out));
 	CU(cudaEventRecord(h->ev_out[k], h->s_out));
+	return TGPU_OK;
+	API_END
+}
+// The copies of one tgpu_vcycle_host_async step and nothing else: host -> dst_dev on the copy-in stream and src_dev -> host
+// on the copy-out stream at the same time, then both are waited for.  Measures what the host link gives the e2e path.
+extern "C" int tgpu_vec_transfer_pair(tgpu_hier *h, tgpu_vec *dst_dev, const double *src_pinned, const tgpu_vec *src_dev, double *dst_pinned)
+{
+	API_BEGIN
+	TRY(check_level_vec(h, 0, dst_dev, "tgpu_vec_transfer_pair"));
+	TRY(check_level_vec(h, 0, src_dev, "tgpu_vec_transfer_pair"));
+	if (!src_pinned || !dst_pinned) return fail(TGPU_ERR_ARG, "tgpu_vec_transfer_pair: null host buffer");
+	if (!h->s_in) {
+		CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+		for (int k = 0; k < 2; k++) {
+			CU(cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&h->ev_cyc[k], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming));
+		}
+	}
+	CU(cudaStreamSynchronize(h->ctx->stream));
+	CU(cudaMemcpyAsync(dst_dev->d, src_pinned, dst_dev->n * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
+	CU(cudaMemcpyAsync(dst_pinned, src_dev->d, src_dev->n * sizeof(double), cudaMemcpyDeviceToHost, h->s_out));
+	CU(cudaStreamSynchronize(h->s_in));
+	CU(cudaStreamSynchronize(h->s_out));
 	return TGPU_OK;
 	API_END
 }
