@@ -1,6 +1,9 @@
 // tgpu_plugin.hpp - C++ host side above the C ABI (tgpu.h), mirroring ThunderEgg's GMG plugin
 // surface class for class so that code written against the reference's interfaces (BiCGStab,
 // apps/*/steady.cpp, GMG::Cycle) can drive the B200 kernels unchanged apart from the namespace.
+// Interfaces and thin delegates only: no algorithm of the reference is restated here.  The adaptors that derive from the
+// reference's OWN headers (so that its unmodified GMG::VCycle / WCycle / BiCGStab templates run on the GPU) are in
+// include/tgpu_thunderegg.hpp.
 //
 //   reference (src/Thunderegg/...)                         here (namespace tgpu)
 //   Vector<D>                     Vector.h:179-322         Vector<D>  (same virtual ops)  -> DeviceVector<D>
@@ -9,12 +12,11 @@
 //   GMG::Smoother<D>              GMG/Smoother.h:39        GMG::Smoother<D>               -> DeviceSmoother<D>, DeviceJacobiSmoother<D>
 //   GMG::Restrictor<D>            GMG/Restrictor.h:39-40   GMG::Restrictor<D>             -> DeviceRestrictor<D>
 //   GMG::Interpolator<D>          GMG/Interpolator.h:39-40 GMG::Interpolator<D>           -> DeviceInterpolator<D>
-//   GMG::Level<D>                 GMG/Level.h:37-205       GMG::Level<D>
-//   GMG::Cycle/VCycle/WCycle<D>   GMG/Cycle.h, VCycle.h, WCycle.h   GMG::Cycle/VCycle/WCycle<D> (host recursion over Levels)
-//                                                          GMG::FusedCycle<D> (one tgpu_vcycle call, CUDA-graph replay)
+//   GMG::Cycle/VCycle/WCycle<D>   GMG/Cycle.h, VCycle.h, WCycle.h   GMG::FusedCycle<D> (one tgpu_vcycle call: fused schedule with
+//                                                          CUDA-graph replay, or the reference's call-by-call sequence)
 //   GMG::CycleOpts                GMG/CycleOpts.h:51-80    GMG::CycleOpts
 //   GMG::CycleFactory{2,3}d       GMG/CycleFactory3d.cpp:69-134     GMG::CycleFactory<D>::getCycle
-//   BiCGStab<D>::solve            BiCGStab.h:45-106        BiCGStab<D>::solve (same statement order)
+//   BiCGStab<D>::solve            BiCGStab.h:45-106        BiCGStab<D>::solve (same signature; delegates to tgpu_bicgstab)
 //   Tree<D> + ThundereggDomGen<D> OctTree.h, ThundereggDomGen.h     Mesh, Hierarchy (RAII over tgpu_mesh / tgpu_hier)
 //
 // Error behaviour: the reference throws an int (`throw 3;`) on type mismatches
@@ -22,7 +24,6 @@
 // tgpu::Error (std::runtime_error) carrying tgpu_last_error().
 #pragma once
 #include <cmath>
-#include <list>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -213,10 +214,9 @@ template <size_t D> class Operator
 // SchurDomainOp / DomainWrapOp (Operators/SchurDomainOp.h:51-54): b = A x on one level
 template <size_t D> class DeviceOperator : public Operator<D>
 {
+	public:
 	std::shared_ptr<Hierarchy> h;
 	int                        level;
-
-	public:
 	DeviceOperator(std::shared_ptr<Hierarchy> h, int level) : h(h), level(level) {}
 	void apply(std::shared_ptr<const Vector<D>> x, std::shared_ptr<Vector<D>> b) const override
 	{
@@ -307,145 +307,26 @@ template <size_t D> class DeviceInterpolator : public Interpolator<D>
 	}
 };
 
-// GMG/Level.h:37-205
-template <size_t D> class Level
-{
-	std::shared_ptr<VectorGenerator<D>> vg;
-	std::shared_ptr<Operator<D>>        op;
-	std::shared_ptr<Restrictor<D>>      restrictor;
-	std::shared_ptr<Interpolator<D>>    interpolator;
-	std::shared_ptr<Smoother<D>>        smoother;
-	std::shared_ptr<Level>              coarser;
-	std::weak_ptr<Level>                finer;
-
-	public:
-	explicit Level(std::shared_ptr<VectorGenerator<D>> vg) : vg(vg) {}
-	void setRestrictor(std::shared_ptr<Restrictor<D>> r) { restrictor = r; }
-	const Restrictor<D> &getRestrictor() const { return *restrictor; }
-	void setInterpolator(std::shared_ptr<Interpolator<D>> i) { interpolator = i; }
-	const Interpolator<D> &getInterpolator() const { return *interpolator; }
-	void setOperator(std::shared_ptr<Operator<D>> o) { op = o; }
-	const Operator<D> &getOperator() const { return *op; }
-	void setSmoother(std::shared_ptr<Smoother<D>> s) { smoother = s; }
-	const Smoother<D> &getSmoother() const { return *smoother; }
-	void setCoarser(std::shared_ptr<Level> c) { coarser = c; }
-	const Level &getCoarser() const { return *coarser; }
-	void setFiner(std::shared_ptr<Level> f) { finer = f; }
-	std::shared_ptr<VectorGenerator<D>> getVectorGenerator() const { return vg; }
-	bool finest() const { return finer.expired(); }
-	bool coarsest() const { return coarser == nullptr; }
-};
-
-// GMG/Cycle.h:34-126 - host recursion over Levels through the virtual plugin calls
-template <size_t D> class Cycle : public Operator<D>
-{
-	std::shared_ptr<Level<D>> finest_level;
-
-	protected:
-	using VecList      = std::list<std::shared_ptr<Vector<D>>>;
-	using ConstVecList = std::list<std::shared_ptr<const Vector<D>>>;
-	void prepCoarser(const Level<D> &level, VecList &u_vectors, ConstVecList &f_vectors) const
-	{
-		std::shared_ptr<Vector<D>> r = level.getVectorGenerator()->getNewVector();
-		level.getOperator().apply(u_vectors.front(), r);
-		r->scaleThenAdd(-1, f_vectors.front());
-		std::shared_ptr<Vector<D>> new_u = level.getCoarser().getVectorGenerator()->getNewVector();
-		std::shared_ptr<Vector<D>> new_f = level.getCoarser().getVectorGenerator()->getNewVector();
-		level.getRestrictor().restrict(new_f, r);
-		u_vectors.push_front(new_u);
-		f_vectors.push_front(new_f);
-	}
-	void prepFiner(const Level<D> &level, VecList &u_vectors, ConstVecList &f_vectors) const
-	{
-		std::shared_ptr<Vector<D>> old_u = u_vectors.front();
-		u_vectors.pop_front();
-		f_vectors.pop_front();
-		level.getInterpolator().interpolate(old_u, u_vectors.front());
-	}
-	void smooth(const Level<D> &level, VecList &u_vectors, ConstVecList &f_vectors) const
-	{
-		level.getSmoother().smooth(f_vectors.front(), u_vectors.front());
-	}
-	virtual void visit(const Level<D> &level, VecList &u_vectors, ConstVecList &f_vectors) const = 0;
-
-	public:
-	explicit Cycle(std::shared_ptr<Level<D>> finest_level) : finest_level(finest_level) {}
-	void apply(std::shared_ptr<const Vector<D>> f, std::shared_ptr<Vector<D>> u) const override
-	{
-		u->set(0);
-		VecList      u_vectors;
-		ConstVecList f_vectors;
-		f_vectors.push_back(f);
-		u_vectors.push_back(u);
-		visit(*finest_level, u_vectors, f_vectors);
-	}
-};
-template <size_t D> class VCycle : public Cycle<D> // GMG/VCycle.h:44-62
-{
-	int pre, post, coarse;
-	using typename Cycle<D>::VecList;
-	using typename Cycle<D>::ConstVecList;
-	void visit(const Level<D> &level, VecList &u, ConstVecList &f) const override
-	{
-		if (level.coarsest()) {
-			for (int i = 0; i < coarse; i++) this->smooth(level, u, f);
-		} else {
-			for (int i = 0; i < pre; i++) this->smooth(level, u, f);
-			this->prepCoarser(level, u, f);
-			this->visit(level.getCoarser(), u, f);
-			for (int i = 0; i < post; i++) this->smooth(level, u, f);
-		}
-		if (!level.finest()) this->prepFiner(level, u, f);
-	}
-
-	public:
-	VCycle(std::shared_ptr<Level<D>> finest, const CycleOpts &o)
-	: Cycle<D>(finest), pre(o.pre_sweeps), post(o.post_sweeps), coarse(o.coarse_sweeps)
-	{
-	}
-};
-template <size_t D> class WCycle : public Cycle<D> // GMG/WCycle.h:45-68
-{
-	int pre, post, mid, coarse;
-	using typename Cycle<D>::VecList;
-	using typename Cycle<D>::ConstVecList;
-	void visit(const Level<D> &level, VecList &u, ConstVecList &f) const override
-	{
-		if (level.coarsest()) {
-			for (int i = 0; i < coarse; i++) this->smooth(level, u, f);
-		} else {
-			for (int i = 0; i < pre; i++) this->smooth(level, u, f);
-			this->prepCoarser(level, u, f);
-			this->visit(level.getCoarser(), u, f);
-			for (int i = 0; i < mid; i++) this->smooth(level, u, f);
-			this->prepCoarser(level, u, f);
-			this->visit(level.getCoarser(), u, f);
-			for (int i = 0; i < post; i++) this->smooth(level, u, f);
-		}
-		if (!level.finest()) this->prepFiner(level, u, f);
-	}
-
-	public:
-	WCycle(std::shared_ptr<Level<D>> finest, const CycleOpts &o)
-	: Cycle<D>(finest), pre(o.pre_sweeps), post(o.post_sweeps), mid(o.mid_sweeps), coarse(o.coarse_sweeps)
-	{
-	}
-};
-// The whole cycle as one ABI call: fused kernel schedule + CUDA-graph replay (tgpu_vcycle).
-// Same result as VCycle/WCycle over the Device* plugins (tests/test_cpp_plugin).
+// GMG::Cycle<D> (GMG/Cycle.h:34,116-126, with VCycle.h:44-62 / WCycle.h:45-68) as ONE ABI call.  `granular = false`: the fused
+// kernel schedule with CUDA-graph replay; `granular = true`: the library replays the reference's sequence call by call
+// (zero fill, smooth, residual, restrict, ... one kernel launch per plugin call of the reference: TgpuCycleOpts.fused = 0).
+// The host recursion over Level objects itself is not restated here: where the reference's own GMG::VCycle / WCycle
+// classes should drive the kernels, include/tgpu_thunderegg.hpp derives adaptors from the reference's real headers.
 template <size_t D> class FusedCycle : public Operator<D>
 {
+	public:
 	std::shared_ptr<Hierarchy> h;
 	TgpuCycleOpts              o;
-
-	public:
-	FusedCycle(std::shared_ptr<Hierarchy> h, const CycleOpts &opts) : h(h)
+	FusedCycle(std::shared_ptr<Hierarchy> h, const CycleOpts &opts, bool granular = false) : h(h)
 	{
 		tgpu_cycle_opts_default(&o);
-		o.pre_sweeps    = opts.pre_sweeps;
-		o.post_sweeps   = opts.post_sweeps;
-		o.mid_sweeps    = opts.mid_sweeps;
-		o.coarse_sweeps = opts.coarse_sweeps;
+		o.max_levels       = opts.max_levels;
+		o.patches_per_proc = opts.patches_per_proc;
+		o.pre_sweeps       = opts.pre_sweeps;
+		o.post_sweeps      = opts.post_sweeps;
+		o.mid_sweeps       = opts.mid_sweeps;
+		o.coarse_sweeps    = opts.coarse_sweeps;
+		if (granular) o.fused = 0;
 		if (opts.cycle_type == "V") o.cycle_type = 0;
 		else if (opts.cycle_type == "W") o.cycle_type = 1;
 		else throw Error(TGPU_ERR_ARG, "unknown cycle type " + opts.cycle_type); // reference: throw 3
@@ -455,44 +336,24 @@ template <size_t D> class FusedCycle : public Operator<D>
 		check(tgpu_vcycle(h->p, &o, DeviceVector<D>::raw(f), DeviceVector<D>::raw(u)));
 	}
 };
-// GMG/CycleFactory3d.cpp:69-134: one Level per hierarchy level with operator, block-Jacobi
-// smoother, AvgRstr-type restrictor and DrctIntp-type interpolator, linked finest -> coarsest.
+// GMG::CycleFactory{2,3}d::getCycle (GMG/CycleFactory3d.cpp:69-134): the level list lives in the Hierarchy; max_levels and
+// patches_per_proc (:101-104) are honoured per cycle call by the library
 template <size_t D> struct CycleFactory {
-	static std::shared_ptr<Level<D>> buildLevels(std::shared_ptr<Hierarchy> h)
+	// the reference's call-by-call sequence (one kernel launch per Smoother / Operator / Restrictor / Interpolator call)
+	static std::shared_ptr<Operator<D>> getCycle(const CycleOpts &opts, std::shared_ptr<Hierarchy> h)
 	{
-		std::shared_ptr<Level<D>> finest, finer;
-		for (int l = 0; l < h->nlevels; l++) {
-			auto level = std::make_shared<Level<D>>(std::make_shared<DeviceVG<D>>(h, l));
-			level->setOperator(std::make_shared<DeviceOperator<D>>(h, l));
-			level->setSmoother(std::make_shared<DeviceSmoother<D>>(h, l));
-			if (finer) {
-				level->setFiner(finer);
-				finer->setCoarser(level);
-				finer->setRestrictor(std::make_shared<DeviceRestrictor<D>>(h, l - 1));
-				level->setInterpolator(std::make_shared<DeviceInterpolator<D>>(h, l - 1));
-			} else {
-				finest = level;
-			}
-			finer = level;
-		}
-		return finest;
-	}
-	// plugin-granular cycle (every step a virtual call, like the reference)
-	static std::shared_ptr<Cycle<D>> getCycle(const CycleOpts &opts, std::shared_ptr<Hierarchy> h)
-	{
-		auto finest = buildLevels(h);
-		if (opts.cycle_type == "V") return std::make_shared<VCycle<D>>(finest, opts);
-		if (opts.cycle_type == "W") return std::make_shared<WCycle<D>>(finest, opts);
-		throw Error(TGPU_ERR_ARG, "unknown cycle type " + opts.cycle_type);
+		return std::make_shared<FusedCycle<D>>(h, opts, true);
 	}
 	static std::shared_ptr<Operator<D>> getFusedCycle(const CycleOpts &opts, std::shared_ptr<Hierarchy> h)
 	{
-		return std::make_shared<FusedCycle<D>>(h, opts);
+		return std::make_shared<FusedCycle<D>>(h, opts, false);
 	}
 };
 } // namespace GMG
 
-// BiCGStab.h:45-106, statement for statement
+// BiCGStab<D>::solve (BiCGStab.h:45-106): same signature and meaning; the iteration itself runs inside the library
+// (tgpu_bicgstab: device-resident scalars, fused vector passes).  A must be the finest-level DeviceOperator, Mr a cycle
+// from GMG::CycleFactory or null.  (The reference's own BiCGStab template runs unchanged over include/tgpu_thunderegg.hpp.)
 template <size_t D> class BiCGStab
 {
 	public:
@@ -500,50 +361,17 @@ template <size_t D> class BiCGStab
 	                 std::shared_ptr<const Vector<D>> b, std::shared_ptr<const Operator<D>> Mr = nullptr, int max_it = 1000,
 	                 double tolerance = 1e-12)
 	{
-		std::shared_ptr<Vector<D>> resid = vg->getNewVector();
-		std::shared_ptr<Vector<D>> ms, mp;
+		(void) vg; // work vectors belong to the hierarchy
+		auto op = dynamic_cast<const DeviceOperator<D> *>(A.get());
+		if (op == nullptr || op->level != 0) throw Error(TGPU_ERR_ARG, "BiCGStab: A must be the finest-level DeviceOperator");
+		const GMG::FusedCycle<D> *cyc = nullptr;
 		if (Mr != nullptr) {
-			ms = vg->getNewVector();
-			mp = vg->getNewVector();
+			cyc = dynamic_cast<const GMG::FusedCycle<D> *>(Mr.get());
+			if (cyc == nullptr) throw Error(TGPU_ERR_ARG, "BiCGStab: Mr must come from GMG::CycleFactory");
 		}
-		A->apply(x, resid);
-		resid->scaleThenAdd(-1, b);
-		double                     r0_norm = resid->twoNorm();
-		std::shared_ptr<Vector<D>> rhat    = vg->getNewVector();
-		rhat->copy(resid);
-		std::shared_ptr<Vector<D>> p = vg->getNewVector();
-		p->copy(resid);
-		std::shared_ptr<Vector<D>> ap = vg->getNewVector(), as = vg->getNewVector(), s = vg->getNewVector();
-		double                     rho     = rhat->dot(resid);
-		int                        num_its = 0;
-		while (resid->twoNorm() / r0_norm > tolerance && num_its < max_it) {
-			if (Mr != nullptr) {
-				Mr->apply(p, mp);
-				A->apply(mp, ap);
-			} else {
-				A->apply(p, ap);
-			}
-			double alpha = rho / rhat->dot(ap);
-			s->copy(resid);
-			s->addScaled(-alpha, ap);
-			if (Mr != nullptr) {
-				Mr->apply(s, ms);
-				A->apply(ms, as);
-			} else {
-				A->apply(s, as);
-			}
-			double omega = as->dot(s) / as->dot(as);
-			if (Mr != nullptr) x->addScaled(alpha, mp, omega, ms);
-			else x->addScaled(alpha, p, omega, s);
-			resid->addScaled(-alpha, ap, -omega, as);
-			double rho_new = resid->dot(rhat);
-			double beta    = rho_new * alpha / (rho * omega);
-			p->addScaled(-omega, ap);
-			p->scaleThenAdd(beta, resid);
-			num_its++;
-			rho = rho_new;
-		}
-		return num_its;
+		int its = 0;
+		check(tgpu_bicgstab(op->h->p, cyc ? &cyc->o : nullptr, DeviceVector<D>::raw(b), DeviceVector<D>::raw(x), tolerance, max_it, &its, nullptr));
+		return its;
 	}
 };
 } // namespace tgpu

@@ -57,6 +57,88 @@ constexpr int TGPU_THREADS = 256;
 // completed and flushed.  Both are no-ops for launches without the programmatic-serialization attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v)
+{
+	asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p)
+{
+	uint64_t v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo hand-over inside the compute kernels (multi-GPU, peer-to-peer exchange; protocol: tgpu.cu, "peer-to-peer halo
+// exchange").  A kernel that consumes halo faces is launched over ALL owned patches of the level - interior patches
+// first - and every CTA polls the peers' DATA flags itself right before the first patch that needs them (patch index >=
+// first_halo_patch), so the patches without off-rank neighbours are swept while the faces are still in flight and no
+// separate wait / signal launches (and no second, short launch for the boundary patches) are needed.  The last CTA to
+// finish advances the generation counter and acknowledges the halo to the peers (ACK flags).
+// cnt[]: 0 data sent, 1 data awaited, 2 ack sent, 3 ack awaited (generation counters of the level, device memory).
+// ---------------------------------------------------------------------------------------------
+struct HaloSync {
+	const uint64_t *  data_flags    = nullptr; // my DATA flag row [nranks], written by the peers
+	const int32_t *   peer_rank     = nullptr; // [npeers]
+	uint64_t *const * peer_ack_flag = nullptr; // [npeers] my entry of each peer's ACK row
+	uint64_t *        cnt           = nullptr;
+	unsigned *        ticket        = nullptr; // CTAs that have finished
+	int *             abort         = nullptr; // device flag: a wait of this hierarchy timed out
+	int *             host_err      = nullptr; // mapped host flag (rank + 1 that was waited for)
+	int               npeers           = 0;
+	int               first_halo_patch = 0;
+	int               enabled          = 0;
+};
+// one thread: wait until every peer's faces of the generation after "data awaited" have landed (bounded, see
+// p2p_wait_kernel).  The counter is only advanced by the last CTA to finish (halo_finish), i.e. after every CTA has polled.
+// (scalar arguments: a struct reference would put a copy of HaloSync on every caller's stack)
+__device__ __noinline__ void halo_poll(const uint64_t *data_flags, const int32_t *peer_rank, int npeers, const uint64_t *cnt, int *abort, int *host_err)
+{
+	if (*abort) return;
+	const uint64_t expected = cnt[1] + 1;
+	for (int k = 0; k < npeers; k++) {
+		const uint64_t *f = data_flags + peer_rank[k];
+		unsigned long long t0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		while (ld_acquire_sys(f) < expected) {
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > 20000000000ull) { // 20 s
+				atomicExch(abort, 1);
+				*(volatile int *) host_err = peer_rank[k] + 1;
+				__threadfence_system();
+				return;
+			}
+			__nanosleep(100);
+		}
+	}
+}
+// CTA-wide (every thread calls; ends with a barrier): make the halo of this level visible before patch p is gathered
+__device__ __forceinline__ void halo_wait_cta(const HaloSync &hs, int p, bool &waited)
+{
+	if (!hs.enabled || waited || p < hs.first_halo_patch) return; // CTA-uniform
+	if (threadIdx.x == 0) halo_poll(hs.data_flags, hs.peer_rank, hs.npeers, hs.cnt, hs.abort, hs.host_err);
+	__syncthreads();
+	waited = true;
+}
+// end of the kernel (every thread calls): the last CTA advances "data awaited" and acknowledges the halo to the peers
+__device__ __forceinline__ void halo_finish(const HaloSync &hs)
+{
+	if (!hs.enabled) return;
+	__syncthreads();
+	if (threadIdx.x != 0) return;
+	__threadfence();
+	const unsigned done = atomicAdd(hs.ticket, 1u);
+	if (done != gridDim.x * gridDim.y - 1) return;
+	__threadfence();
+	*hs.ticket = 0;
+	if (*hs.abort) return; // the protocol stays where it broke
+	hs.cnt[1] += 1;
+	const uint64_t v = hs.cnt[2] + 1;
+	__threadfence_system();
+	for (int k = 0; k < hs.npeers; k++) st_release_sys(hs.peer_ack_flag[k], v);
+	hs.cnt[2] = v;
+}
 // resident smoother CTAs per SM the register budget is tuned for (N = 32 pencils need > 128 registers)
 #ifndef SMOOTH_BLOCKS_16
 #define SMOOTH_BLOCKS_16 3
@@ -1044,15 +1126,17 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
 template <bool DIFF>
 __global__ void __launch_bounds__(TGPU_THREADS, FRR16_MINB)
 face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
-                                const double *__restrict__ Fold, double *__restrict__ coarse)
+                                const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
 {
 	using G = Geo<3, 16>;
 	pdl_launch_dependents();
 	pdl_wait();
 	__shared__ __align__(16) double R[G::S][G::M]; // fast path uses the first 6 x 64 entries as Rc[s][c]
-	const int t = threadIdx.x;
+	const int      t        = threadIdx.x;
+	bool           halo_ok  = false;
 	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
 		const int        p  = p0 + g;
+		halo_wait_cta(hs, p, halo_ok);
 		const PatchMeta &pm = meta[p];
 		bool             fast = pm.orth_on_parent >= 0;
 #pragma unroll
@@ -1108,6 +1192,7 @@ face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int 
 		}
 		__syncthreads();
 	}
+	halo_finish(hs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1318,15 +1403,50 @@ __global__ void unpack_faces_kernel(int nfaces, const int32_t *__restrict__ slot
 // release/acquire on per-peer generation counters.  Replaces pack + ncclSend/ncclRecv + unpack
 // (and with it the reference's interface VecScatters, SchurHelper.h:123-150).
 // ---------------------------------------------------------------------------------------------
+// hand-over state of a push (see HaloSync for the consumer side): ACK flags to wait for before the peers' halo slots may be
+// overwritten, DATA flags to publish afterwards
+struct PushSync {
+	const uint64_t *  ack_flags      = nullptr; // my ACK flag row [nranks], written by the peers
+	const int32_t *   peer_rank      = nullptr; // [npeers]
+	uint64_t *const * peer_data_flag = nullptr; // [npeers] my entry of each peer's DATA row
+	uint64_t *        cnt            = nullptr; // generation counters of the level (HaloSync)
+	unsigned *        ticket         = nullptr;
+	int *             abort          = nullptr;
+	int *             host_err       = nullptr;
+	int               npeers         = 0;
+	int               enabled        = 0;       // 0: plain push (separate wait / signal kernels around it)
+};
 template <int D, int N, bool PROLONG>
 __global__ void push_faces_kernel(const PatchMeta *__restrict__ meta, int nfaces, const int32_t *__restrict__ patch,
                                   const int32_t *__restrict__ side, const int32_t *__restrict__ peer_of,
                                   const int32_t *__restrict__ ridx, const double *__restrict__ F, const double *__restrict__ uc,
-                                  double *const *__restrict__ peerF)
+                                  double *const *__restrict__ peerF, PushSync ps = PushSync{})
 {
 	pdl_launch_dependents();
 	pdl_wait();
 	using G            = Geo<D, N>;
+	if (ps.enabled) { // the peers must have consumed the previous generation of my faces (ACK) before their slots are rewritten
+		if (threadIdx.x == 0 && !*ps.abort) {
+			const uint64_t expected = ps.cnt[3];
+			for (int k = 0; k < ps.npeers; k++) {
+				const uint64_t *f = ps.ack_flags + ps.peer_rank[k];
+				unsigned long long t0;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+				while (ld_acquire_sys(f) < expected) {
+					unsigned long long t1;
+					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+					if (t1 - t0 > 20000000000ull) { // 20 s
+						atomicExch(ps.abort, 1);
+						*(volatile int *) ps.host_err = ps.peer_rank[k] + 1;
+						__threadfence_system();
+						break;
+					}
+					__nanosleep(100);
+				}
+			}
+		}
+		__syncthreads();
+	}
 	const size_t total = (size_t) nfaces * G::M;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
 		const int m = (int) (i % G::M), k = (int) (i / G::M);
@@ -1339,16 +1459,22 @@ __global__ void push_faces_kernel(const PatchMeta *__restrict__ meta, int nfaces
 		}
 		peerF[peer_of[k]][(size_t) ridx[k] * G::M + m] = v;
 	}
-}
-__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v)
-{
-	asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p)
-{
-	uint64_t v;
-	asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
-	return v;
+	if (ps.enabled) { // the last block publishes the faces: DATA generation + 1 in every peer's flag row
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence_system();
+			if (atomicAdd(ps.ticket, 1u) == gridDim.x - 1) {
+				__threadfence_system();
+				*ps.ticket = 0;
+				if (!*ps.abort) {
+					ps.cnt[3] += 1;
+					const uint64_t v = ps.cnt[0] + 1;
+					for (int k = 0; k < ps.npeers; k++) st_release_sys(ps.peer_data_flag[k], v);
+					ps.cnt[0] = v;
+				}
+			}
+		}
+	}
 }
 // generation = ++counter; every peer's flag (in the peer's memory) is set to it.  Runs after the kernels
 // whose stores it publishes (stream order), so their peer writes have been performed.
@@ -1761,4 +1887,5 @@ __global__ void patch_integrals_kernel(int P, const double *__restrict__ spacing
 } // namespace tgpu
 #include "smooth3d16.cuh"
 #include "patch3d32.cuh"
+#include "apply_tma.cuh"
 #include "smooth2d32.cuh"

@@ -202,7 +202,17 @@ smooth3d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 // ---------------------------------------------------------------------------------------------
 constexpr int    C32_THREADS = 512, C32_ROW = 34, C32_PL = 32 * C32_ROW, C32_TILE = 16 * C32_PL;
 // tile + two exchange planes (double buffered) + z-face interface values + per-warp x/y-face values + x-face output staging
+#ifndef C32_ZREG
+#define C32_ZREG 0 // 1: z pencils stay in registers across the cluster barrier instead of a store / reload of the eliminated planes
+                   // (measured on 4096 patches: -3 % on the variants without gathers, +9 % (spills) on the two the fused cycle uses)
+#endif
+#ifndef C32_FACETAIL
+#define C32_FACETAIL 1 // faces-only sweeps from a zero guess: dot products + 60 one-dimensional transforms instead of full inverse transforms
+#endif
+constexpr int    C32_FV = 65; // row pitch of the face-vector staging [32][65] (faces-only sweeps, see the tail of the kernel)
+// (188 KB: the next shared-memory carve-out step, 228 KB, would leave the L1 28 KB instead of 60 KB - measured 4-7 % slower)
 constexpr size_t smooth3d32c_smem_bytes() { return sizeof(double) * (C32_TILE + 2 * 1024 + 1024 + 16 * 128 + 16 * 64); }
+static_assert(32 * C32_FV <= 1024 + 16 * 128, "the face-vector staging aliases the interface-value buffers of sweeps from a zero guess");
 __device__ __forceinline__ unsigned cluster_ctarank()
 {
 	unsigned r;
@@ -269,7 +279,7 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C32_THREADS, 1)
 smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                    const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
-                   const double *__restrict__ uc)
+                   const double *__restrict__ uc, HaloSync hs = HaloSync{})
 {
 	constexpr int N = 32, ROW = C32_ROW, PL = C32_PL, M = N * N, NC = N * N * N;
 	extern __shared__ __align__(16) double S[];
@@ -277,6 +287,8 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 	double *       GZ   = X + 2 * M;     // [M] (2/h^2) gamma on this half's z face
 	double *       GXY  = GZ + M;        // [16 warps][4][32] x- and y-face values of a plane
 	double *       EX   = GXY + 16 * 128; // [16 warps][2][32] staging of the new x-face slices
+	double *       FV   = GZ;             // [32][C32_FV] faces-only sweeps from a zero guess (GZ and GXY are unused there): partially
+	                                      // transformed face vectors, entry j of vector i at j * C32_FV + i
 	const int      t = threadIdx.x, lane = t & 31, w = t >> 5;
 	const unsigned rank = cluster_ctarank();
 	const int      z    = rank == 0 ? w : N - 1 - w; // plane of the patch behind local plane w
@@ -289,8 +301,11 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 	pdl_launch_dependents();
 	pdl_wait();
 	int g = blockIdx.x / 2;
+	// multi-GPU: each CTA polls the peers' flags itself before the first patch whose gamma needs halo faces (HaloSync)
+	bool halo_ok = false;
 	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
 		const int    p    = p0 + g;
+		halo_wait_cta(hs, p, halo_ok);
 		const double cfac = 2.0 * meta[p].inv_h2;
 #pragma unroll
 		for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = cfac * gamma_entry32<PROLONG>(meta, p, s, mf, Fin, uc);
@@ -345,6 +360,7 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
 		}
 		__syncthreads();
+		if (!ZERO_GUESS && next) halo_wait_cta(hs, pn, halo_ok); // gamma of patch pn is gathered from here on
 		// z: elimination step j on local plane j, in place; pencils (k_x, k_y) = (lane, w) and (lane, w + 16).
 		// The interface values of the NEXT patch are gathered around this phase (the transform registers are free here).
 		// (two batches of three: loads issued before the elimination / the back substitution, combined after it)
@@ -358,10 +374,13 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 		}
 		const double hs = h2 * (4.0 / (N * N));
 		double *     Xo = X + (it & 1) * M;
+#if C32_ZREG
+		double       rz[2][16]; // the two pencils stay in registers across the cluster barrier (no store / reload of the eliminated planes)
+#endif
 #pragma unroll
 		for (int q = 0; q < 2; q++) {
 			const int     ky = w + 16 * q;
-			double *      zp = S + ky * ROW + lane;
+			const double *zp = S + ky * ROW + lane;
 			const double *tb = tri + ky * N + lane;
 			double        rho = 0.0;
 #pragma unroll
@@ -369,7 +388,11 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 				const double a = __ldg(tb + j * M);
 				const double r = zp[j * PL] * (hs * a);
 				rho            = (j == 0) ? r : fma(-a, rho, r);
-				zp[j * PL]     = rho;
+#if C32_ZREG
+				rz[q][j]       = rho;
+#else
+				const_cast<double *>(zp)[j * PL] = rho;
+#endif
 			}
 			Xo[ky * N + lane] = rho;
 		}
@@ -388,11 +411,19 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			double *      zp = S + ky * ROW + lane;
 			const double *tb = tri + ky * N + lane;
 			const double  a15 = __ldg(tb + 15 * M), kap = __ldg(tb + 16 * M);
+#if C32_ZREG
+			double        y   = kap * fma(-a15, ld_dsmem(Xo + ky * N + lane, rank ^ 1), rz[q][15]);
+#else
 			double        y   = kap * fma(-a15, ld_dsmem(Xo + ky * N + lane, rank ^ 1), zp[15 * PL]);
+#endif
 			zp[15 * PL]       = y;
 #pragma unroll
 			for (int j = 14; j >= 0; j--) {
+#if C32_ZREG
+				y          = fma(-__ldg(tb + j * M), y, rz[q][j]);
+#else
 				y          = fma(-__ldg(tb + j * M), y, zp[j * PL]);
+#endif
 				zp[j * PL] = y;
 			}
 		}
@@ -402,51 +433,95 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			GZ[t + 512]    = gm[2].finish(meta, pn, sz, t + 512, Fin, uc, cfn);
 		}
 		__syncthreads();
-		{ // x inverse
+		constexpr bool FACE_TAIL = C32_FACETAIL && ZERO_GUESS && !WRITE_U;
+		if (!FACE_TAIL || w == 0) {
+			// full inverse transforms: every plane of a sweep that writes u; in a faces-only sweep only the plane that is
+			// this half's z face (local plane 0)
+			{ // x inverse
 #pragma unroll
-			for (int j = 0; j < N / 2; j++) {
+				for (int j = 0; j < N / 2; j++) {
+					const double2 d = rowp[j];
+					v[2 * j]        = d.x;
+					v[2 * j + 1]    = d.y;
+				}
+				Dst3<N, N>::run(v, mg);
+#pragma unroll
+				for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			}
+			__syncwarp();
+			{ // y inverse: pencil (x, z) = (lane, z), straight to memory
+				const double *col = S + w * PL + lane;
+#pragma unroll
+				for (int k = 0; k < N; k++) v[k] = col[k * ROW];
+				Dst3<N, N>::run(v, mg);
+				if (WRITE_U) {
+					double *up = u + (size_t) p * NC + (size_t) z * M + lane;
+#pragma unroll
+					for (int k = 0; k < N; k++) __stcs(up + k * N, v[k]);
+				}
+				if (EMIT) {
+					double *Fp = Fout + (size_t) p * 6 * M;
+					Fp[2 * M + mf] = v[0]; // y faces: entry (x, z)
+					Fp[3 * M + mf] = v[N - 1];
+					if (w == 0) { // z face of this half: entries (x, y)
+						double *Fz = Fp + sz * M + lane;
+#pragma unroll
+						for (int k = 0; k < N; k++) Fz[N * k] = v[k];
+					}
+					double *ex = EX + w * 64;
+					if (lane == 0 || lane == N - 1) { // x faces: entries (y, z), held by lanes 0 and 31
+						double *q = ex + (lane ? 32 : 0);
+#pragma unroll
+						for (int k = 0; k < N; k++) q[k] = v[k];
+					}
+					__syncwarp();
+					Fp[0 * M + mf] = ex[lane];
+					Fp[1 * M + mf] = ex[32 + lane];
+				}
+			}
+		} else {
+			// Faces-only sweep, planes other than the z face: only u(0 | 31, y, z) and u(x, 0 | 31, z) are wanted.  With
+			// T = the DST-III matrix (DftPatchSolver.h:269-281), T[0][j] = sin(pi (j+1) / 2n), T[0][n-1] = 1/2 and
+			// T[n-1][j] = (-1)^j T[0][j], contract the axis normal to the face first - two dot products per row / column of
+			// the plane instead of a transform - and leave the 4 x 15 remaining 1-D transforms of the CTA to two warps.
+			double E = 0.0, O = 0.0;
+#pragma unroll
+			for (int j = 0; j < N / 2; j++) { // row (k_y, plane) = (lane, w): contract k_x
 				const double2 d = rowp[j];
-				v[2 * j]        = d.x;
-				v[2 * j + 1]    = d.y;
+				E               = fma(mg.sinq(2 * j + 1), d.x, E);
+				O               = fma((2 * j + 1 == N - 1) ? 0.5 : mg.sinq(2 * j + 2), d.y, O);
 			}
-			Dst3<N, N>::run(v, mg);
+			const int vi = 4 * (w - 1); // vectors 4 (w - 1) + {0: x = 0, 1: x = 31, 2: y = 0, 3: y = 31}, entry index = lane
+			FV[lane * C32_FV + vi]     = E + O;
+			FV[lane * C32_FV + vi + 1] = E - O;
+			const double *col = S + w * PL + lane; // column (k_x, plane) = (lane, w): contract k_y
+			E = O = 0.0;
 #pragma unroll
-			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			for (int k = 0; k < N; k += 2) {
+				E = fma(mg.sinq(k + 1), col[k * ROW], E);
+				O = fma((k + 1 == N - 1) ? 0.5 : mg.sinq(k + 2), col[(k + 1) * ROW], O);
+			}
+			FV[lane * C32_FV + vi + 2] = E + O;
+			FV[lane * C32_FV + vi + 3] = E - O;
 		}
-		__syncwarp();
-		{ // y inverse: pencil (x, z) = (lane, z), straight to memory
-			const double *col = S + w * PL + lane;
+		if (FACE_TAIL) {
+			__syncthreads();
+			const int vec = (w - 1) * 32 + lane; // warps 1 and 2: one face vector per lane
+			if ((w == 1 || w == 2) && vec < 60) {
 #pragma unroll
-			for (int k = 0; k < N; k++) v[k] = col[k * ROW];
-			Dst3<N, N>::run(v, mg);
-			if (WRITE_U) {
-				double *up = u + (size_t) p * NC + (size_t) z * M + lane;
+				for (int j = 0; j < N; j++) v[j] = FV[j * C32_FV + vec];
+				Dst3<N, N>::run(v, mg);
+				const int lp = 1 + (vec >> 2), kind = vec & 3;             // local plane, which face
+				const int zz = rank == 0 ? lp : N - 1 - lp;
+				double *  Fq = Fout + (size_t) p * 6 * M + kind * M + N * zz; // x faces: entries (y, z); y faces: entries (x, z)
 #pragma unroll
-				for (int k = 0; k < N; k++) __stcs(up + k * N, v[k]);
-			}
-			if (EMIT) {
-				double *Fp = Fout + (size_t) p * 6 * M;
-				Fp[2 * M + mf] = v[0]; // y faces: entry (x, z)
-				Fp[3 * M + mf] = v[N - 1];
-				if (w == 0) { // z face of this half: entries (x, y)
-					double *Fz = Fp + sz * M + lane;
-#pragma unroll
-					for (int k = 0; k < N; k++) Fz[N * k] = v[k];
-				}
-				double *ex = EX + w * 64;
-				if (lane == 0 || lane == N - 1) { // x faces: entries (y, z), held by lanes 0 and 31
-					double *q = ex + (lane ? 32 : 0);
-#pragma unroll
-					for (int k = 0; k < N; k++) q[k] = v[k];
-				}
-				__syncwarp();
-				Fp[0 * M + mf] = ex[lane];
-				Fp[1 * M + mf] = ex[32 + lane];
+				for (int j = 0; j < N / 2; j++) *reinterpret_cast<double2 *>(Fq + 2 * j) = make_double2(v[2 * j], v[2 * j + 1]);
 			}
 		}
 		__syncwarp();
 	}
 	cluster_sync_all(); // a CTA must not exit while its peer may still read its exchange plane
+	if (!ZERO_GUESS) halo_finish(hs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -619,7 +694,7 @@ apply3d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double
 template <int D, int N, bool DIFF>
 __global__ void __launch_bounds__(TGPU_THREADS)
 face_residual_restrict_big_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
-                                  const double *__restrict__ Fold, double *__restrict__ coarse)
+                                  const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
 {
 	using G         = Geo<D, N>;
 	constexpr int H = N / 2, M = G::M;
@@ -627,8 +702,10 @@ face_residual_restrict_big_kernel(const PatchMeta *__restrict__ meta, int p0, in
 	const int t = threadIdx.x;
 	pdl_launch_dependents();
 	pdl_wait();
+	bool halo_ok = false;
 	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
 		const int        p      = p0 + g;
+		halo_wait_cta(hs, p, halo_ok);
 		const PatchMeta &pm     = meta[p];
 		const int        orth   = pm.orth_on_parent;
 		const double     cfac   = 2.0 * pm.inv_h2;
@@ -689,5 +766,6 @@ face_residual_restrict_big_kernel(const PatchMeta *__restrict__ meta, int p0, in
 		}
 		__syncthreads();
 	}
+	halo_finish(hs);
 }
 } // namespace tgpu

@@ -242,7 +242,7 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE 
 __global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE))
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{})
+                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{})
 {
 	constexpr int N = 16, ROW = S16_ROW, PL = S16_PL;
 	using G = Geo<3, 16>;
@@ -271,13 +271,19 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	};
 
 	int g = blockIdx.x;
-	if (g >= npatch) return;
+	// multi-GPU: the CTA polls the peers' flags itself before the first patch whose gamma needs halo faces (HaloSync)
+	bool halo_ok = false;
+	if (g >= npatch) {
+		if (!ZERO_GUESS) halo_finish(hs);
+		return;
+	}
 	constexpr bool DIRECT = s16_direct(ZERO_GUESS, SRC_FINE); // f goes straight from memory into the z pencils, one tile
 	double gz0 = 0.0, gz1 = 0.0; // (2/h^2) gamma of entry t on the two z faces of the current patch
 	SideGamma16<PROLONG> sg;
 	if (!ZERO_GUESS) {
 		// first patch of this CTA: nothing to hide the gathers behind
 		const int p = p0 + g;
+		halo_wait_cta(hs, p, halo_ok);
 		describe(meta[p], p, 0);
 		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
 		__syncthreads();
@@ -308,6 +314,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			// the previous patch's last stage has read the tile; Gs and the descriptors written during the
 			// previous iteration become visible
 			__syncthreads();
+			if (!ZERO_GUESS && next) halo_wait_cta(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
 			h2 = ZERO_GUESS ? meta[p].h2 : GD[b].h2;
 			// table entry of the patch after the next -> metaS (read by describe() after the next barrier but one)
 			if (!ZERO_GUESS && t < MW && gn + (int) gridDim.x < npatch)
@@ -513,5 +520,6 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			Gs[768 + t] = sg.finish(gp, 3, meta, pn, t, Fin, uc);
 		}
 	}
+	if (!ZERO_GUESS) halo_finish(hs);
 }
 } // namespace tgpu

@@ -208,6 +208,7 @@ struct LevelDev {
 	uint64_t **peer_data_flag = nullptr, **peer_ack_flag = nullptr; // device [npeers]: my entry of the peers' flag rows
 	uint64_t * data_flags = nullptr, *ack_flags = nullptr;       // my flag rows [nranks] (in the arena, written by peers)
 	uint64_t * cnt = nullptr;                                    // generation counters: data sent / awaited, ack sent / awaited
+	unsigned * tickets = nullptr;                                // [2] finished-CTA counters of the fused push / consumer kernels
 };
 
 struct GraphEntry {
@@ -404,6 +405,9 @@ static int setup_3d32(tgpu_hier *h)
 	TRY((set_smem_attr_3d32<false, true, true, false>()));
 	CU(cudaFuncSetAttribute(apply3d32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
 	CU(cudaFuncSetAttribute(apply3d32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(apply3d32_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_tma_smem_bytes()));
+	CU(cudaFuncSetAttribute(apply3d32_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_tma_smem_bytes()));
+	CU(cudaFuncSetAttribute(apply3d32_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_tma_smem_bytes()));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	for (const LevelDev &L : h->levels)
@@ -423,6 +427,10 @@ template <int D, int N> static int set_smem_attrs()
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
 	CU(cudaFuncSetAttribute(apply_kernel<D, N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_tma_kernel<D, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_tma_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_tma_kernel<D, N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_tma_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_tma_kernel<D, N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_tma_smem_bytes<D, N>()));
+	CU(cudaFuncSetAttribute(apply_tma_kernel<D, N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply_tma_smem_bytes<D, N>()));
 	return TGPU_OK;
 }
 
@@ -1081,6 +1089,8 @@ static int setup_p2p(tgpu_hier *h, const Partition &pt)
 		L.ack_flags  = (uint64_t *) ((char *) h->arena + mine.flags_off) + ((size_t) l * 2 + 1) * nr;
 		CU(cudaMalloc(&L.cnt, 4 * sizeof(uint64_t)));
 		CU(cudaMemset(L.cnt, 0, 4 * sizeof(uint64_t)));
+		CU(cudaMalloc(&L.tickets, 2 * sizeof(unsigned)));
+		CU(cudaMemset(L.tickets, 0, 2 * sizeof(unsigned)));
 		const int np = (int) L.peers.size();
 		// my halo slots as the peers see them: they send (slot, side) lists in the agreed order
 		int32_t *d_rslot = nullptr;
@@ -1235,6 +1245,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.peer_data_flag);
 		cudaFree(L.peer_ack_flag);
 		cudaFree(L.cnt);
+		cudaFree(L.tickets);
 		for (int e = 0; e < 4; e++)
 			if (L.ev[e]) cudaEventDestroy(L.ev[e]);
 		cudaFree(L.send_patch);
@@ -1492,6 +1503,29 @@ static int need_smoother(const tgpu_hier *h, int level)
 	return TGPU_OK;
 }
 
+// consumer side of the hand-over for kernels that poll the DATA flags themselves and acknowledge from their last CTA
+static bool halo_in_kernel(const tgpu_hier *h, int l)
+{
+	static const bool off = getenv("TGPU_HALO_IN_KERNEL") && atoi(getenv("TGPU_HALO_IN_KERNEL")) == 0;
+	const LevelDev &  L   = h->levels[l];
+	return !off && L.p2p && h->D == 3 && (h->N == 16 || h->N == 32) && !h->generic_kernels && !L.has_neumann && h->lambda == 0.0;
+}
+static HaloSync halo_sync(tgpu_hier *h, int l)
+{
+	LevelDev &L = h->levels[l];
+	HaloSync  hs;
+	hs.data_flags       = L.data_flags;
+	hs.peer_rank        = L.peer_rank;
+	hs.peer_ack_flag    = L.peer_ack_flag;
+	hs.cnt              = L.cnt;
+	hs.ticket           = L.tickets + 1;
+	hs.abort            = h->p2p_abort;
+	hs.host_err         = (int *) h->ctx->p2p_err;
+	hs.npeers           = (int) L.peers.size();
+	hs.first_halo_patch = L.n_interior;
+	hs.enabled          = 1;
+	return hs;
+}
 static int k_extract_faces(tgpu_hier *h, int l, const double *u, double *F)
 {
 	LevelDev &L = h->levels[l];
@@ -1499,13 +1533,51 @@ static int k_extract_faces(tgpu_hier *h, int l, const double *u, double *F)
 	DISPATCH_DN_ALL(h->D, h->N, return launch(h->ctx, extract_faces_kernel<DD, NN>, dim3(grid_for(h->ctx, L.nface)), dim3(256), 0, L.P, u, F));
 }
 // mode 0: out = A u; 1: out = f - A u; 2: coarse = R (f - A u).  F must hold the faces of u.
+// mode 3 (TMA kernels only, see apply_tma_available): out = A u with the block partial sums of out . f and out . out written to
+// ctx->d_partial ([0..nb), [MAX_PARTIAL / 2 ..)); *nb_out = number of partials
+static bool apply_tma_available()
+{
+	// TGPU_APPLY_TMA=0: the tile is staged with per-element cp.async (LDGSTS) into a ghosted tile (apply_kernel /
+	// apply3d32_kernel) instead of one TMA bulk copy per patch group (apply_tma.cuh)
+	static const bool tma = !(getenv("TGPU_APPLY_TMA") && atoi(getenv("TGPU_APPLY_TMA")) == 0);
+	return tma;
+}
 static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double *f, const double *F, double *out, double *coarse,
-                   int p0 = 0, int p1 = -1)
+                   int p0 = 0, int p1 = -1, int *nb_out = nullptr)
 {
 	LevelDev &L = h->levels[l];
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return TGPU_OK;
-	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : "residual_restrict"), l);
+	Tag       tg(h->ctx, mode == 0 ? "apply" : (mode == 1 ? "residual" : (mode == 2 ? "residual_restrict" : "apply_dots")), l);
+	const bool tma = apply_tma_available();
+	if (mode == 3 && !tma) return fail(TGPU_ERR_ARG, "k_apply: the fused dot products need the TMA kernels");
+	double *const  part    = h->ctx->d_partial;
+	constexpr int  pstride = MAX_PARTIAL / 2;
+	if (tma && is_3d32(h)) {
+		if (mode == 2) {
+			if (p0 != 0 || p1 != L.P) return fail(TGPU_ERR_UNSUPPORTED, "residual+restrict on a patch range is not available for 32^3 patches");
+			TRY(launch(h->ctx, apply3d32_tma_kernel<1>, dim3(std::min((p1 - p0) * 4, h->ctx->sm_count * 2)), dim3(TGPU_THREADS), apply3d32_tma_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, L.r, part, pstride));
+			return launch(h->ctx, restrict_kernel<3, 32>, dim3(grid_for(h->ctx, L.ncells)), dim3(256), 0, (const PatchMeta *) L.meta, L.P, (const double *) L.r, coarse);
+		}
+		const dim3 grid(std::min((p1 - p0) * 4, h->ctx->sm_count * 2));
+		if (nb_out) *nb_out = (int) grid.x;
+		if (mode == 0) return launch(h->ctx, apply3d32_tma_kernel<0>, grid, dim3(TGPU_THREADS), apply3d32_tma_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, out, part, pstride);
+		if (mode == 3) return launch(h->ctx, apply3d32_tma_kernel<3>, grid, dim3(TGPU_THREADS), apply3d32_tma_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, out, part, pstride);
+		return launch(h->ctx, apply3d32_tma_kernel<1>, grid, dim3(TGPU_THREADS), apply3d32_tma_smem_bytes(), (const PatchMeta *) L.meta, p0, p1, u, f, F, out, part, pstride);
+	}
+	if (tma && !is_3d32(h)) {
+		DISPATCH_DN(h->D, h->N, {
+			using G        = Geo<DD, NN>;
+			const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
+			const int grid = std::min(nblk, h->ctx->sm_count * 2);
+			const size_t sm = apply_tma_smem_bytes<DD, NN>();
+			if (nb_out) *nb_out = grid;
+			if (mode == 0) return launch(h->ctx, apply_tma_kernel<DD, NN, 0>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse, part, pstride);
+			if (mode == 1) return launch(h->ctx, apply_tma_kernel<DD, NN, 1>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse, part, pstride);
+			if (mode == 3) return launch(h->ctx, apply_tma_kernel<DD, NN, 3>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse, part, pstride);
+			return launch(h->ctx, apply_tma_kernel<DD, NN, 2>, dim3(grid), dim3(TGPU_THREADS), sm, (const PatchMeta *) L.meta, p0, p1, u, f, F, out, coarse, part, pstride);
+		});
+	}
 	if (is_3d32(h)) {
 		if (mode == 2) { // no fused form for 32^3 patches: residual into the level's work vector, then restrict
 			if (p0 != 0 || p1 != L.P) return fail(TGPU_ERR_UNSUPPORTED, "residual+restrict on a patch range is not available for 32^3 patches");
@@ -1531,11 +1603,11 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 // write_u = false (needs emit): only the faces of the new u are wanted (the generic kernel still writes u)
 template <bool Z, bool E, bool PR, bool W, bool SF = false>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
-                             const double *uc, FineSrc16 src = FineSrc16{})
+                             const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{})
 {
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * s16_ctas_per_sm(Z, SF))), block(S16_BLOCK);
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
-	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src);
+	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs);
 }
 // can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?
 // Opt-in (TGPU_FINE_SOURCE=1): measured on config B the assembly stage's dependent gathers (children -> neighbour
@@ -1547,9 +1619,14 @@ static bool can_source_from_fine(const tgpu_hier *h, int lc)
 	return enabled && lc >= 1 && h->D == 3 && h->N == 16 && !h->generic_kernels && h->ctx->nranks == 1 && h->levels[lc].children
 	       && !h->levels[lc].has_neumann;
 }
+// hsp != nullptr (multi-GPU, kernels that support it: halo_in_kernel): the launch covers interior and boundary patches and
+// does the halo hand-over itself
 static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const double *f, double *u, const double *Fin, double *Fout,
-                    const double *uc = nullptr, int p0 = 0, int p1 = -1, bool write_u = true, const double *fine_faces = nullptr)
+                    const double *uc = nullptr, int p0 = 0, int p1 = -1, bool write_u = true, const double *fine_faces = nullptr,
+                    const HaloSync *hsp = nullptr)
 {
+	const HaloSync hs = hsp ? *hsp : HaloSync{};
+	if (hsp && !halo_in_kernel(h, l)) return fail(TGPU_ERR_ARG, "k_smooth: in-kernel halo hand-over is not available for this level");
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
 	if (p1 < 0) p1 = L.P;
@@ -1571,7 +1648,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm  = smooth3d32c_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 #define S32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc);
+	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs);
 		switch (key) {
 			S32_CASE(8 | 4 | 1, true, true, false, true)
 			S32_CASE(8 | 1, true, false, false, true)
@@ -1597,15 +1674,15 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !general) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		switch (key) {
-		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 8 | 1: return launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 8 | 4: return launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 4 | 1: return launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 1: return launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 4: return launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 4 | 2 | 1: return launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 2 | 1: return launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc);
-		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc);
+		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 8 | 1: return launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 8 | 4: return launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 4 | 1: return launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 1: return launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 4: return launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 4 | 2 | 1: return launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 2 | 1: return launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
 		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
 		}
 	}
@@ -1647,21 +1724,24 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 }
 // coarse = R (f - A u) for a u that a block-Jacobi sweep has just produced: needs only the faces of the new
 // (Fnew) and, unless the sweep started from zero (Fold == nullptr), the previous (Fold) iterate
-static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, const double *Fold, double *coarse, int p0 = 0, int p1 = -1)
+static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, const double *Fold, double *coarse, int p0 = 0, int p1 = -1,
+                                    const HaloSync *hsp = nullptr)
 {
 	LevelDev &L = h->levels[l];
+	const HaloSync hs = hsp ? *hsp : HaloSync{};
+	if (hsp && !halo_in_kernel(h, l)) return fail(TGPU_ERR_ARG, "k_face_residual_restrict: in-kernel halo hand-over is not available for this level");
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return TGPU_OK;
 	Tag tg(h->ctx, "face_residual_restrict", l);
 	if (is_3d32(h)) {
 		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 4)), block(TGPU_THREADS);
-		if (Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
-		return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		if (Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	}
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
 		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 8)), block(TGPU_THREADS);
-		if (Fold) return launch(h->ctx, face_residual_restrict16_kernel<true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
-		return launch(h->ctx, face_residual_restrict16_kernel<false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		if (Fold) return launch(h->ctx, face_residual_restrict16_kernel<true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		return launch(h->ctx, face_residual_restrict16_kernel<false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	}
 	DISPATCH_DN(h->D, h->N, {
 		using G        = Geo<DD, NN>;
@@ -1721,24 +1801,36 @@ static int p2p_wait(tgpu_hier *h, int l, int kind, int lag)
 	return launch(h->ctx, p2p_wait_kernel, dim3(1), dim3(32), 0, (const uint64_t *) (kind == P2P_DATA ? L.data_flags : L.ack_flags),
 	              (const int32_t *) L.peer_rank, (int) L.peers.size(), L.cnt + (kind == P2P_DATA ? 1 : 3), lag, h->p2p_abort, (int *) h->ctx->p2p_err);
 }
-// store my boundary faces (F, or F + P uc on the boundary cells) into the peers' halo slots and publish them
+// store my boundary faces (F, or F + P uc on the boundary cells) into the peers' halo slots and publish them: one kernel
+// that waits for the peers' ACK of the previous generation, pushes, and signals DATA from its last block (PushSync)
 static int p2p_push(tgpu_hier *h, int l, double *F, const double *uc)
 {
 	LevelDev &L   = h->levels[l];
 	tgpu_ctx *ctx = h->ctx;
 	if (F != L.Fa && F != L.Fb) return fail(TGPU_ERR_ARG, "p2p_push: not a face buffer of this level");
-	TRY(p2p_wait(h, l, P2P_ACK, 1)); // the peers are done with the previous generation
 	size_t M = 1;
 	for (int i = 0; i < h->D - 1; i++) M *= h->N;
-	if (L.nsend) {
-		Tag             tg(ctx, "p2p_push_faces", l);
-		double *const *pf = (F == L.Fa) ? L.peerFa : L.peerFb;
-		DISPATCH_DN_ALL(h->D, h->N, {
-			if (uc) TRY(launch(ctx, push_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
-			else TRY(launch(ctx, push_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf));
-		});
+	if (!L.nsend) { // nothing of mine is needed by anybody, but the protocol's generations still advance
+		TRY(p2p_wait(h, l, P2P_ACK, 1));
+		return p2p_signal(h, l, P2P_DATA);
 	}
-	return p2p_signal(h, l, P2P_DATA);
+	PushSync ps;
+	ps.ack_flags      = L.ack_flags;
+	ps.peer_rank      = L.peer_rank;
+	ps.peer_data_flag = L.peer_data_flag;
+	ps.cnt            = L.cnt;
+	ps.ticket         = L.tickets;
+	ps.abort          = h->p2p_abort;
+	ps.host_err       = (int *) ctx->p2p_err;
+	ps.npeers         = (int) L.peers.size();
+	ps.enabled        = 1;
+	Tag             tg(ctx, "p2p_push_faces", l);
+	double *const *pf = (F == L.Fa) ? L.peerFa : L.peerFb;
+	DISPATCH_DN_ALL(h->D, h->N, {
+		if (uc) TRY(launch(ctx, push_faces_kernel<DD, NN, true>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf, ps));
+		else TRY(launch(ctx, push_faces_kernel<DD, NN, false>, dim3(grid_for(ctx, L.nsend * M)), dim3(256), 0, (const PatchMeta *) L.meta, (int) L.nsend, (const int32_t *) L.send_patch, (const int32_t *) L.send_side, (const int32_t *) L.send_peer, (const int32_t *) L.send_ridx, (const double *) F, uc, pf, ps));
+	});
+	return TGPU_OK;
 }
 static bool exchanges(const tgpu_hier *h, int l)
 {
@@ -2031,9 +2123,14 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		TRY(fused_visit(h, o, l + 1, C.f, C.u, false, Fcur));
 	} else {
 	if (crosses_replication(h, l)) TRY(k_set(h, C.f, C.ncells, 0.0));
-	if (overlap && L.p2p) {
-		// the faces of the pre-smoothed u go straight into the neighbours' halo slots; theirs arrive while
-		// the patches without off-rank neighbours are swept
+	if (overlap && L.p2p && from_faces && halo_in_kernel(h, l)) {
+		// the faces of the pre-smoothed u go straight into the neighbours' halo slots; theirs arrive while the patches
+		// without off-rank neighbours are swept: ONE launch over all owned patches whose CTAs poll the peers' flags
+		// before their first boundary patch and whose last CTA acknowledges the halo (HaloSync, kernels.cuh)
+		const HaloSync hs = halo_sync(h, l);
+		TRY(p2p_push(h, l, Fcur, nullptr));
+		TRY(k_face_residual_restrict(h, l, Fcur, Fold, C.f, 0, L.P, &hs));
+	} else if (overlap && L.p2p) {
 		TRY(p2p_push(h, l, Fcur, nullptr));
 		TRY(residual_restrict(0, L.n_interior));
 		TRY(p2p_wait(h, l, P2P_DATA, 0));
@@ -2059,7 +2156,10 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		const bool emit      = !lastsweep || want_faces;
 		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
-		if (i == 0 && overlap) {
+		if (i == 0 && overlap && L.p2p && halo_in_kernel(h, l)) {
+			const HaloSync hs = halo_sync(h, l);
+			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.P, lastsweep, nullptr, &hs));
+		} else if (i == 0 && overlap) {
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior, lastsweep));
 			if (L.p2p) TRY(p2p_wait(h, l, P2P_DATA, 0));
 			else CU(cudaStreamWaitEvent(h->ctx->stream, L.ev[3], 0));
@@ -2279,15 +2379,27 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 	auto A = [&](const tgpu_vec *in, tgpu_vec *out) { return tgpu_apply(h, 0, in, out); };
 	// the preconditioner's last sweep emits the boundary slices of its result, which is all A needs besides the result
 	auto M = [&](const tgpu_vec *in, tgpu_vec *out) { return cycle_ptr(h, opts, in->d, out->d, true); };
-	auto AM = [&](const tgpu_vec *in, tgpu_vec *out) { // out = A in for in = the vector M has just produced
-		if (!h->cycle_faces) return tgpu_apply(h, 0, in, out);
-		TRY(k_exchange(h, 0, h->cycle_faces, nullptr));
-		TRY(k_apply(h, 0, 0, in->d, nullptr, h->cycle_faces, out->d, nullptr));
+	// out = A in for in = the vector M has just produced (its boundary slices are in h->cycle_faces), with the dot products the
+	// iteration needs next (out . dotv, out . out) formed by the same kernel where it can: *fused tells whether it did
+	auto AM = [&](const tgpu_vec *in, tgpu_vec *out, const tgpu_vec *dotv, int *nbp, bool *fused) {
+		*fused = false;
+		double *F = h->cycle_faces;
+		if (!F) {
+			F = h->levels[0].Fa;
+			TRY(k_extract_faces(h, 0, in->d, F));
+		}
+		TRY(k_exchange(h, 0, F, nullptr));
+		if (apply_tma_available()) {
+			TRY(k_apply(h, 0, 3, in->d, dotv->d, F, out->d, nullptr, 0, -1, nbp));
+			*fused = true;
+		} else {
+			TRY(k_apply(h, 0, 0, in->d, nullptr, F, out->d, nullptr));
+		}
 		return k_exchange_done(h, 0);
 	};
-	auto finish = [&](int step) {
+	auto finish = [&](int step, int nparts) {
 		Tag tg(ctx, "bicg_scalars", 0);
-		TRY(launch(ctx, bicg_finish_kernel, dim3(1), dim3(256), 0, nb, stride, (const double *) ctx->d_partial, sc, step, dist ? 0 : 1));
+		TRY(launch(ctx, bicg_finish_kernel, dim3(1), dim3(256), 0, nparts, stride, (const double *) ctx->d_partial, sc, step, dist ? 0 : 1));
 		if (dist) {
 			NC(g_nccl.AllReduce(sc + SC_SUM0, sc + SC_SUM0, 2, ncclDouble, ncclSum, ctx->comm, ctx->stream));
 			TRY(launch(ctx, bicg_scalars_kernel, dim3(1), dim3(32), 0, sc, step));
@@ -2297,7 +2409,7 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 	auto dots = [&](const tgpu_vec *a, const tgpu_vec *c, int step) {
 		Tag tg(ctx, "bicg_dots", 0);
 		TRY(launch(ctx, bicg_dots_kernel, dim3(nb), dim3(256), 0, n, (const double *) a->d, (const double *) c->d, ctx->d_partial, stride));
-		return finish(step);
+		return finish(step, nb);
 	};
 	auto read_rnorm = [&](double *out) {
 		CU(cudaMemcpyAsync(ctx->h_result, sc + SC_RNORM, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2316,31 +2428,36 @@ static int bicgstab_fused(tgpu_hier *h, const TgpuCycleOpts *opts, const tgpu_ve
 	int its = 0;
 	while (rn / r0_norm > tol && its < max_it) {
 		const tgpu_vec *pp = p, *ss = s;
+		bool fused_dots = false;
+		int  nparts     = nb;
 		if (prec) {
 			TRY(M(p, mp));
 			pp = mp;
-			TRY(AM(pp, ap));
+			TRY(AM(pp, ap, rhat, &nparts, &fused_dots)); // ap = A mp, ap . rhat riding along
 		} else {
 			TRY(A(pp, ap));
 		}
-		TRY(dots(rhat, ap, 1)); // alpha
+		if (fused_dots) TRY(finish(1, nparts));
+		else TRY(dots(rhat, ap, 1)); // alpha
 		{
 			Tag tg(ctx, "bicg_s", 0);
 			TRY(launch(ctx, bicg_s_kernel, dim3(grid_for(ctx, n)), dim3(256), 0, n, (const double *) resid->d, (const double *) ap->d, s->d, (const double *) sc));
 		}
+		fused_dots = false;
 		if (prec) {
 			TRY(M(s, ms));
 			ss = ms;
-			TRY(AM(ss, as));
+			TRY(AM(ss, as, s, &nparts, &fused_dots)); // as = A ms, as . s and as . as riding along
 		} else {
 			TRY(A(ss, as));
 		}
-		TRY(dots(as, s, 2)); // omega
+		if (fused_dots) TRY(finish(2, nparts));
+		else TRY(dots(as, s, 2)); // omega
 		{
 			Tag tg(ctx, "bicg_xr", 0);
 			TRY(launch(ctx, bicg_xr_kernel, dim3(nb), dim3(256), 0, n, x->d, (const double *) pp->d, (const double *) ss->d, resid->d, (const double *) ap->d, (const double *) as->d, (const double *) rhat->d, (const double *) sc, ctx->d_partial, stride));
 		}
-		TRY(finish(3)); // rho, beta, |r|
+		TRY(finish(3, nb)); // rho, beta, |r|
 		{
 			Tag tg(ctx, "bicg_p", 0);
 			TRY(launch(ctx, bicg_p_kernel, dim3(grid_for(ctx, n)), dim3(256), 0, n, p->d, (const double *) ap->d, (const double *) resid->d, (const double *) sc));
