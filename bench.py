@@ -41,12 +41,16 @@ CONFIGS = {
     "D2": (3, "3uni.bin", 1, 32, 16777216, "3uni.bin --divide 1, 512 patches of 32^3 (16,777,216 cells), 4 levels, trig RHS"),
     "E": (2, "2d_multi_refine_8.bin", 4, 32, 41943040, "config E: apps/2d/steady2d GMG, deeply refined quadtree multi_refine_8.bin (tree levels 3-9) --divide 4, 40,960 patches of 32^2 (41,943,040 cells), 13 levels, trig RHS"),
     "E5": (2, "2d_multi_refine_8.bin", 5, 32, 167772160, "config E, one more --divide: 163,840 patches of 32^2 (167,772,160 cells), 14 levels, trig RHS"),
+    "GMGEX": (3, "3d_multi_refine_8.bin", 2, 16, 73662464, "the reference's shipped GMG example (apps/3d/config/gmg_example.ini: Neumann boundaries, problem gauss, 16^3 patches, meshes/multi_refine_8.bin) --divide 2: 17,984 patches of 16^3 (73,662,464 cells), 11 levels"),
     "small": (3, "3uni.bin", 1, 16, 2097152, "3uni.bin --divide 1, 512 patches of 16^3 (2,097,152 cells), 4 levels, trig RHS"),
     "small32": (3, "3uni.bin", 0, 32, 2097152, "3uni.bin, 64 patches of 32^3 (2,097,152 cells), 3 levels, trig RHS"),
 }
-# config E weak scaling: the finest leaves with centre x < frac are refined once more (refine_box) on top of --divide k,
-# sized so that cells per GPU stay close to the 1-GPU point (41.9 M); the exact cell counts are reported
-E_WEAK = {1: ("E", None), 2: ("E", 0.5), 4: ("E5", None), 8: ("E5", 0.5)}
+# config E weak scaling: the mesh family grows by a factor 4 per --divide, so the 1- and 4-GPU points are an exact weak pair
+# (41.9 M cells per GPU); the 2- and 8-GPU points run the same two meshes at half the cells per GPU (a 2:1-balanced mesh with
+# twice the cells does not exist in this family).  cells_per_gpu and DOF/s per GPU are reported with every point.
+E_WEAK = {1: ("E", None), 2: ("E", None), 4: ("E5", None), 8: ("E5", None)}
+# workloads with Neumann conditions on the whole domain boundary: name -> manufactured problem (apps/3d/steady.cpp:230-282)
+NEUMANN = {"GMGEX": "gauss"}
 ALGO_BYTES_PER_CELL_VISIT = 48.0  # pre-smooth 16 + residual/restrict 16 + post-smooth 16
 CYCLE = "V(1,1), 1 coarse sweep, all levels down to the root patch"
 DFT_CAVEAT = ("patch solver = the reference's first-party DftPatchSolver (dense n x n transform matrices through a naive dgemv_ shim): "
@@ -215,6 +219,8 @@ def build_hierarchy(env, cfg, box_frac=None, distributed=True):
     D, mesh_file, divide, n, _, _ = CONFIGS[cfg]
     t0 = time.perf_counter()
     mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
+    if cfg in NEUMANN:
+        mesh.set_neumann(True)
     if box_frac is not None:
         mesh.refine_box((0.0, 0.0, 0.0), (box_frac, 1.0, 1.0))
     part = None
@@ -467,7 +473,12 @@ def measure_config(env, cfg, steps, warmup, box_frac=None, profile=True):
     cells = h.ncells(0)
     level_cells = [h.ncells(l) for l in range(h.nlevels)]
     f, u = h.new_vec(0), h.new_vec(0)
-    h.init_trig_rhs(f)
+    if cfg in NEUMANN:  # Init::initNeumann + the mean removal of apps/3d/steady.cpp:330-334
+        h.init_neumann_rhs(f, None, NEUMANN[cfg])
+        integral, volume = h.integrate(f)
+        f.shift(-integral / volume)
+    else:
+        h.init_trig_rhs(f)
     opts = pps.CycleOpts.default()
     if env.world > 1:
         opts.use_graph = 2  # capture the halo exchanges into the CUDA graph as well
@@ -505,6 +516,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cycle-only", action="store_true", help="only the device-resident V-cycle timing and its roofline")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--with-solve", action="store_true", help="with --cycle-only: also the time to 1e-10 residual")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -534,6 +546,8 @@ def main():
         line["e2e"] = e2e_block(env, h, f, u, opts, args.steps, cells, total_cells)
     else:
         line["e2e"] = None
+        if args.with_solve:
+            line["time_to_solution"] = time_to_solution(env, h, f, opts, total_cells)
     close_all(state)
 
     if env.world > 1 and not args.cycle_only:
@@ -570,15 +584,17 @@ def main():
     if env.rank == 0 and env.world == 1 and not args.cycle_only and not args.no_other_configs:
         # the other BASELINE configs (and config D's mesh with 16^3 patches), each in a child process with the same kernels
         others = {}
-        for name in ("B", "A", "C", "E", "D16", "D2"):
+        for name in ("B", "A", "C", "E", "D16", "D2", "GMGEX"):
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", name, "--cycle-only", "--steps", "10", "--warmup", "3",
-                                      "--no-cpu-baseline"], capture_output=True, text=True, timeout=900).stdout
+                                      "--no-cpu-baseline"] + (["--with-solve"] if name in ("B", "GMGEX") else []), capture_output=True, text=True, timeout=900).stdout
                 o = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
                 others[name] = {"workload": o["config"]["workload"], "n_gpus": 1, "value": o["value"], "unit": "DOF/s", "ms_per_step": o["ms_per_step"],
                                 "steps": o["steps"], "cells": o["config"]["cells"], "setup_s": o["setup_s"],
                                 "vcycle_frac_of_hbm_roofline": o["roofline"]["vcycle_frac"], "smoother_frac": o["roofline"]["frac"],
                                 "smoother_per_instantiation": {k: round(v["frac"], 4) for k, v in o["roofline"]["per_instantiation"].items()}}
+                if "time_to_solution" in o:
+                    others[name]["time_to_solution"] = {k: o["time_to_solution"][k] for k in ("bicgstab_ms", "bicgstab_iterations", "stationary_ms", "stationary_cycles")}
             except Exception as ex:
                 others[name] = {"error": str(ex)[:300]}
         line["other_configs"] = others

@@ -121,23 +121,29 @@ __device__ __forceinline__ void halo_wait_cta(const HaloSync &hs, int p, bool &w
 	__syncthreads();
 	waited = true;
 }
-// end of the kernel (every thread calls): the last CTA advances "data awaited" and acknowledges the halo to the peers
+// end of the kernel: the last CTA to finish advances "data awaited" and acknowledges the halo to the peers (one thread; out
+// of line, the fences and the release stores are cold code)
+__device__ __noinline__ void halo_finish_thread0(unsigned *ticket, unsigned nctas, int *abort, uint64_t *cnt, uint64_t *const *peer_ack_flag, int npeers)
+{
+	__threadfence();
+	const unsigned done = atomicAdd(ticket, 1u);
+	if (done != nctas - 1) return;
+	__threadfence();
+	*ticket = 0;
+	if (*abort) return; // the protocol stays where it broke
+	cnt[1] += 1;
+	const uint64_t v = cnt[2] + 1;
+	__threadfence_system();
+#pragma unroll 1
+	for (int k = 0; k < npeers; k++) st_release_sys(peer_ack_flag[k], v);
+	cnt[2] = v;
+}
+// (every thread calls)
 __device__ __forceinline__ void halo_finish(const HaloSync &hs)
 {
 	if (!hs.enabled) return;
 	__syncthreads();
-	if (threadIdx.x != 0) return;
-	__threadfence();
-	const unsigned done = atomicAdd(hs.ticket, 1u);
-	if (done != gridDim.x * gridDim.y - 1) return;
-	__threadfence();
-	*hs.ticket = 0;
-	if (*hs.abort) return; // the protocol stays where it broke
-	hs.cnt[1] += 1;
-	const uint64_t v = hs.cnt[2] + 1;
-	__threadfence_system();
-	for (int k = 0; k < hs.npeers; k++) st_release_sys(hs.peer_ack_flag[k], v);
-	hs.cnt[2] = v;
+	if (threadIdx.x == 0) halo_finish_thread0(hs.ticket, gridDim.x * gridDim.y, hs.abort, hs.cnt, hs.peer_ack_flag, hs.npeers);
 }
 // resident smoother CTAs per SM the register budget is tuned for (N = 32 pencils need > 128 registers)
 #ifndef SMOOTH_BLOCKS_16

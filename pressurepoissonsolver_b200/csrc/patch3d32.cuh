@@ -306,11 +306,18 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
 		const int    p    = p0 + g;
 		halo_wait_cta(hs, p, halo_ok);
-		const double cfac = 2.0 * meta[p].inv_h2;
+		const PatchMeta &pq   = meta[p];
+		const double     cfac = 2.0 * pq.inv_h2;
+		// all loads of the six interface values in flight at once: one memory round trip (coarse levels: one patch per cluster)
+		Gam32<PROLONG> g6[6];
 #pragma unroll
-		for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = cfac * gamma_entry32<PROLONG>(meta, p, s, mf, Fin, uc);
-		GZ[t]       = cfac * gamma_entry32<PROLONG>(meta, p, sz, t, Fin, uc);
-		GZ[t + 512] = cfac * gamma_entry32<PROLONG>(meta, p, sz, t + 512, Fin, uc);
+		for (int s = 0; s < 4; s++) g6[s].issue(pq, p, s, mf, Fin, uc);
+		g6[4].issue(pq, p, sz, t, Fin, uc);
+		g6[5].issue(pq, p, sz, t + 512, Fin, uc);
+#pragma unroll
+		for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = g6[s].finish(meta, p, s, mf, Fin, uc, cfac);
+		GZ[t]       = g6[4].finish(meta, p, sz, t, Fin, uc, cfac);
+		GZ[t + 512] = g6[5].finish(meta, p, sz, t + 512, Fin, uc, cfac);
 		__syncthreads();
 	}
 	for (int it = 0; g < npatch; g += ncl, it++) {
@@ -691,80 +698,153 @@ apply3d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double
 // residual + restriction from face data for patches whose face (M entries) is larger than the block
 // (see face_residual_restrict_kernel for the identity used); one patch per CTA, R[6][M] in dynamic smem
 // ---------------------------------------------------------------------------------------------
+// one patch, general form (any neighbour types, patches present on both levels); R = [S][M] staging in shared memory;
+// every thread of the CTA calls; ends with a barrier
+template <int D, int N, bool DIFF>
+__device__ __forceinline__ void frr_big_patch(const PatchMeta *__restrict__ meta, int p, double *R, const double *__restrict__ Fnew,
+                                              const double *__restrict__ Fold, double *__restrict__ coarse)
+{
+	using G         = Geo<D, N>;
+	constexpr int H = N / 2, M = G::M;
+	const int        t      = threadIdx.x;
+	const PatchMeta &pm     = meta[p];
+	const int        orth   = pm.orth_on_parent;
+	const double     cfac   = 2.0 * pm.inv_h2;
+	double *         dst    = coarse + (size_t) pm.parent_idx * G::NC;
+	const FaceVals<D, N, DIFF ? FV_DIFF : FV_NEG> fv{Fnew, Fold, meta};
+	for (int i = t; i < G::S * M; i += TGPU_THREADS) {
+		const int s = i / M, m = i % M;
+		R[i]        = cfac * gamma_entry(pm, p, s, m, fv);
+	}
+	__syncthreads();
+	auto Rp = [&](int s, int m) { return R[s * M + m]; };
+	if (orth < 0) { // patch present on both levels: coarse = r (dense, zero in the interior)
+		for (int c = t; c < G::NC; c += TGPU_THREADS) {
+			const int x = c % N, y = (c / N) % N, k = (D == 2) ? 0 : c / (N * N);
+			double    v = 0.0;
+			if (D == 2) {
+				if (x == 0) v += Rp(0, y);
+				if (x == N - 1) v += Rp(1, y);
+				if (y == 0) v += Rp(2, x);
+				if (y == N - 1) v += Rp(3, x);
+			} else {
+				if (x == 0) v += Rp(0, y + N * k);
+				if (x == N - 1) v += Rp(1, y + N * k);
+				if (y == 0) v += Rp(2, x + N * k);
+				if (y == N - 1) v += Rp(3, x + N * k);
+				if (k == 0) v += Rp(4, x + N * y);
+				if (k == N - 1) v += Rp(5, x + N * y);
+			}
+			dst[c] = v;
+		}
+	} else {
+		const int     ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
+		constexpr int CC = G::NC >> D;
+		for (int c = t; c < CC; c += TGPU_THREADS) {
+			const int X = c % H, Y = (c / H) % H, Z = (D == 2) ? 0 : c / (H * H);
+			double    v = 0.0;
+			if (D == 2) {
+				auto blk = [&](int s, int I) { return (Rp(s, 2 * I) + Rp(s, 2 * I + 1)) / 4.0; };
+				if (X == 0) v += blk(0, Y);
+				if (X == H - 1) v += blk(1, Y);
+				if (Y == 0) v += blk(2, X);
+				if (Y == H - 1) v += blk(3, X);
+				dst[(Y + oy) * N + (X + ox)] = v;
+			} else {
+				auto blk = [&](int s, int I, int J) {
+					const int b = 2 * I + N * 2 * J;
+					return ((Rp(s, b) + Rp(s, b + 1)) + (Rp(s, b + N) + Rp(s, b + N + 1))) / 8.0;
+				};
+				if (X == 0) v += blk(0, Y, Z);
+				if (X == H - 1) v += blk(1, Y, Z);
+				if (Y == 0) v += blk(2, X, Z);
+				if (Y == H - 1) v += blk(3, X, Z);
+				if (Z == 0) v += blk(4, X, Y);
+				if (Z == H - 1) v += blk(5, X, Y);
+				dst[((Z + oz) * N + (Y + oy)) * N + (X + ox)] = v;
+			}
+		}
+	}
+	__syncthreads();
+}
 template <int D, int N, bool DIFF>
 __global__ void __launch_bounds__(TGPU_THREADS)
 face_residual_restrict_big_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
                                   const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
 {
-	using G         = Geo<D, N>;
-	constexpr int H = N / 2, M = G::M;
+	using G = Geo<D, N>;
 	extern __shared__ __align__(16) double R[]; // [S][M]
 	const int t = threadIdx.x;
 	pdl_launch_dependents();
 	pdl_wait();
 	bool halo_ok = false;
 	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
-		const int        p      = p0 + g;
+		const int p = p0 + g;
 		halo_wait_cta(hs, p, halo_ok);
-		const PatchMeta &pm     = meta[p];
-		const int        orth   = pm.orth_on_parent;
-		const double     cfac   = 2.0 * pm.inv_h2;
-		double *         dst    = coarse + (size_t) pm.parent_idx * G::NC;
-		const FaceVals<D, N, DIFF ? FV_DIFF : FV_NEG> fv{Fnew, Fold, meta};
-		for (int i = t; i < G::S * M; i += TGPU_THREADS) {
-			const int s = i / M, m = i % M;
-			R[i]        = cfac * gamma_entry(pm, p, s, m, fv);
-		}
-		__syncthreads();
-		auto Rp = [&](int s, int m) { return R[s * M + m]; };
-		if (orth < 0) { // patch present on both levels: coarse = r (dense, zero in the interior)
-			for (int c = t; c < G::NC; c += TGPU_THREADS) {
-				const int x = c % N, y = (c / N) % N, k = (D == 2) ? 0 : c / (N * N);
-				double    v = 0.0;
-				if (D == 2) {
-					if (x == 0) v += Rp(0, y);
-					if (x == N - 1) v += Rp(1, y);
-					if (y == 0) v += Rp(2, x);
-					if (y == N - 1) v += Rp(3, x);
-				} else {
-					if (x == 0) v += Rp(0, y + N * k);
-					if (x == N - 1) v += Rp(1, y + N * k);
-					if (y == 0) v += Rp(2, x + N * k);
-					if (y == N - 1) v += Rp(3, x + N * k);
-					if (k == 0) v += Rp(4, x + N * y);
-					if (k == N - 1) v += Rp(5, x + N * y);
+		if (D == 3 && N == 32) {
+			// Refined patches whose six sides have same-level neighbours (or none) - every patch of a uniform level - take a
+			// leaner path, like face_residual_restrict16_kernel: one thread per COARSE face entry (6 x 256 per patch) loads
+			// its 2 x 2 block of the patch's and the neighbour's slices with four 128-bit loads and stores the block
+			// average; the 16^3 coarse cells under the patch are then assembled two per thread and stored as double2.
+			// Same expressions and summation order as frr_big_patch.
+			const PatchMeta &pm   = meta[p];
+			bool             fast = pm.orth_on_parent >= 0;
+#pragma unroll
+			for (int s = 0; s < 6; s++) fast = fast && pm.nbr_type[s] <= NBR_NORMAL;
+			if (fast) { // CTA-uniform
+				const double cfac = 2.0 * pm.inv_h2;
+				double *     Rc   = R; // [6][256]
+#pragma unroll
+				for (int k = 0; k < 6; k++) {
+					const int e = t + TGPU_THREADS * k, s = k, c = t, m0 = 2 * (c & 15) + 64 * (c >> 4);
+					double    val = 0.0;
+					if (pm.nbr_type[s] == NBR_NORMAL) {
+						const size_t oa = ((size_t) p * 6 + s) * 1024 + m0, ob = ((size_t) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 1024 + m0;
+						auto ld = [&](size_t o) {
+							double2 v = __ldg(reinterpret_cast<const double2 *>(Fnew + o));
+							if (DIFF) {
+								const double2 w = __ldg(reinterpret_cast<const double2 *>(Fold + o));
+								v.x = w.x - v.x, v.y = w.y - v.y;
+							} else {
+								v.x = -v.x, v.y = -v.y;
+							}
+							return v;
+						};
+						const double2 a0 = ld(oa), a1 = ld(oa + 32), b0 = ld(ob), b1 = ld(ob + 32);
+						const double  r00 = cfac * (0.5 * a0.x + 0.5 * b0.x), r01 = cfac * (0.5 * a0.y + 0.5 * b0.y);
+						const double  r10 = cfac * (0.5 * a1.x + 0.5 * b1.x), r11 = cfac * (0.5 * a1.y + 0.5 * b1.y);
+						val               = ((r00 + r01) + (r10 + r11)) / 8.0;
+					}
+					Rc[e] = val;
 				}
-				dst[c] = v;
-			}
-		} else {
-			const int     ox = (orth & 1) * H, oy = ((orth >> 1) & 1) * H, oz = (D == 2) ? 0 : ((orth >> 2) & 1) * H;
-			constexpr int CC = G::NC >> D;
-			for (int c = t; c < CC; c += TGPU_THREADS) {
-				const int X = c % H, Y = (c / H) % H, Z = (D == 2) ? 0 : c / (H * H);
-				double    v = 0.0;
-				if (D == 2) {
-					auto blk = [&](int s, int I) { return (Rp(s, 2 * I) + Rp(s, 2 * I + 1)) / 4.0; };
-					if (X == 0) v += blk(0, Y);
-					if (X == H - 1) v += blk(1, Y);
-					if (Y == 0) v += blk(2, X);
-					if (Y == H - 1) v += blk(3, X);
-					dst[(Y + oy) * N + (X + ox)] = v;
-				} else {
-					auto blk = [&](int s, int I, int J) {
-						const int b = 2 * I + N * 2 * J;
-						return ((Rp(s, b) + Rp(s, b + 1)) + (Rp(s, b + N) + Rp(s, b + N + 1))) / 8.0;
-					};
-					if (X == 0) v += blk(0, Y, Z);
-					if (X == H - 1) v += blk(1, Y, Z);
-					if (Y == 0) v += blk(2, X, Z);
-					if (Y == H - 1) v += blk(3, X, Z);
-					if (Z == 0) v += blk(4, X, Y);
-					if (Z == H - 1) v += blk(5, X, Y);
-					dst[((Z + oz) * N + (Y + oy)) * N + (X + ox)] = v;
+				__syncthreads();
+				const int orth = pm.orth_on_parent;
+				const int ox = (orth & 1) * 16, oy = ((orth >> 1) & 1) * 16, oz = ((orth >> 2) & 1) * 16;
+				double *  dst = coarse + (size_t) pm.parent_idx * G::NC;
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const int q = t + TGPU_THREADS * k;                          // pair index: cells (X, Y, Z), (X + 1, Y, Z)
+					const int X = (q & 7) * 2, Y = (q >> 3) & 15, Z = q >> 7;
+					double    v[2];
+#pragma unroll
+					for (int i = 0; i < 2; i++) {
+						const int x = X + i;
+						double    a = 0.0;
+						if (x == 0) a += Rc[0 * 256 + Y + 16 * Z];
+						if (x == 15) a += Rc[1 * 256 + Y + 16 * Z];
+						if (Y == 0) a += Rc[2 * 256 + x + 16 * Z];
+						if (Y == 15) a += Rc[3 * 256 + x + 16 * Z];
+						if (Z == 0) a += Rc[4 * 256 + x + 16 * Y];
+						if (Z == 15) a += Rc[5 * 256 + x + 16 * Y];
+						v[i] = a;
+					}
+					*reinterpret_cast<double2 *>(dst + ((Z + oz) * 32 + (Y + oy)) * 32 + (X + ox)) = make_double2(v[0], v[1]);
 				}
+				__syncthreads();
+				continue;
 			}
 		}
-		__syncthreads();
+		frr_big_patch<D, N, DIFF>(meta, p, R, Fnew, Fold, coarse);
 	}
 	halo_finish(hs);
 }

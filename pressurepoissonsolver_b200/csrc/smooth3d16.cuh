@@ -287,16 +287,19 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		describe(meta[p], p, 0);
 		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
 		__syncthreads();
+		// all six sides' loads in flight at once (no transform registers are live yet): one memory round trip instead
+		// of six, which is most of the latency of a coarse level where every CTA solves a single patch
+		SideGamma16<PROLONG> s6[6];
+		s6[0].template issue<0>(GD[0].d[0], t, lo, hi, Fin, uc);
+		s6[1].template issue<0>(GD[0].d[1], t, lo, hi, Fin, uc);
+		s6[2].template issue<1>(GD[0].d[2], t, lo, hi, Fin, uc);
+		s6[3].template issue<1>(GD[0].d[3], t, lo, hi, Fin, uc);
+		s6[4].template issue<2>(GD[0].d[4], t, lo, hi, Fin, uc);
+		s6[5].template issue<2>(GD[0].d[5], t, lo, hi, Fin, uc);
 #pragma unroll
-		for (int s = 0; s < 4; s++) {
-			if (s < 2) sg.template issue<0>(GD[0].d[s], t, lo, hi, Fin, uc);
-			else sg.template issue<1>(GD[0].d[s], t, lo, hi, Fin, uc);
-			Gs[s * 256 + t] = sg.finish(GD[0], s, meta, p, t, Fin, uc);
-		}
-		sg.template issue<2>(GD[0].d[4], t, lo, hi, Fin, uc);
-		gz0 = sg.finish(GD[0], 4, meta, p, t, Fin, uc);
-		sg.template issue<2>(GD[0].d[5], t, lo, hi, Fin, uc);
-		gz1 = sg.finish(GD[0], 5, meta, p, t, Fin, uc);
+		for (int s = 0; s < 4; s++) Gs[s * 256 + t] = s6[s].finish(GD[0], s, meta, p, t, Fin, uc);
+		gz0 = s6[4].finish(GD[0], 4, meta, p, t, Fin, uc);
+		gz1 = s6[5].finish(GD[0], 5, meta, p, t, Fin, uc);
 	}
 	for (int it = 0; g < npatch; g += gridDim.x, it++) {
 		const int       b    = it & 1;

@@ -2118,7 +2118,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		return k_apply(h, l, 2, u, f, Fcur, nullptr, C.f, p0, p1);
 	};
 	// residual + restriction fused into the coarser level's first sweep where that kernel exists
-	const bool defer = from_faces && !Fold && can_source_from_fine(h, l + 1);
+	const bool defer = from_faces && !Fold && o.cycle_type == 0 && can_source_from_fine(h, l + 1);
 	if (defer) {
 		TRY(fused_visit(h, o, l + 1, C.f, C.u, false, Fcur));
 	} else {
@@ -2148,6 +2148,20 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	if (crosses_replication(h, l)) TRY(k_allreduce_sum(h, C.f, C.ncells));
 	TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
 	}
+	if (o.cycle_type == 1) {
+		// W cycle (GMG/WCycle.h:57-63; one GPU, mid_sweeps >= 1): the second coarse-grid correction.  The iterate before the
+		// mid sweeps is u_pre + P u_c, seen only through its boundary slices: Fcur += (P u_c) on the boundary cells; every
+		// mid sweep emits the slices of its result, and the residual after the last one is again supported on the faces
+		// (old slices - new slices), so neither u_pre + P u_c nor the mid-smoothed u is ever written.
+		TRY(k_prolong_faces(h, l, C.u, Fcur));
+		for (int i = 0; i < o.mid_sweeps; i++) {
+			TRY(k_smooth(h, l, false, true, f, u, Fcur, Falt, nullptr, 0, -1, !from_faces));
+			std::swap(Fcur, Falt);
+		}
+		Fold = Falt;
+		TRY(residual_restrict(0, L.P));
+		TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
+	}
 	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
 	if (overlap && L.p2p) TRY(p2p_push(h, l, Fcur, C.u));
 	else if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
@@ -2174,16 +2188,18 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 	if (l == 0 && want_faces) h->cycle_faces = Fcur; // the last sweep emitted the slices of u here
 	return TGPU_OK;
 }
-// the fused schedule covers V cycles with at least one sweep everywhere and the piecewise-constant interpolator
-static bool fused_schedule(const TgpuCycleOpts &o)
+// the fused schedule covers cycles with at least one sweep everywhere and the piecewise-constant interpolator: V cycles on
+// any number of GPUs, W cycles (with at least one mid sweep) on one GPU
+static bool fused_schedule(const TgpuCycleOpts &o, int nranks)
 {
-	return o.fused && o.cycle_type == 0 && o.interpolator == 0 && o.pre_sweeps >= 1 && o.post_sweeps >= 1 && o.coarse_sweeps >= 1;
+	if (!o.fused || o.interpolator != 0 || o.pre_sweeps < 1 || o.post_sweeps < 1 || o.coarse_sweeps < 1) return false;
+	return o.cycle_type == 0 || (o.cycle_type == 1 && o.mid_sweeps >= 1 && nranks == 1);
 }
 // want_faces: the caller applies the operator to the result next (BiCGStab: v = A M^-1 p), so the last sweep also
 // writes the result's boundary slices (h->cycle_faces != nullptr afterwards) and no extraction pass is needed
 static int run_cycle(tgpu_hier *h, const TgpuCycleOpts &o, const double *f, double *u, bool want_faces = false)
 {
-	const bool fused = fused_schedule(o);
+	const bool fused = fused_schedule(o, h->ctx->nranks);
 	h->cycle_faces   = nullptr;
 	if (fused) return fused_visit(h, o, 0, f, u, want_faces && h->last_level > 0);
 	TRY(k_set(h, u, h->levels[0].ncells, 0.0)); // Cycle::apply: u->set(0)
@@ -2214,7 +2230,7 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 	}
 	for (size_t l = 0; l <= (size_t) h->last_level; l++) {
 		TRY(need_smoother(h, (int) l));
-		const bool fused_sched = fused_schedule(o);
+		const bool fused_sched = fused_schedule(o, ctx->nranks);
 		TRY(ensure_work(h, (int) l, !fused_sched || (o.fused == 2 && is_3d32(h))));
 	}
 	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u, want_faces);
