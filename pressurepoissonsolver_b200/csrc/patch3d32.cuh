@@ -275,6 +275,78 @@ template <bool PROLONG> struct Gam32 {
 	}
 };
 
+// Gather descriptor of one patch side (the 32^3 analogue of GDesc16, smooth3d16.cuh): everything that is uniform over the
+// 1024 face entries, resolved once per patch by one thread, so that an entry's four loads are "base + per-thread constant":
+//   (2/h^2) gamma = c (0.5 (a0[m] + a1[o]) + 0.5 (b0[m] + wb b1[o])),  o = the entry's offset on the parent's plane
+// a0 / b0: own / neighbour face slice, a1 / b1: the parents' cells under them (DrctIntp.h:92-111, only with the prolongation
+// fused in), c = 0 on sides without a neighbour, wb = 0 for halo faces that already carry the correction, SA / SB: the
+// parent is a refined patch (two entries per coarse cell) or the same patch one level up (copy-add).  Sides with coarse /
+// fine neighbours are flagged GD_SLOW and take gamma_entry32.
+#ifndef C32_GDESC
+#define C32_GDESC 1 // 0: per-thread neighbour-table reads and index arithmetic for every entry (Gam32)
+#endif
+struct __align__(16) GDesc32 {
+	unsigned a0, b0, a1, b1; // element offsets into F (a0, b0) and into uc (a1, b1)
+	double   c;
+	int      flags, pad;
+};
+struct GPatch32 {
+	GDesc32 d[6];
+};
+template <bool PROLONG>
+__device__ __forceinline__ void make_gdesc32(const PatchMeta &pm, int p, int s, GPatch32 &out)
+{
+	GDesc32 & d  = out.d[s];
+	const int ty = pm.nbr_type[s];
+	const int ax = s >> 1;
+	const int st = (ax == 0) ? 1 : (ax == 1 ? 32 : 1024); // stride of the face-normal axis
+	d.a0 = d.b0 = ((unsigned) p * 6 + s) * 1024;
+	d.a1 = d.b1 = 0;
+	d.c         = (ty == NBR_NONE) ? 0.0 : 2.0 * pm.inv_h2;
+	int fl      = GD_SA | GD_SB | GD_WB;
+	if (ty == NBR_NORMAL) {
+		d.b0 = ((unsigned) pm.nbr_idx[s][0] * 6 + (s ^ 1)) * 1024;
+		if (PROLONG) {
+			const int o = pm.orth_on_parent, qp = pm.nbr_parent[s], qo = pm.nbr_orth[s];
+			if (o >= 0) d.a1 = (unsigned) pm.parent_idx * 32768 + 16 * ((o & 1) + 32 * ((o >> 1) & 1) + 1024 * ((o >> 2) & 1)) + ((s & 1) ? 15 * st : 0);
+			else d.a1 = (unsigned) pm.parent_idx * 32768 + ((s & 1) ? 31 * st : 0), fl &= ~GD_SA;
+			if (qp < 0) d.b1 = d.a1, fl = (fl & ~(GD_SB | GD_WB)) | ((fl & GD_SA) ? GD_SB : 0);
+			else if (qo >= 0) d.b1 = (unsigned) qp * 32768 + 16 * ((qo & 1) + 32 * ((qo >> 1) & 1) + 1024 * ((qo >> 2) & 1)) + ((s & 1) ? 0 : 15 * st);
+			else d.b1 = (unsigned) qp * 32768 + ((s & 1) ? 0 : 31 * st), fl &= ~GD_SB;
+		}
+	} else if (ty > NBR_NORMAL) {
+		fl = GD_SA | GD_SB | GD_WB | GD_SLOW; // harmless addresses; the value comes from gamma_entry32
+	}
+	d.flags = fl;
+}
+template <bool PROLONG> struct SideGamma32 {
+	double a0, a1, b0, b1;
+	// AX: face-normal axis; entry m = lo + 32 hi lies over cell (lo >> s) * A + (hi >> s) * B of the parent's plane
+	template <int AX>
+	__device__ __forceinline__ void issue(const GDesc32 &d, int m, int lo, int hi, const double *__restrict__ F, const double *__restrict__ uc)
+	{
+		constexpr int A = (AX == 0) ? 32 : 1, B = (AX == 2) ? 32 : 1024;
+		const uint4   o = *reinterpret_cast<const uint4 *>(&d);
+		a0 = __ldg(F + o.x + m);
+		b0 = __ldg(F + o.y + m);
+		a1 = b1 = 0.0;
+		if (PROLONG) {
+			const int fl = d.flags, sa = fl & GD_SA, sb = (fl >> 1) & 1;
+			a1 = __ldg(uc + o.z + ((lo >> sa) * A + (hi >> sa) * B));
+			b1 = __ldg(uc + o.w + ((lo >> sb) * A + (hi >> sb) * B));
+		}
+	}
+	__device__ __forceinline__ double finish(const GDesc32 &d, const PatchMeta *__restrict__ meta, int p, int s, int m, const double *__restrict__ F,
+	                                         const double *__restrict__ uc) const
+	{
+		const double c  = d.c;
+		const int    fl = d.flags;
+		double       g  = c * (0.5 * (a0 + a1) + 0.5 * (b0 + ((fl & GD_WB) ? b1 : 0.0)));
+		if (fl & GD_SLOW) g = c * gamma_entry32<PROLONG>(meta, p, s, m, F, uc);
+		return g;
+	}
+};
+
 template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C32_THREADS, 1)
 smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
@@ -303,6 +375,37 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 	int g = blockIdx.x / 2;
 	// multi-GPU: each CTA polls the peers' flags itself before the first patch whose gamma needs halo faces (HaloSync)
 	bool halo_ok = false;
+#if C32_GDESC
+	// neighbour-table entry of the patch after the next (staged with cp.async) and the gather descriptors of the next
+	// patch (GD[(it + 1) & 1]) / the one after it, resolved by lane 31 of warps 0-5
+	constexpr int                   MW = (int) (sizeof(PatchMeta) / sizeof(double));
+	__shared__ __align__(16) double metaS[MW];
+	__shared__ GPatch32             GD[2];
+	auto describe = [&](const PatchMeta &pm, int q, int slot) {
+		if (lane == 31 && w < 6) make_gdesc32<PROLONG>(pm, q, w, GD[slot]);
+	};
+	const int zlo = t & 31, zhi = t >> 5; // z-face entries t and t + 512: (x, y) = (zlo, zhi), (zlo, zhi + 16)
+	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
+		const int p = p0 + g;
+		halo_wait_cta(hs, p, halo_ok);
+		describe(meta[p], p, 0);
+		if (g + ncl < npatch) describe(meta[p + ncl], p + ncl, 1);
+		__syncthreads();
+		// all loads of the six interface values in flight at once: one memory round trip (coarse levels: one patch per cluster)
+		SideGamma32<PROLONG> g6[6];
+		g6[0].template issue<0>(GD[0].d[0], mf, lane, z, Fin, uc);
+		g6[1].template issue<0>(GD[0].d[1], mf, lane, z, Fin, uc);
+		g6[2].template issue<1>(GD[0].d[2], mf, lane, z, Fin, uc);
+		g6[3].template issue<1>(GD[0].d[3], mf, lane, z, Fin, uc);
+		g6[4].template issue<2>(GD[0].d[sz], t, zlo, zhi, Fin, uc);
+		g6[5].template issue<2>(GD[0].d[sz], t + 512, zlo, zhi + 16, Fin, uc);
+#pragma unroll
+		for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = g6[s].finish(GD[0].d[s], meta, p, s, mf, Fin, uc);
+		GZ[t]       = g6[4].finish(GD[0].d[sz], meta, p, sz, t, Fin, uc);
+		GZ[t + 512] = g6[5].finish(GD[0].d[sz], meta, p, sz, t + 512, Fin, uc);
+		__syncthreads();
+	}
+#else
 	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
 		const int    p    = p0 + g;
 		halo_wait_cta(hs, p, halo_ok);
@@ -320,12 +423,17 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 		GZ[t + 512] = g6[5].finish(meta, p, sz, t + 512, Fin, uc, cfac);
 		__syncthreads();
 	}
+#endif
 	for (int it = 0; g < npatch; g += ncl, it++) {
 		const int    p    = p0 + g;
 		const bool   next = g + ncl < npatch;
 		const int    pn   = p + ncl;
 		const double h2   = meta[p].h2;
 		double       v[N];
+#if C32_GDESC
+		// table entry of the patch after the next -> metaS (described after this iteration's first barrier)
+		if (!ZERO_GUESS && t < MW && g + 2 * ncl < npatch) cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pn + ncl) + t, true);
+#endif
 		{ // y forward: pencil (x, z) = (lane, z), straight from memory
 			const double *fp = f + (size_t) p * NC + (size_t) z * M + lane;
 #pragma unroll
@@ -366,11 +474,25 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 #pragma unroll
 			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
 		}
+#if C32_GDESC
+		if (!ZERO_GUESS) cp_async_wait_all(); // metaS has landed (made visible by the barrier)
+#endif
 		__syncthreads();
 		if (!ZERO_GUESS && next) halo_wait_cta(hs, pn, halo_ok); // gamma of patch pn is gathered from here on
 		// z: elimination step j on local plane j, in place; pencils (k_x, k_y) = (lane, w) and (lane, w + 16).
 		// The interface values of the NEXT patch are gathered around this phase (the transform registers are free here).
 		// (two batches of three: loads issued before the elimination / the back substitution, combined after it)
+#if C32_GDESC
+		SideGamma32<PROLONG> gm[3];
+		const GPatch32 &     gp = GD[(it + 1) & 1]; // descriptors of patch pn
+		if (!ZERO_GUESS && next) {
+			gm[0].template issue<0>(gp.d[0], mf, lane, z, Fin, uc);
+			gm[1].template issue<0>(gp.d[1], mf, lane, z, Fin, uc);
+			gm[2].template issue<1>(gp.d[2], mf, lane, z, Fin, uc);
+			// descriptors of the patch after the next; GD[it & 1] (patch p) was last read during the previous iteration
+			if (g + 2 * ncl < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + ncl, it & 1);
+		}
+#else
 		Gam32<PROLONG> gm[3];
 		double         cfn = 0.0;
 		if (!ZERO_GUESS && next) {
@@ -379,7 +501,8 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 #pragma unroll
 			for (int s = 0; s < 3; s++) gm[s].issue(pq, pn, s, mf, Fin, uc);
 		}
-		const double hs = h2 * (4.0 / (N * N));
+#endif
+		const double hsc = h2 * (4.0 / (N * N));
 		double *     Xo = X + (it & 1) * M;
 #if C32_ZREG
 		double       rz[2][16]; // the two pencils stay in registers across the cluster barrier (no store / reload of the eliminated planes)
@@ -393,7 +516,7 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 #pragma unroll
 			for (int j = 0; j < 16; j++) {
 				const double a = __ldg(tb + j * M);
-				const double r = zp[j * PL] * (hs * a);
+				const double r = zp[j * PL] * (hsc * a);
 				rho            = (j == 0) ? r : fma(-a, rho, r);
 #if C32_ZREG
 				rz[q][j]       = rho;
@@ -404,12 +527,20 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			Xo[ky * N + lane] = rho;
 		}
 		if (!ZERO_GUESS && next) { // (the buffers were consumed before this iteration's first barrier)
+#if C32_GDESC
+#pragma unroll
+			for (int s = 0; s < 3; s++) gxy[s * 32 + lane] = gm[s].finish(gp.d[s], meta, pn, s, mf, Fin, uc);
+			gm[0].template issue<1>(gp.d[3], mf, lane, z, Fin, uc);
+			gm[1].template issue<2>(gp.d[sz], t, zlo, zhi, Fin, uc);
+			gm[2].template issue<2>(gp.d[sz], t + 512, zlo, zhi + 16, Fin, uc);
+#else
 #pragma unroll
 			for (int s = 0; s < 3; s++) gxy[s * 32 + lane] = gm[s].finish(meta, pn, s, mf, Fin, uc, cfn);
 			const PatchMeta &pq = meta[pn];
 			gm[0].issue(pq, pn, 3, mf, Fin, uc);
 			gm[1].issue(pq, pn, sz, t, Fin, uc);
 			gm[2].issue(pq, pn, sz, t + 512, Fin, uc);
+#endif
 		}
 		cluster_sync_all(); // both halves are eliminated; the peer's last plane is readable
 #pragma unroll
@@ -435,9 +566,15 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			}
 		}
 		if (!ZERO_GUESS && next) {
+#if C32_GDESC
+			gxy[96 + lane] = gm[0].finish(gp.d[3], meta, pn, 3, mf, Fin, uc);
+			GZ[t]          = gm[1].finish(gp.d[sz], meta, pn, sz, t, Fin, uc);
+			GZ[t + 512]    = gm[2].finish(gp.d[sz], meta, pn, sz, t + 512, Fin, uc);
+#else
 			gxy[96 + lane] = gm[0].finish(meta, pn, 3, mf, Fin, uc, cfn);
 			GZ[t]          = gm[1].finish(meta, pn, sz, t, Fin, uc, cfn);
 			GZ[t + 512]    = gm[2].finish(meta, pn, sz, t + 512, Fin, uc, cfn);
+#endif
 		}
 		__syncthreads();
 		constexpr bool FACE_TAIL = C32_FACETAIL && ZERO_GUESS && !WRITE_U;
