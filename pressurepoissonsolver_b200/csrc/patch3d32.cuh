@@ -483,12 +483,20 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 		// The interface values of the NEXT patch are gathered around this phase (the transform registers are free here).
 		// (two batches of three: loads issued before the elimination / the back substitution, combined after it)
 #if C32_GDESC
-		SideGamma32<PROLONG> gm[3];
+#ifndef C32_GATHER6
+#define C32_GATHER6 0 // 1: all six sides' loads in flight across the whole z phase instead of two batches of three (measured: -5 % on the sweeps without prolongation, none with it, and spills)
+#endif
+		SideGamma32<PROLONG> gm[C32_GATHER6 ? 6 : 3];
 		const GPatch32 &     gp = GD[(it + 1) & 1]; // descriptors of patch pn
 		if (!ZERO_GUESS && next) {
 			gm[0].template issue<0>(gp.d[0], mf, lane, z, Fin, uc);
 			gm[1].template issue<0>(gp.d[1], mf, lane, z, Fin, uc);
 			gm[2].template issue<1>(gp.d[2], mf, lane, z, Fin, uc);
+#if C32_GATHER6
+			gm[3].template issue<1>(gp.d[3], mf, lane, z, Fin, uc);
+			gm[4].template issue<2>(gp.d[sz], t, zlo, zhi, Fin, uc);
+			gm[5].template issue<2>(gp.d[sz], t + 512, zlo, zhi + 16, Fin, uc);
+#endif
 			// descriptors of the patch after the next; GD[it & 1] (patch p) was last read during the previous iteration
 			if (g + 2 * ncl < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + ncl, it & 1);
 		}
@@ -527,7 +535,9 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			Xo[ky * N + lane] = rho;
 		}
 		if (!ZERO_GUESS && next) { // (the buffers were consumed before this iteration's first barrier)
-#if C32_GDESC
+#if C32_GDESC && C32_GATHER6
+			// (nothing here: the six values are combined after the back substitution)
+#elif C32_GDESC
 #pragma unroll
 			for (int s = 0; s < 3; s++) gxy[s * 32 + lane] = gm[s].finish(gp.d[s], meta, pn, s, mf, Fin, uc);
 			gm[0].template issue<1>(gp.d[3], mf, lane, z, Fin, uc);
@@ -566,7 +576,12 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 			}
 		}
 		if (!ZERO_GUESS && next) {
-#if C32_GDESC
+#if C32_GDESC && C32_GATHER6
+#pragma unroll
+			for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = gm[s].finish(gp.d[s], meta, pn, s, mf, Fin, uc);
+			GZ[t]       = gm[4].finish(gp.d[sz], meta, pn, sz, t, Fin, uc);
+			GZ[t + 512] = gm[5].finish(gp.d[sz], meta, pn, sz, t + 512, Fin, uc);
+#elif C32_GDESC
 			gxy[96 + lane] = gm[0].finish(gp.d[3], meta, pn, 3, mf, Fin, uc);
 			GZ[t]          = gm[1].finish(gp.d[sz], meta, pn, sz, t, Fin, uc);
 			GZ[t + 512]    = gm[2].finish(gp.d[sz], meta, pn, sz, t + 512, Fin, uc);

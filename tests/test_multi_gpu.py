@@ -113,3 +113,54 @@ def test_distributed_cycle_specialised_kernels_match_oracle(n, divide):
     ref = go.vcycle(levels, fn)
     assert rel_l2(gather("vcycle"), ref.reshape(-1, n ** 3)) < 1e-12
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
+
+
+def _replicated_worker(rank, world, idfile, ret):
+    sys.path.insert(0, ROOT)
+    import time
+    import pressurepoissonsolver_b200 as pps
+    ctx = pps.Context(rank)
+    if rank == 0:
+        uid = pps.comm_unique_id()
+        with open(idfile + ".tmp", "wb") as fh:
+            fh.write(uid)
+        os.rename(idfile + ".tmp", idfile)
+    else:
+        while not os.path.exists(idfile):
+            time.sleep(0.05)
+        uid = open(idfile, "rb").read()
+    ctx.comm_init(uid, rank, world)
+    mesh = pps.Mesh.load(os.path.join(MESHES, "2uni.bin"), 3)
+    part = pps.Partition(mesh, 8, rank, world, min_patches_per_rank=64)  # 8 patches < world * 64: every level replicated
+    h = pps.Hierarchy.from_partition(ctx, part)
+    f, u = h.new_vec(0), h.new_vec(0)
+    h.init_trig_rhs(f)
+    h.vcycle(f, u)
+    ret[rank] = {"ndist": part.ndist, "integral": h.integrate(f), "fnorm": f.two_norm(), "u": u.download()}
+    h.close()
+    ctx.close()
+
+
+def test_replicated_hierarchy_sums_are_not_multiplied_by_the_rank_count():
+    """a mesh too small to distribute (ndist == 0): every rank owns every patch, so Domain::integrate / volume and the
+    norms must come out once, not nranks times (no all-reduce on replicated levels)"""
+    world = min(_ngpu(), 2)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import tempfile
+    import torch.multiprocessing as mp
+    mpc = mp.get_context("spawn")
+    ret = mpc.Manager().dict()
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [mpc.Process(target=_replicated_worker, args=(r, world, os.path.join(tmp, "id"), ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+            assert p.exitcode == 0
+    g = load_golden("3d_2uni_n8")
+    for r in range(world):
+        assert ret[r]["ndist"] == 0
+        assert abs(ret[r]["integral"][1] - 1.0) < 1e-13  # volume of the unit cube
+        assert abs(ret[r]["fnorm"] / np.linalg.norm(g["rhs_f"]) - 1) < 1e-13
+        assert rel_l2(ret[r]["u"], g["vcycle"]) < 1e-12
