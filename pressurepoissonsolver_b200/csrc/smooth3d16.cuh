@@ -36,6 +36,26 @@ __device__ __forceinline__ void     cp_async16(double *smem_dst, const double *g
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// L2 residency hint experiment: the face buffers (50 MB on config B) are re-read by the next two kernels of the cycle, the
+// patch data streaming past them (f, u: 134 MB each) is not.  S16_L2HINT=1 stores the faces with an evict_last policy;
+// measured on configs B and C: no change (0.2242 vs 0.2251 ms, 0.5788 vs 0.5788 ms), so it stays off.
+#ifndef S16_L2HINT
+#define S16_L2HINT 0
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ void st_keep_l2(double *p, double v, uint64_t pol)
+{
+#if S16_L2HINT
+	asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;\n" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+	*p = v;
+#endif
+}
 constexpr int    S16_BLOCK = TGPU_THREADS; // threads per CTA (the host launches with this)
 constexpr int    S16_ROW = 18, S16_PL = 290, S16_TILE = 16 * S16_PL;
 // Sweeps from a zero guess have no interface values to fold into the right-hand side, so f needs no staging:
@@ -261,6 +281,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	const int npatch = P - p0;
 	Mags<N> mg;
 	mg.load();
+	const uint64_t l2keep = l2_policy_evict_last();
 	pdl_launch_dependents();
 	pdl_wait();
 
@@ -442,23 +463,23 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			for (int k = 0; k < N; k++) __stcs(up + k * G::M, v[k]); // streaming store: u is not read again soon, the face buffers should stay in L2
 			if (EMIT) {
 				double *Fp       = Fout + (size_t) p * G::S * G::M;
-				Fp[4 * G::M + t] = v[0];
-				Fp[5 * G::M + t] = v[N - 1];
+				st_keep_l2(&Fp[4 * G::M + t], v[0], l2keep);
+				st_keep_l2(&Fp[5 * G::M + t], v[N - 1], l2keep);
 				if (lo == 0) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[0 * G::M + k * N + hi] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[0 * G::M + k * N + hi], v[k], l2keep);
 				}
 				if (lo == N - 1) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[1 * G::M + k * N + hi] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[1 * G::M + k * N + hi], v[k], l2keep);
 				}
 				if (hi == 0) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[2 * G::M + k * N + lo] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[2 * G::M + k * N + lo], v[k], l2keep);
 				}
 				if (hi == N - 1) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[3 * G::M + k * N + lo] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[3 * G::M + k * N + lo], v[k], l2keep);
 				}
 			}
 		} else {
@@ -487,23 +508,23 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 #pragma unroll
 				for (int k = 0; k < N; k++) v[k] = q[k * PL];
 				dst3_inverse<N>(v, mg);
-				Fp[4 * G::M + x + N * y] = v[0];
-				Fp[5 * G::M + x + N * y] = v[N - 1];
+				st_keep_l2(&Fp[4 * G::M + x + N * y], v[0], l2keep);
+				st_keep_l2(&Fp[5 * G::M + x + N * y], v[N - 1], l2keep);
 				if (x == 0) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[0 * G::M + k * N + y] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[0 * G::M + k * N + y], v[k], l2keep);
 				}
 				if (x == N - 1) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[1 * G::M + k * N + y] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[1 * G::M + k * N + y], v[k], l2keep);
 				}
 				if (y == 0) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[2 * G::M + k * N + x] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[2 * G::M + k * N + x], v[k], l2keep);
 				}
 				if (y == N - 1) {
 #pragma unroll
-					for (int k = 0; k < N; k++) Fp[3 * G::M + k * N + x] = v[k];
+					for (int k = 0; k < N; k++) st_keep_l2(&Fp[3 * G::M + k * N + x], v[k], l2keep);
 				}
 			} else {
 				const int     idx = t - 64, x = 1 + idx % 14, y = 1 + idx / 14;
@@ -514,8 +535,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 					E = fma(mg.sinq(j + 1), q[j * PL], E);
 					O = fma((j + 1 == N - 1) ? 0.5 : mg.sinq(j + 2), q[(j + 1) * PL], O);
 				}
-				Fp[4 * G::M + x + N * y] = E + O;
-				Fp[5 * G::M + x + N * y] = E - O;
+				st_keep_l2(&Fp[4 * G::M + x + N * y], E + O, l2keep);
+				st_keep_l2(&Fp[5 * G::M + x + N * y], E - O, l2keep);
 			}
 		}
 		if (!ZERO_GUESS && next) {
