@@ -441,21 +441,22 @@ def multi_gpu_parity(env):
         h.close()
         part.close()
         mesh.close()
-    for n, mesh_file, divide in ((16, "2refine.bin", 1), (32, "2refine.bin", 1)):
-        mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), 3).refine_leaves(divide)
+    for D, n, mesh_file, divide in ((3, 16, "2refine.bin", 1), (3, 32, "2refine.bin", 1), (2, 32, "2d_multi_refine_8.bin", 1)):
+        mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
         h1 = pps.Hierarchy.from_mesh(env.ctx, mesh, n)  # the whole mesh on this GPU
         f1, u1 = h1.new_vec(0), h1.new_vec(0)
         h1.init_trig_rhs(f1)
         h1.vcycle(f1, u1)
-        ref = u1.download().reshape(-1, n ** 3)
-        fg = f1.download().reshape(-1, n ** 3)
+        ref = u1.download().reshape(-1, n ** D)
+        fg = f1.download().reshape(-1, n ** D)
         h1.close()
         part = pps.Partition(mesh, n, env.rank, env.world, min_patches_per_rank=2)
         h = pps.Hierarchy.from_partition(env.ctx, part)
         own = part.level(0)["owned_global"]
         f, u = h.new_vec(0, fg[own]), h.new_vec(0)
         h.vcycle(f, u, pps.CycleOpts.default(use_graph=2))
-        out["vs_single_gpu_n%d" % n] = {"rel_l2": rel(u.download().reshape(-1, n ** 3), ref[own]), "distributed_levels": part.ndist}
+        h.vcycle(f, u, pps.CycleOpts.default(use_graph=2))  # replayed graph
+        out["vs_single_gpu_%dd_n%d" % (D, n)] = {"rel_l2": rel(u.download().reshape(-1, n ** D), ref[own]), "distributed_levels": part.ndist}
         h.close()
         part.close()
         mesh.close()

@@ -121,6 +121,14 @@ __device__ __forceinline__ void halo_wait_cta(const HaloSync &hs, int p, bool &w
 	__syncthreads();
 	waited = true;
 }
+// warp-wide form for kernels whose warps work on patches independently (every lane of the warp calls)
+__device__ __forceinline__ void halo_wait_warp(const HaloSync &hs, int p, bool &waited)
+{
+	if (!hs.enabled || waited || p < hs.first_halo_patch) return; // warp-uniform
+	if ((threadIdx.x & 31) == 0) halo_poll(hs.data_flags, hs.peer_rank, hs.npeers, hs.cnt, hs.abort, hs.host_err);
+	__syncwarp();
+	waited = true;
+}
 // end of the kernel: the last CTA to finish advances "data awaited" and acknowledges the halo to the peers (one thread; out
 // of line, the fences and the release stores are cold code)
 __device__ __noinline__ void halo_finish_thread0(unsigned *ticket, unsigned nctas, int *abort, uint64_t *cnt, uint64_t *const *peer_ack_flag, int npeers)
@@ -1108,7 +1116,7 @@ __device__ __forceinline__ void frr_patch(const PatchMeta *__restrict__ meta, in
 template <int D, int N, bool DIFF>
 __global__ void __launch_bounds__(TGPU_THREADS)
 face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
-                              const double *__restrict__ Fold, double *__restrict__ coarse)
+                              const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
 {
 	using G = Geo<D, N>;
 	pdl_launch_dependents();
@@ -1116,10 +1124,13 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
 	__shared__ double R[G::PPB][G::S][G::M];
 	const int t = threadIdx.x, pp = t / G::M, m = t % G::M;
 	const int nblk = (P - p0 + G::PPB - 1) / G::PPB;
+	bool      halo_ok = false;
 	for (int g = blockIdx.x; g < nblk; g += gridDim.x) {
 		const int p = p0 + g * G::PPB + pp;
+		halo_wait_cta(hs, p0 + g * G::PPB + G::PPB - 1, halo_ok); // the last patch of the group decides for the whole CTA
 		frr_patch<D, N, DIFF>(meta, p, p < P, m, R[pp], Fnew, Fold, coarse);
 	}
+	halo_finish(hs);
 }
 // D = 3, N = 16: refined patches whose six sides have same-level neighbours (or none) -- every patch of a uniform
 // level -- go through a leaner path: one thread per COARSE face entry (6 x 64 per patch) loads its 2 x 2 block of the

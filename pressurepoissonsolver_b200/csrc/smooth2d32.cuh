@@ -68,7 +68,7 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __launch_bounds__(TGPU_THREADS, 2)
 smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
-                  const double *__restrict__ uc)
+                  const double *__restrict__ uc, HaloSync hs = HaloSync{})
 {
 	constexpr int N = 32, ROW = Q32_ROW, NC = N * N;
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
@@ -84,8 +84,10 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	const int npatch = P - p0, nw = gridDim.x * Q32_WARPS;
 	int       g = blockIdx.x * Q32_WARPS + w;
 	double    gy0 = 0.0, gy1 = 0.0; // (2/h^2) gamma of entry x = lane on the two y faces
+	bool      halo_ok = false;      // multi-GPU: the warp polls the peers' flags before its first patch that needs halo faces
 	if (!ZERO_GUESS && g < npatch) { // the warp's first patch: nothing to hide the gathers behind
 		const int    p    = p0 + g;
+		halo_wait_warp(hs, p, halo_ok);
 		const double cfac = 2.0 * meta[p].inv_h2;
 		GX[lane]      = cfac * gamma_entry2d32<PROLONG>(meta, p, 0, lane, Fin, uc);
 		GX[32 + lane] = cfac * gamma_entry2d32<PROLONG>(meta, p, 1, lane, Fin, uc);
@@ -99,6 +101,7 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		const int    pn   = p + nw;
 		const double h2   = meta[p].h2;
 		double       v[N];
+		if (!ZERO_GUESS && next) halo_wait_warp(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
 		Gam2d32<PROLONG> ga, gb;
 		double           cfn = 0.0;
 		{ // y forward: column x = lane, straight from memory
@@ -185,5 +188,6 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		}
 		__syncwarp();
 	}
+	if (!ZERO_GUESS) halo_finish(hs);
 }
 } // namespace tgpu

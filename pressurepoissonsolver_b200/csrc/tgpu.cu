@@ -1508,7 +1508,8 @@ static bool halo_in_kernel(const tgpu_hier *h, int l)
 {
 	static const bool off = getenv("TGPU_HALO_IN_KERNEL") && atoi(getenv("TGPU_HALO_IN_KERNEL")) == 0;
 	const LevelDev &  L   = h->levels[l];
-	return !off && L.p2p && h->D == 3 && (h->N == 16 || h->N == 32) && !h->generic_kernels && !L.has_neumann && h->lambda == 0.0;
+	const bool kernels = (h->D == 3 && (h->N == 16 || h->N == 32)) || (h->D == 2 && h->N == 32); // smoothers + face residuals that take a HaloSync
+	return !off && L.p2p && kernels && !h->generic_kernels && !L.has_neumann && h->lambda == 0.0;
 }
 static HaloSync halo_sync(tgpu_hier *h, int l)
 {
@@ -1692,7 +1693,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm  = smooth2d32_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 #define Q32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc);
+	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs);
 		switch (key) {
 			Q32_CASE(8 | 4 | 1, true, true, false, true)
 			Q32_CASE(8 | 1, true, false, false, true)
@@ -1747,8 +1748,8 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
 		const dim3 grid(std::min(nblk, h->ctx->sm_count * 8)), block(TGPU_THREADS);
-		if (Fold) return launch(h->ctx, face_residual_restrict_kernel<DD, NN, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
-		return launch(h->ctx, face_residual_restrict_kernel<DD, NN, false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse);
+		if (Fold) return launch(h->ctx, face_residual_restrict_kernel<DD, NN, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		return launch(h->ctx, face_residual_restrict_kernel<DD, NN, false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	});
 }
 static int k_restrict(tgpu_hier *h, int l, const double *fine, double *coarse)

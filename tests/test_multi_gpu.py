@@ -18,7 +18,8 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret):
+def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret, env=None):
+    os.environ.update(env or {})  # exchange-path switches are read when the library first needs them
     sys.path.insert(0, ROOT)
     import time
     import pressurepoissonsolver_b200 as pps
@@ -60,14 +61,14 @@ def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret):
     ctx.close()
 
 
-def run_distributed(world, mesh_file, D, n, divide, f_global):
+def run_distributed(world, mesh_file, D, n, divide, f_global, env=None):
     import tempfile
     import torch.multiprocessing as mp
     mpc = mp.get_context("spawn")
     ret = mpc.Manager().dict()
     with tempfile.TemporaryDirectory() as tmp:
         idfile = os.path.join(tmp, "nccl_id")
-        procs = [mpc.Process(target=_worker, args=(r, world, idfile, mesh_file, D, n, divide, f_global, ret)) for r in range(world)]
+        procs = [mpc.Process(target=_worker, args=(r, world, idfile, mesh_file, D, n, divide, f_global, ret, env)) for r in range(world)]
         for p in procs:
             p.start()
         for p in procs:
@@ -97,21 +98,38 @@ def test_distributed_cycle_matches_reference(name):
     assert rel_l2(gather("x"), g["bicgstab_u"]) < 1e-10
 
 
-@pytest.mark.parametrize("n,divide", [(16, 1), (32, 0)])
-def test_distributed_cycle_specialised_kernels_match_oracle(n, divide):
-    """The D = 3 kernels specialised for 16^3 (smooth3d16) and 32^3 (cluster-pair smooth3d32c) patches, launched on
-    interior / boundary patch ranges with halo faces from the peers, against the oracle on a refined octree."""
+@pytest.mark.parametrize("mesh_file,D,n,divide", [("2refine.bin", 3, 16, 1), ("2refine.bin", 3, 32, 0), ("2d_multi_refine_8.bin", 2, 32, 0)])
+def test_distributed_cycle_specialised_kernels_match_oracle(mesh_file, D, n, divide):
+    """The kernels specialised for 16^3 (smooth3d16), 32^3 (cluster-pair smooth3d32c) and 2D 32^2 (smooth2d32) patches with the
+    in-kernel halo hand-over (one launch over interior + boundary patches, CTAs / warps poll the peers' flags themselves),
+    against the oracle on refined meshes."""
     world = min(_ngpu(), 2)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import gmg_oracle as go
-    levels = go.build_hierarchy(os.path.join(MESHES, "2refine.bin"), 3, n, divide)
+    levels = go.build_hierarchy(os.path.join(MESHES, mesh_file), D, n, divide)
     fn = np.random.default_rng(11).standard_normal(levels[0].shape)
-    ret, gather, ncells = run_distributed(world, "2refine.bin", 3, n, divide, fn)
+    ret, gather, ncells = run_distributed(world, mesh_file, D, n, divide, fn)
     assert ret[0]["ndist"] >= 1 and ncells == fn.size
     ref = go.vcycle(levels, fn)
-    assert rel_l2(gather("vcycle"), ref.reshape(-1, n ** 3)) < 1e-12
+    assert rel_l2(gather("vcycle"), ref.reshape(-1, n ** D)) < 1e-12
+    assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
+
+
+@pytest.mark.parametrize("env", [{"TGPU_HALO_IN_KERNEL": "0"}, {"TGPU_P2P": "0"}])
+def test_alternative_exchange_paths_match_reference(env):
+    """the exchange paths behind the diagnostic switches - separate wait / signal kernels with split interior / boundary
+    launches, and pack -> ncclSend/ncclRecv -> unpack (the fallback when peer mapping is unavailable) - give the same cycle"""
+    world = min(_ngpu(), 2)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gmg_oracle as go
+    levels = go.build_hierarchy(os.path.join(MESHES, "2refine.bin"), 3, 16, 1)
+    fn = np.random.default_rng(12).standard_normal(levels[0].shape)
+    ret, gather, ncells = run_distributed(world, "2refine.bin", 3, 16, 1, fn, env=env)
+    assert rel_l2(gather("vcycle"), go.vcycle(levels, fn).reshape(-1, 16 ** 3)) < 1e-12
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
 
 
