@@ -228,7 +228,8 @@ template <int N> struct Mags {
 #endif
 template <int H> __device__ __forceinline__ void dst4_fast(const double (&x)[H], double (&y)[H])
 {
-	if constexpr (H == 16) dst4_16(x, y);
+	if constexpr (H == 32) dst4_32(x, y);
+	else if constexpr (H == 16) dst4_16(x, y);
 	else if constexpr (H == 8) dst4_8(x, y);
 }
 // DST-II of a register pencil.  S[k][j] = sin(pi (k+1)(2j+1) / 2n)  (DftPatchSolver.h:262-268).
@@ -612,12 +613,49 @@ __device__ __forceinline__ AxisKind axis_kind(int neumann_bits, int axis)
 template <int N>
 __device__ __forceinline__ void dense_to_smem(const double *__restrict__ T, const double (&v)[N], double *q, int step)
 {
+	// two rows per trip, matrix rows read 16 bytes at a time (every thread of the patch reads the same address: one
+	// broadcast request per load); the sums run over j in the same order as the scalar form
 #pragma unroll 1
-	for (int k = 0; k < N; k++) {
-		double acc = 0.0;
+	for (int k = 0; k < N; k += 2) {
+		const double2 *r0 = reinterpret_cast<const double2 *>(T + k * N), *r1 = reinterpret_cast<const double2 *>(T + (k + 1) * N);
+		double         a0 = 0.0, a1 = 0.0;
 #pragma unroll
-		for (int j = 0; j < N; j++) acc = fma(__ldg(T + k * N + j), v[j], acc);
-		q[k * step] = acc;
+		for (int j = 0; j < N / 2; j++) {
+			const double2 t0 = __ldg(r0 + j), t1 = __ldg(r1 + j);
+			a0 = fma(t0.x, v[2 * j], a0);
+			a0 = fma(t0.y, v[2 * j + 1], a0);
+			a1 = fma(t1.x, v[2 * j], a1);
+			a1 = fma(t1.y, v[2 * j + 1], a1);
+		}
+		q[k * step]       = a0;
+		q[(k + 1) * step] = a1;
+	}
+}
+
+// One axis of the general patch solve: y = T_kind v, stored to q[k * step].  The four kinds that occur on a patch with at
+// most one Neumann side per axis have fast forms: DST-II / DST-III (the Dirichlet transforms of the plain path) and, for
+// n = 8, 16 and 32, DST-IV (generated FFT-based code, dst4_fast.cuh) and DCT-IV = DST-IV of the reversed input with alternating
+// signs (cos(pi (2k+1)(2j+1) / 4n) = (-1)^k sin(pi (2k+1)(2(n-1-j)+1) / 4n)).  DCT-II / DCT-III (Neumann on both sides of an
+// axis: patches that span the whole domain) and the other sizes keep the dense matrix (DftPatchSolver.h:237-289).
+template <int N>
+__device__ __forceinline__ void general_transform(const double *__restrict__ mats, int kind, double (&v)[N], double *q, int step, const Mags<N> &mg)
+{
+	constexpr bool FAST4 = TGPU_FAST_DST4 && (N == 32 || N == 16 || N == 8);
+	if (kind == TK_DST_II || kind == TK_DST_III) {
+		if (kind == TK_DST_II) dst2_forward<N>(v, mg);
+		else dst3_inverse<N>(v, mg);
+#pragma unroll
+		for (int k = 0; k < N; k++) q[k * step] = v[k];
+	} else if (FAST4 && (kind == TK_DST_IV || kind == TK_DCT_IV)) {
+		const bool c4 = kind == TK_DCT_IV;
+		double     x[N], y[N];
+#pragma unroll
+		for (int j = 0; j < N; j++) x[j] = c4 ? v[N - 1 - j] : v[j];
+		dst4_fast<N>(x, y);
+#pragma unroll
+		for (int k = 0; k < N; k++) q[k * step] = (c4 && (k & 1)) ? -y[k] : y[k];
+	} else {
+		dense_to_smem<N>(mats + kind * N * N, v, q, step);
 	}
 }
 
@@ -634,8 +672,11 @@ template <int D, int N, bool ZERO_GUESS, bool EMIT, bool PROLONG>
 __global__ void __launch_bounds__(TGPU_THREADS, smooth_min_blocks<N>())
 smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
               const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-              const double *__restrict__ uc, const double *__restrict__ mats, const double *__restrict__ lam, double lam_shift)
+              const double *__restrict__ uc, const double *__restrict__ mats, const double *__restrict__ lam, double lam_shift,
+              int only_neumann = 0)
 {
+	// only_neumann != 0: only patches with Neumann domain sides are swept - the others of the range belong to a specialised
+	// kernel launched over the same range (smooth3d16_kernel / smooth2d32_kernel with skip_neumann)
 	// lam_shift: the patch solver's "lambda" (FftwPatchSolver.h:66,170, DftPatchSolver.h:78,168): the patch problems are
 	// (Laplacian + lambda) u = rhs; != 0 sends every patch through the general transform path, whose eigenvalue sums are
 	// formed on the fly
@@ -659,8 +700,15 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 	Mags<N> mg;
 	mg.load();
 
+	auto mine = [&](int g) { // does this CTA sweep group g at all?  (CTA-uniform: any patch of the group with Neumann sides)
+		if (!only_neumann) return true;
+		bool any = false;
+		for (int k = 0; k < G::PPB; k++) any = any || (p0 + g * G::PPB + k < P && meta[p0 + g * G::PPB + k].neumann != 0);
+		return any;
+	};
 	auto prefetch = [&](int g, double *Sdst) {
 		const int pb = p0 + g * G::PPB;
+		if (!mine(g)) return;
 #pragma unroll
 		for (int k = 0; k < N; k++) {
 			const int  e  = t + TGPU_THREADS * k;
@@ -677,16 +725,17 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 	for (int it = 0; g < nblk; g += gridDim.x, it++) {
 		double *   Sall  = (it & 1) ? Sbuf1 : Sbuf0;
 		const int  p     = p0 + g * G::PPB + pp;
-		const bool valid = p < P;
+		const bool valid = p < P && (!only_neumann || meta[p].neumann != 0); // only_neumann: the other patches of the group idle
 		// the other buffer was last read in the previous iteration, before its closing barrier
 		if (g + (int) gridDim.x < nblk) {
 			prefetch(g + gridDim.x, (it & 1) ? Sbuf0 : Sbuf1);
-			if (!ZERO_GUESS) { // pull the faces the next group's gamma needs into L2 one iteration ahead
+			if (!ZERO_GUESS && mine(g + gridDim.x)) { // pull the faces the next group's gamma needs into L2 one iteration ahead
 				const int pn = p0 + (g + gridDim.x) * G::PPB + pp;
 				if (pn < P) prefetch_faces_l2<D, N>(meta, pn, m, Fin);
 			}
 		}
 		cp_async_commit();
+		if (!mine(g)) continue; // (no barrier has been passed in this iteration; the buffers alternate as before)
 
 		double *S = Sall + pp * G::SP;
 		double  cfac = 0.0, h2 = 0.0;
@@ -742,7 +791,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 				if (ntype[G::S - 1] != NBR_NONE) v[N - 1] -= gam[G::S - 1];
 			}
 			if (general) {
-				dense_to_smem<N>(mats + axis_kind(neu, D - 1).fwd * N * N, v, S + base, step);
+				general_transform<N>(mats, axis_kind(neu, D - 1).fwd, v, S + base, step, mg);
 			} else {
 				dst2_forward<N>(v, mg);
 #pragma unroll
@@ -755,7 +804,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
 			if (general) {
-				dense_to_smem<N>(mats + axis_kind(neu, 1).fwd * N * N, v, S + base, G::ROW);
+				general_transform<N>(mats, axis_kind(neu, 1).fwd, v, S + base, G::ROW, mg);
 			} else {
 				dst2_forward<N>(v, mg);
 #pragma unroll
@@ -769,7 +818,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 			for (int k = 0; k < N; k++) v[k] = S[m * G::ROW + k];
 			if (general) {
 				const AxisKind kx = axis_kind(neu, 0), ky = axis_kind(neu, 1), kz = axis_kind(neu, 2);
-				dense_to_smem<N>(mats + kx.fwd * N * N, v, S + m * G::ROW, 1);
+				general_transform<N>(mats, kx.fwd, v, S + m * G::ROW, 1, mg);
 				// eigenvalue sum of row m = (k_y, k_z) (2D: k_y) on the fly; scale (2/N)^D as in DftPatchSolver.h:214
 				const double rest  = (D == 2) ? __ldg(lam + ky.lam * N + m) : __ldg(lam + ky.lam * N + m % N) + __ldg(lam + kz.lam * N + m / N);
 				double       scale = h2;
@@ -781,7 +830,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 					const double sum = __ldg(lam + kx.lam * N + k) + rest + lam_shift * h2;
 					v[k]             = (singular && k == 0 && m == 0) ? 0.0 : S[m * G::ROW + k] * scale / sum;
 				}
-				dense_to_smem<N>(mats + kx.inv * N * N, v, S + m * G::ROW, 1);
+				general_transform<N>(mats, kx.inv, v, S + m * G::ROW, 1, mg);
 			} else {
 #if TGPU_S16_TRIDIAG
 				// the other axes are diagonalised: row m is a tridiagonal system along x (TriSolve); eig = multiplier table
@@ -805,7 +854,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * G::ROW];
 			if (general) {
-				dense_to_smem<N>(mats + axis_kind(neu, 1).inv * N * N, v, S + base, G::ROW);
+				general_transform<N>(mats, axis_kind(neu, 1).inv, v, S + base, G::ROW, mg);
 			} else {
 				dst3_inverse<N>(v, mg);
 #pragma unroll
@@ -820,7 +869,7 @@ smooth_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *_
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = S[base + k * step];
 			if (general) { // general path: transform through the pencil's own slots, then pick the result up again
-				dense_to_smem<N>(mats + axis_kind(neu, D - 1).inv * N * N, v, S + base, step);
+				general_transform<N>(mats, axis_kind(neu, D - 1).inv, v, S + base, step, mg);
 #pragma unroll
 				for (int k = 0; k < N; k++) v[k] = S[base + k * step];
 			}

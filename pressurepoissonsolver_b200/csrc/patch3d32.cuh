@@ -292,6 +292,7 @@ struct __align__(16) GDesc32 {
 };
 struct GPatch32 {
 	GDesc32 d[6];
+	int     neu, pad[3]; // Neumann bits of the patch (levels with Neumann patches: the cluster kernel skips them)
 };
 template <bool PROLONG>
 __device__ __forceinline__ void make_gdesc32(const PatchMeta &pm, int p, int s, GPatch32 &out)
@@ -351,8 +352,10 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C32_THREADS, 1)
 smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                    const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
-                   const double *__restrict__ uc, HaloSync hs = HaloSync{})
+                   const double *__restrict__ uc, HaloSync hs = HaloSync{}, int skip_neumann = 0)
 {
+	// skip_neumann != 0: patches with Neumann domain sides are left to smooth3d32n_kernel (launched over the same range
+	// with only_neumann); both CTAs of the cluster skip together and keep gathering the next patch's interface values
 	constexpr int N = 32, ROW = C32_ROW, PL = C32_PL, M = N * N, NC = N * N * N;
 	extern __shared__ __align__(16) double S[];
 	double *       X    = S + C32_TILE;  // [2][M] last eliminated plane, for the peer
@@ -383,6 +386,7 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 	__shared__ GPatch32             GD[2];
 	auto describe = [&](const PatchMeta &pm, int q, int slot) {
 		if (lane == 31 && w < 6) make_gdesc32<PROLONG>(pm, q, w, GD[slot]);
+		if (lane == 31 && w == 6) GD[slot].neu = pm.neumann;
 	};
 	const int zlo = t & 31, zhi = t >> 5; // z-face entries t and t + 512: (x, y) = (zlo, zhi), (zlo, zhi + 16)
 	if (!ZERO_GUESS && g < npatch) { // first patch of this cluster: nothing to hide the gathers behind
@@ -433,6 +437,32 @@ smooth3d32c_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 #if C32_GDESC
 		// table entry of the patch after the next -> metaS (described after this iteration's first barrier)
 		if (!ZERO_GUESS && t < MW && g + 2 * ncl < npatch) cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pn + ncl) + t, true);
+		if (skip_neumann && (ZERO_GUESS ? meta[p].neumann : GD[it & 1].neu)) { // cluster-uniform: this patch belongs to the general path
+			if (!ZERO_GUESS) {
+				// keep the pipeline of the next patch's interface values going: all six at once, nothing to hide behind
+				cp_async_wait_all();
+				__syncthreads(); // metaS has landed; gxy / GZ of this (skipped) patch are free
+				const GPatch32 &gq = GD[(it + 1) & 1];
+				if (next) {
+					halo_wait_cta(hs, pn, halo_ok);
+					SideGamma32<PROLONG> s6[6];
+					s6[0].template issue<0>(gq.d[0], mf, lane, z, Fin, uc);
+					s6[1].template issue<0>(gq.d[1], mf, lane, z, Fin, uc);
+					s6[2].template issue<1>(gq.d[2], mf, lane, z, Fin, uc);
+					s6[3].template issue<1>(gq.d[3], mf, lane, z, Fin, uc);
+					s6[4].template issue<2>(gq.d[sz], t, zlo, zhi, Fin, uc);
+					s6[5].template issue<2>(gq.d[sz], t + 512, zlo, zhi + 16, Fin, uc);
+#pragma unroll
+					for (int s = 0; s < 4; s++) gxy[s * 32 + lane] = s6[s].finish(gq.d[s], meta, pn, s, mf, Fin, uc);
+					GZ[t]       = s6[4].finish(gq.d[sz], meta, pn, sz, t, Fin, uc);
+					GZ[t + 512] = s6[5].finish(gq.d[sz], meta, pn, sz, t + 512, Fin, uc);
+					if (g + 2 * ncl < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + ncl, it & 1);
+				}
+				__syncthreads(); // the values and descriptors are visible to the next iteration
+			}
+			cluster_sync_all(); // keeps the pair in step: the exchange planes alternate by iteration parity
+			continue;
+		}
 #endif
 		{ // y forward: pencil (x, z) = (lane, z), straight from memory
 			const double *fp = f + (size_t) p * NC + (size_t) z * M + lane;
@@ -696,17 +726,22 @@ __global__ void __launch_bounds__(TGPU_THREADS)
 smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                    const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ uc,
                    const double *__restrict__ mats, const double *__restrict__ lam, double *__restrict__ scratch, int zero_guess,
-                   int emit, int prolong, int write_u, double lam_shift)
+                   int emit, int prolong, int write_u, double lam_shift, int only_neumann = 0)
 {
+	// only_neumann != 0: only patches with Neumann domain sides are swept (the others of the range belong to
+	// smooth3d32c_kernel, skip_neumann)
 	constexpr int N = 32, M = N * N, NC = M * N;
 	const int     t = threadIdx.x;
 	double *      W = scratch + (size_t) blockIdx.x * NC;
+	Mags<N>       mg;
+	mg.load();
 	pdl_launch_dependents();
 	pdl_wait();
 	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
 		const int        p    = p0 + g;
 		const PatchMeta &pm   = meta[p];
 		const int        neu  = pm.neumann;
+		if (only_neumann && !neu) continue; // CTA-uniform
 		const double     cfac = 2.0 * pm.inv_h2, h2 = pm.h2;
 		for (int i = t; i < NC; i += TGPU_THREADS) W[i] = __ldg(f + (size_t) p * NC + i);
 		__syncthreads();
@@ -728,8 +763,7 @@ smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 		for (int pass = 0; pass < 6; pass++) {
 			const int      axis = pass < 3 ? 2 - pass : pass - 3;
 			const AxisKind ak   = axis_kind(neu, axis);
-			const double * T    = mats + (size_t) (pass < 3 ? ak.fwd : ak.inv) * N * N;
-			const int      step = axis == 0 ? 1 : (axis == 1 ? N : M);
+				const int      step = axis == 0 ? 1 : (axis == 1 ? N : M);
 			if (pass == 3) {
 				const AxisKind kx = axis_kind(neu, 0), ky = axis_kind(neu, 1), kz = axis_kind(neu, 2);
 				const double   scale = h2 * (2.0 / N) * (2.0 / N) * (2.0 / N);
@@ -744,13 +778,8 @@ smooth3d32n_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doub
 				const int base = axis == 0 ? q * N : (axis == 1 ? (q % N) + (q / N) * M : q);
 #pragma unroll
 				for (int j = 0; j < N; j++) v[j] = W[base + j * step];
-#pragma unroll 1
-				for (int k = 0; k < N; k++) {
-					double acc = 0.0;
-#pragma unroll
-					for (int j = 0; j < N; j++) acc = fma(__ldg(T + k * N + j), v[j], acc);
-					W[base + k * step] = acc;
-				}
+				// fast forms for DST-II / III and DST-IV / DCT-IV, the dense matrix for DCT-II / III (kernels.cuh)
+				general_transform<N>(mats, pass < 3 ? ak.fwd : ak.inv, v, W + base, step, mg);
 			}
 			__syncthreads();
 		}

@@ -68,8 +68,10 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
 __global__ void __launch_bounds__(TGPU_THREADS, 2)
 smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
-                  const double *__restrict__ uc, HaloSync hs = HaloSync{})
+                  const double *__restrict__ uc, HaloSync hs = HaloSync{}, int skip_neumann = 0)
 {
+	// skip_neumann != 0: patches with Neumann domain sides are left to the general path of smooth_kernel (launched over
+	// the same range with only_neumann); the warp still gathers its next patch's interface values
 	constexpr int N = 32, ROW = Q32_ROW, NC = N * N;
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
 	extern __shared__ __align__(16) double smem[];
@@ -102,6 +104,18 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		const double h2   = meta[p].h2;
 		double       v[N];
 		if (!ZERO_GUESS && next) halo_wait_warp(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
+		if (skip_neumann && meta[p].neumann) { // warp-uniform
+			if (!ZERO_GUESS && next) {
+				const double cf = 2.0 * meta[pn].inv_h2;
+				__syncwarp(); // GX of the skipped patch is not needed
+				GX[lane]      = cf * gamma_entry2d32<PROLONG>(meta, pn, 0, lane, Fin, uc);
+				GX[32 + lane] = cf * gamma_entry2d32<PROLONG>(meta, pn, 1, lane, Fin, uc);
+				gy0           = cf * gamma_entry2d32<PROLONG>(meta, pn, 2, lane, Fin, uc);
+				gy1           = cf * gamma_entry2d32<PROLONG>(meta, pn, 3, lane, Fin, uc);
+				__syncwarp();
+			}
+			continue;
+		}
 		Gam2d32<PROLONG> ga, gb;
 		double           cfn = 0.0;
 		{ // y forward: column x = lane, straight from memory

@@ -98,6 +98,7 @@ enum { GD_SA = 1, GD_SB = 2, GD_WB = 4, GD_SLOW = 8 };
 struct GPatch16 {
 	GDesc16 d[6];
 	double  h2;
+	int     neu, pad; // Neumann bits of the patch (a level with Neumann patches: this kernel skips them, see skip_neumann)
 };
 template <bool PROLONG>
 __device__ __forceinline__ void make_gdesc16(const PatchMeta &pm, int p, int s, GPatch16 &out)
@@ -262,8 +263,11 @@ template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE 
 __global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE))
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{})
+                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0)
 {
+	// skip_neumann != 0: patches with Neumann domain sides are left alone (their patch solve is not the plain Dirichlet
+	// one; the general path of smooth_kernel sweeps them in a second launch over the same range); the interface values of
+	// the next patch are still gathered while one is skipped
 	constexpr int N = 16, ROW = S16_ROW, PL = S16_PL;
 	using G = Geo<3, 16>;
 	static_assert(WRITE_U || EMIT, "a sweep must produce something");
@@ -288,7 +292,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	// one thread per side (lane 31 of warps 0-5) resolves the descriptors of patch q into GD[slot]
 	auto describe = [&](const PatchMeta &pm, int q, int slot) {
 		if ((t & 31) == 31 && t < 6 * 32) make_gdesc16<PROLONG>(pm, q, t >> 5, GD[slot]);
-		if (t == 6 * 32 + 31) GD[slot].h2 = pm.h2;
+		if (t == 6 * 32 + 31) GD[slot].h2 = pm.h2, GD[slot].neu = pm.neumann;
 	};
 
 	int g = blockIdx.x;
@@ -343,6 +347,30 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			// table entry of the patch after the next -> metaS (read by describe() after the next barrier but one)
 			if (!ZERO_GUESS && t < MW && gn + (int) gridDim.x < npatch)
 				cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pn + gridDim.x) + t, true);
+			if (skip_neumann && (ZERO_GUESS ? meta[p].neumann : GD[b].neu)) { // CTA-uniform: this patch belongs to the general path
+				if (!ZERO_GUESS) {
+					// keep the pipeline of the next patch's interface values going: all six sides at once, nothing to hide behind
+					SideGamma16<PROLONG> s6[6];
+					if (next) {
+						s6[0].template issue<0>(gp.d[0], t, lo, hi, Fin, uc);
+						s6[1].template issue<0>(gp.d[1], t, lo, hi, Fin, uc);
+						s6[2].template issue<1>(gp.d[2], t, lo, hi, Fin, uc);
+						s6[3].template issue<1>(gp.d[3], t, lo, hi, Fin, uc);
+						s6[4].template issue<2>(gp.d[4], t, lo, hi, Fin, uc);
+						s6[5].template issue<2>(gp.d[5], t, lo, hi, Fin, uc);
+					}
+					cp_async_wait_all();
+					__syncthreads(); // metaS has landed
+					if (next) {
+#pragma unroll
+						for (int s = 0; s < 4; s++) Gs[s * 256 + t] = s6[s].finish(gp, s, meta, pn, t, Fin, uc);
+						gz0 = s6[4].finish(gp, 4, meta, pn, t, Fin, uc);
+						gz1 = s6[5].finish(gp, 5, meta, pn, t, Fin, uc);
+						if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + gridDim.x, b);
+					}
+				}
+				continue;
+			}
 		}
 		double v[N];
 		{ // z forward: pencil (x, y) = (lo, hi)

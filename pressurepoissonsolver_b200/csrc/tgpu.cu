@@ -1214,6 +1214,8 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 {
 	if (!h) return TGPU_OK;
 	cudaSetDevice(h->ctx->device);
+	if (h->s_in) cudaStreamSynchronize(h->s_in); // pending copies of the pipelined host path still use the slot vectors
+	if (h->s_out) cudaStreamSynchronize(h->s_out);
 	cudaStreamSynchronize(h->ctx->stream);
 	free_graphs(h);
 	for (tgpu_vec *v : h->krylov_ws) tgpu_vec_destroy(v);
@@ -1604,11 +1606,11 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 // write_u = false (needs emit): only the faces of the new u are wanted (the generic kernel still writes u)
 template <bool Z, bool E, bool PR, bool W, bool SF = false>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
-                             const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{})
+                             const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0)
 {
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * s16_ctas_per_sm(Z, SF))), block(S16_BLOCK);
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
-	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs);
+	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann);
 }
 // can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?
 // Opt-in (TGPU_FINE_SOURCE=1): measured on config B the assembly stage's dependent gathers (children -> neighbour
@@ -1637,19 +1639,26 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
 	const bool general = L.has_neumann || h->lambda != 0.0; // patch solves that are not the plain Dirichlet Poisson solve
+	// 32^3 levels that contain patches with Neumann domain sides: the cluster kernel sweeps the Dirichlet patches of the range,
+	// the general path (smooth3d32n_kernel) exactly the others; lambda != 0 sends every patch through the general path
+	const bool split = !(getenv("TGPU_NEUMANN_SPLIT") && atoi(getenv("TGPU_NEUMANN_SPLIT")) == 0);
+	const bool mixed32 = is_3d32(h) && L.has_neumann && h->lambda == 0.0 && !hsp && split;
 	if (is_3d32(h) && general) { // general transform path through an L2-resident scratch block
 		const int nblk = std::min(p1 - p0, h->ctx->sm_count * 2);
 		if (!h->scratch32) return fail(TGPU_ERR_ARG, "k_smooth: scratch for the general 32^3 patch solve missing");
-		return launch(h->ctx, smooth3d32n_kernel, dim3(nblk), dim3(TGPU_THREADS), 0, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, uc,
-		              (const double *) h->mats, (const double *) h->lam, h->scratch32, (int) zero_guess, (int) emit, (int) (uc != nullptr), (int) write_u, h->lambda);
+		TRY(launch(h->ctx, smooth3d32n_kernel, dim3(nblk), dim3(TGPU_THREADS), 0, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, uc,
+		           (const double *) h->mats, (const double *) h->lam, h->scratch32, (int) zero_guess, (int) emit, (int) (uc != nullptr), (int) write_u, h->lambda,
+		           mixed32 ? 1 : 0));
+		if (!mixed32) return TGPU_OK;
 	}
 	if (is_3d32(h)) {
 		// one cluster of two CTAs (two SMs) per patch, see smooth3d32c_kernel
 		const dim3   grid(2 * std::min(p1 - p0, h->ctx->sm_count / 2)), block(C32_THREADS);
 		const size_t sm  = smooth3d32c_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+		const int    skipn = mixed32 ? 1 : 0;
 #define S32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs);
+	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
 		switch (key) {
 			S32_CASE(8 | 4 | 1, true, true, false, true)
 			S32_CASE(8 | 1, true, false, false, true)
@@ -1672,28 +1681,62 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		if (emit) return launch_smooth3d16<true, true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
 		return launch_smooth3d16<true, false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, src);
 	}
-	if (h->D == 3 && h->N == 16 && !h->generic_kernels && !general) { // the generic kernel has the Neumann path
+	// 16^3 levels that contain patches with Neumann domain sides: the specialised kernel sweeps the Dirichlet patches of the
+	// range and skips the others, the general path of smooth_kernel then sweeps exactly those (two launches, disjoint patches)
+	const bool mixed16 = h->D == 3 && h->N == 16 && !h->generic_kernels && L.has_neumann && h->lambda == 0.0 && !hsp && split;
+	if (h->D == 3 && h->N == 16 && !h->generic_kernels && (!general || mixed16)) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+		const int skipn = mixed16 ? 1 : 0;
+		if (mixed16) { // the general path first (it always writes u), then the specialised kernel on the rest
+			using G        = Geo<3, 16>;
+			const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * smooth_min_blocks<16>())), block(TGPU_THREADS);
+			const size_t sm = smooth_smem_bytes<3, 16, true>();
+			const PatchMeta *meta = L.meta;
+			const double *   eig  = TGPU_S16_TRIDIAG ? h->tri : h->eig;
+			(void) sizeof(G);
+			if (zero_guess && emit) TRY(launch(h->ctx, smooth_kernel<3, 16, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+			else if (zero_guess) TRY(launch(h->ctx, smooth_kernel<3, 16, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+			else if (uc && emit) TRY(launch(h->ctx, smooth_kernel<3, 16, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+			else if (uc) TRY(launch(h->ctx, smooth_kernel<3, 16, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+			else if (emit) TRY(launch(h->ctx, smooth_kernel<3, 16, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+			else TRY(launch(h->ctx, smooth_kernel<3, 16, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		}
 		switch (key) {
-		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 8 | 1: return launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 8 | 4: return launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 4 | 1: return launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 1: return launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 4: return launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 4 | 2 | 1: return launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 2 | 1: return launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
-		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs);
+		case 8 | 4 | 1: return launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 8 | 1: return launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 8 | 4: return launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 4 | 1: return launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 1: return launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 4: return launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 4 | 2 | 1: return launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 2 | 1: return launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
+		case 4 | 2: return launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, hs, skipn);
 		default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
 		}
 	}
-	if (h->D == 2 && h->N == 32 && !h->generic_kernels && !general) { // one warp per patch, see smooth2d32.cuh
+	const bool mixed2d = h->D == 2 && h->N == 32 && !h->generic_kernels && L.has_neumann && h->lambda == 0.0 && !hsp && split;
+	if (mixed2d) { // the general path on the patches with Neumann sides (it always writes u), then the warp-per-patch kernel on the rest
+		using G        = Geo<2, 32>;
+		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
+		const dim3 grid(std::min(nblk, h->ctx->sm_count * smooth_min_blocks<32>())), block(TGPU_THREADS);
+		const size_t sm = smooth_smem_bytes<2, 32, true>();
+		const PatchMeta *meta = L.meta;
+		const double *   eig  = TGPU_S16_TRIDIAG ? h->tri : h->eig;
+		if (zero_guess && emit) TRY(launch(h->ctx, smooth_kernel<2, 32, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		else if (zero_guess) TRY(launch(h->ctx, smooth_kernel<2, 32, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		else if (uc && emit) TRY(launch(h->ctx, smooth_kernel<2, 32, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		else if (uc) TRY(launch(h->ctx, smooth_kernel<2, 32, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		else if (emit) TRY(launch(h->ctx, smooth_kernel<2, 32, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+		else TRY(launch(h->ctx, smooth_kernel<2, 32, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 1));
+	}
+	if (h->D == 2 && h->N == 32 && !h->generic_kernels && (!general || mixed2d)) { // one warp per patch, see smooth2d32.cuh
 		const int    nblk = (p1 - p0 + Q32_WARPS - 1) / Q32_WARPS;
 		const dim3   grid(std::min(nblk, h->ctx->sm_count * 2)), block(TGPU_THREADS);
 		const size_t sm  = smooth2d32_smem_bytes();
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
+		const int    skipn = mixed2d ? 1 : 0;
 #define Q32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs);
+	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
 		switch (key) {
 			Q32_CASE(8 | 4 | 1, true, true, false, true)
 			Q32_CASE(8 | 1, true, false, false, true)
@@ -1715,12 +1758,12 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const size_t sm = smooth_smem_bytes<DD, NN, true>();
 		const PatchMeta *meta = L.meta;
 		const double *   eig  = TGPU_S16_TRIDIAG ? h->tri : h->eig;
-		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
-		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
-		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
-		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
-		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
-		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda);
+		if (zero_guess && emit) return launch(h->ctx, smooth_kernel<DD, NN, true, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
+		if (zero_guess && !emit) return launch(h->ctx, smooth_kernel<DD, NN, true, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
+		if (uc && emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
+		if (uc && !emit) return launch(h->ctx, smooth_kernel<DD, NN, false, false, true>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
+		if (emit) return launch(h->ctx, smooth_kernel<DD, NN, false, true, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
+		return launch(h->ctx, smooth_kernel<DD, NN, false, false, false>, grid, block, sm, meta, p0, p1, f, u, Fin, Fout, eig, uc, (const double *) h->mats, (const double *) h->lam, h->lambda, 0);
 	});
 }
 // coarse = R (f - A u) for a u that a block-Jacobi sweep has just produced: needs only the faces of the new

@@ -18,9 +18,9 @@ def _gen():
 
 def test_generated_dst4_matches_dense_matrix():
     gen = _gen()
-    for N in (8, 16):
+    for N in (8, 16, 32):
         body = gen.gen(N)
-        assert gen.check(N, body) < 1e-14
+        assert gen.check(N, body) < 1e-14 * N / 8
         # an independent evaluation on another input
         rnd = random.Random(N)
         x = [rnd.uniform(-2, 2) for _ in range(N)]
@@ -29,12 +29,12 @@ def test_generated_dst4_matches_dense_matrix():
             exec(ln.replace("const double ", "").rstrip(";"), env)
         for k in range(N):
             ref = sum(x[n] * math.sin(math.pi * (2 * k + 1) * (2 * n + 1) / (4 * N)) for n in range(N))
-            assert abs(env["y"][k] - ref) < 1e-13
+            assert abs(env["y"][k] - ref) < 1e-13 * N / 8
 
 
 def test_committed_header_is_generator_output():
     gen = _gen()
     text = open(os.path.join(ROOT, "pressurepoissonsolver_b200", "csrc", "dst4_fast.cuh")).read()
-    for N in (8, 16):
+    for N in (8, 16, 32):
         for ln in gen.gen(N):
             assert ln in text, (N, ln)

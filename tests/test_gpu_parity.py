@@ -213,7 +213,9 @@ def test_neumann_vs_oracle_seeded(ctx):
     """larger Neumann cases against the oracle, incl. the D = 3, n = 16 size (which must leave its
     specialised Dirichlet kernel for the general path) and multi-sweep cycles"""
     for mesh_file, D, n, divide in (("2refine.bin", 3, 16, 0), ("2d_multi_refine_8.bin", 2, 32, 0), ("3uni.bin", 3, 4, 0),
-                                    ("2uni.bin", 3, 32, 0)):  # 32^3: general path through a scratch block (smooth3d32n_kernel)
+                                    ("2uni.bin", 3, 32, 0),   # 32^3: general path through a scratch block (smooth3d32n_kernel)
+                                    ("3uni.bin", 3, 32, 0),   # 32^3, mixed level: 8 interior patches on the cluster kernel, 56 on the general path
+                                    ("3uni.bin", 3, 16, 1)):  # 16^3, mixed level of 512 patches (smooth3d16_kernel skips, smooth_kernel sweeps the rest)
         mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).set_neumann(True)
         mesh.refine_leaves(divide)
         h = pps.Hierarchy.from_mesh(ctx, mesh, n)

@@ -1,4 +1,4 @@
-"""Generates pressurepoissonsolver_b200/csrc/dst4_fast.cuh: straight-line DST-IV kernels of size 8 and 16,
+"""Generates pressurepoissonsolver_b200/csrc/dst4_fast.cuh: straight-line DST-IV kernels of size 8, 16 and 32,
     Y_k = sum_n x_n sin(pi (2k+1)(2n+1) / (4N)),
 the dense half of the symmetric split of the DST-II / DST-III patch transforms (kernels.cuh, Dst2 / Dst3;
 DftPatchSolver.h:262-281 in the reference).  Algorithm: DST-IV(x)_k = (-1)^k DCT-IV(reversed x)_k and the DCT-IV
@@ -146,17 +146,17 @@ def check(N, body):
         exec(ln.replace("const double ", "").rstrip(";"), env)
     ref = [sum(x[n] * math.sin(math.pi * (2 * k + 1) * (2 * n + 1) / (4 * N)) for n in range(N)) for k in range(N)]
     err = max(abs(a - b) for a, b in zip(y, ref))
-    assert err < 1e-14, (N, err)
+    assert err < 1e-13, (N, err)  # sums of N terms of size <= 1: a few ulps of N
     return err
 
 
 def main():
     out = ["// dst4_fast.cuh - GENERATED by tools/gen_dst4.py, do not edit.",
-           "// Straight-line DST-IV of size 8 and 16, Y_k = sum_n x_n sin(pi (2k+1)(2n+1) / (4N)): the dense half of the",
+           "// Straight-line DST-IV of size 8, 16 and 32, Y_k = sum_n x_n sin(pi (2k+1)(2n+1) / (4N)): the dense half of the",
            "// symmetric split of the DST-II / DST-III patch transforms (Dst2 / Dst3 in kernels.cuh), computed through a",
            "// complex FFT of size N/2 with pre- and post-twiddles instead of an N x N product.",
            "#pragma once", "namespace tgpu", "{"]
-    for N in (8, 16):
+    for N in (8, 16, 32):
         body = gen(N)
         err = check(N, body)
         nops = sum(1 for b in body if b.startswith("const double"))
