@@ -3,8 +3,10 @@
 // error / residual report, apps/3d/steady.cpp:211-215,292-322,453-567) written against the
 // mirrored plugin surface in include/tgpu_plugin.hpp.  Every numerical step runs on the GPU.
 //
-// usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--out u.bin]
-//               [--neumann] [--problem trig|gauss]
+// usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--mid k] [--coarse k] [--max-levels k]
+//               [--patches-per-proc x] [--lambda x] [--out u.bin] [--neumann] [--problem trig|gauss]
+//   --max-levels / --patches-per-proc   GMG::CycleOpts (GMG/CycleOpts.h:55,59, honoured as in GMG/CycleFactory3d.cpp:101-104)
+//   --lambda  the patch solver's shift (FftwPatchSolver(domain, lambda), PatchSolvers/FftwPatchSolver.h:66)
 //   --neumann Neumann domain boundaries (ThundereggDomGen(..., neumann = true), Init::initNeumann, right-hand-side mean
 //             removed as in apps/3d/steady.cpp:301,316-334; 3D); --problem gauss: the app's second manufactured problem
 //   --plugin  drive the cycle through the virtual Level/Smoother/Operator/Restrictor/Interpolator
@@ -25,11 +27,17 @@ template <size_t D> static int run(int argc, char **argv)
 	const int         divide = atoi(argv[3]), n = atoi(argv[4]);
 	GMG::CycleOpts    copts;
 	bool              plugin = false, neumann = false;
+	double            lambda = 0.0;
 	std::string       out, problem = "trig";
 	for (int a = 5; a < argc; a++) {
 		if (!strcmp(argv[a], "--cycle") && a + 1 < argc) copts.cycle_type = argv[++a];
 		else if (!strcmp(argv[a], "--pre") && a + 1 < argc) copts.pre_sweeps = atoi(argv[++a]);
 		else if (!strcmp(argv[a], "--post") && a + 1 < argc) copts.post_sweeps = atoi(argv[++a]);
+		else if (!strcmp(argv[a], "--mid") && a + 1 < argc) copts.mid_sweeps = atoi(argv[++a]);
+		else if (!strcmp(argv[a], "--coarse") && a + 1 < argc) copts.coarse_sweeps = atoi(argv[++a]);
+		else if (!strcmp(argv[a], "--max-levels") && a + 1 < argc) copts.max_levels = atoi(argv[++a]);
+		else if (!strcmp(argv[a], "--patches-per-proc") && a + 1 < argc) copts.patches_per_proc = atof(argv[++a]);
+		else if (!strcmp(argv[a], "--lambda") && a + 1 < argc) lambda = atof(argv[++a]);
 		else if (!strcmp(argv[a], "--plugin")) plugin = true;
 		else if (!strcmp(argv[a], "--neumann")) neumann = true;
 		else if (!strcmp(argv[a], "--problem") && a + 1 < argc) problem = argv[++a];
@@ -40,6 +48,7 @@ template <size_t D> static int run(int argc, char **argv)
 	for (int i = 0; i < divide; i++) mesh.refineLeaves();
 	if (neumann) mesh.setNeumann(true);
 	auto h = std::make_shared<Hierarchy>(ctx, mesh, n);
+	if (lambda != 0.0) check(tgpu_hierarchy_set_lambda(h->p, lambda));
 
 	std::shared_ptr<VectorGenerator<D>> vg(new DeviceVG<D>(h, 0));
 	auto u = vg->getNewVector(), exact = vg->getNewVector(), f = vg->getNewVector(), au = vg->getNewVector();
@@ -92,7 +101,8 @@ template <size_t D> static int run(int argc, char **argv)
 int main(int argc, char **argv)
 {
 	if (argc < 5) {
-		std::cerr << "usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--out u.bin] [--neumann] [--problem trig|gauss]\n";
+		std::cerr << "usage: steady D mesh.bin divide n [--cycle V|W] [--plugin] [--pre k] [--post k] [--mid k] [--coarse k] [--max-levels k] "
+		             "[--patches-per-proc x] [--lambda x] [--out u.bin] [--neumann] [--problem trig|gauss]\n";
 		return 2;
 	}
 	try {

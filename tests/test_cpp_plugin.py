@@ -30,7 +30,7 @@ def test_cpp_app_builds_and_fails_loudly_without_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [[], ["--plugin"]])
+@pytest.mark.parametrize("flags", [[], ["--plugin"], ["--cycle", "W"], ["--cycle", "W", "--plugin"], ["--max-levels", "2"]])
 @pytest.mark.parametrize("name", ["3d_2refine_n8", "2d_2d2ref_d1_n8"])
 def test_cpp_steady_matches_reference_solve(name, flags):
     g = load_golden(name)
@@ -40,6 +40,9 @@ def test_cpp_steady_matches_reference_solve(name, flags):
         res = subprocess.run([app, str(int(g["D"])), os.path.join(MESHES, str(g["mesh"])), str(int(g["divide"])), str(int(g["n"])),
                               "--out", out] + flags, capture_output=True, text=True, check=True)
         its = int(re.search(r"Iterations: (\d+)", res.stdout).group(1))
-        assert its == int(g["bicgstab_info"][0])
         assert float(re.search(r"Residual: (\S+)", res.stdout).group(1)) < 1e-11
-        assert rel_l2(np.fromfile(out), g["bicgstab_u"]) < 1e-10
+        if not [f for f in flags if f != "--plugin"]:  # the reference's default cycle: same Krylov trajectory as the golden solve
+            assert its == int(g["bicgstab_info"][0])
+            assert rel_l2(np.fromfile(out), g["bicgstab_u"]) < 1e-10
+        else:  # other preconditioners converge to the same discrete solution
+            assert rel_l2(np.fromfile(out), g["bicgstab_u"]) < 1e-9
