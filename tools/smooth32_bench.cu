@@ -13,6 +13,10 @@ using namespace tgpu;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
 constexpr int N = 32, NC = N * N * N, M = N * N;
 
+// LOCAL != 0 (experiment): every neighbour is the patch itself and every parent is coarse patch 0, so that the gathered
+// interface data comes from lines the kernel has just touched / from one L2-resident patch: separates the instruction and
+// latency cost of the gathers from their memory traffic
+static int LOCAL = 0;
 static std::vector<PatchMeta> build_meta(int G)
 {
 	std::vector<PatchMeta> m((size_t) G * G * G);
@@ -26,15 +30,15 @@ static std::vector<PatchMeta> build_meta(int G)
 				pm                = PatchMeta{};
 				pm.inv_h2         = 1.0 / (h * h);
 				pm.h2             = h * h;
-				pm.parent_idx     = G > 1 ? pid(x, y, z) : 0;
+				pm.parent_idx     = G > 1 ? (LOCAL ? 0 : pid(x, y, z)) : 0;
 				pm.orth_on_parent = G > 1 ? ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2)) : -1;
 				for (int s = 0; s < 6; s++) {
 					int n[3] = {x, y, z};
 					n[s >> 1] += (s & 1) ? 1 : -1;
 					const bool in = n[s >> 1] >= 0 && n[s >> 1] < G;
 					pm.nbr_type[s] = in ? NBR_NORMAL : NBR_NONE;
-					for (int q = 0; q < 4; q++) pm.nbr_idx[s][q] = in ? id(n[0], n[1], n[2]) : 0;
-					pm.nbr_parent[s] = in && G > 1 ? pid(n[0], n[1], n[2]) : 0;
+					for (int q = 0; q < 4; q++) pm.nbr_idx[s][q] = in ? (LOCAL ? id(x, y, z) : id(n[0], n[1], n[2])) : 0;
+					pm.nbr_parent[s] = in && G > 1 ? (LOCAL ? 0 : pid(n[0], n[1], n[2])) : 0;
 					pm.nbr_orth[s]   = in && G > 1 ? ((n[0] & 1) | ((n[1] & 1) << 1) | ((n[2] & 1) << 2)) : -1;
 				}
 			}
@@ -69,6 +73,7 @@ static double rel_diff(const double *a, const double *b, size_t n)
 int main(int argc, char **argv)
 {
 	const int G = argc > 1 ? atoi(argv[1]) : 8, reps = argc > 2 ? atoi(argv[2]) : 10;
+	LOCAL = argc > 3 ? atoi(argv[3]) : 0;
 	const int P = G * G * G, Pc = std::max(1, P / 8);
 	const size_t nc = (size_t) P * NC, ncc = (size_t) Pc * NC, nf = (size_t) P * 6 * M;
 	std::vector<PatchMeta> hm = build_meta(G);
