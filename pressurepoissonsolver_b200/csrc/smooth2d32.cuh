@@ -64,7 +64,9 @@ template <bool PROLONG> struct Gam2d32 {
 	}
 };
 
-template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U>
+// EXTRA = false compiles the halo hand-over and the Neumann skip out (single GPU, all-Dirichlet levels: the calls and the
+// extra live values cost ~5 % of the sweep through spills otherwise)
+template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool EXTRA = false>
 __global__ void __launch_bounds__(TGPU_THREADS, 2)
 smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ tri,
@@ -89,7 +91,7 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	bool      halo_ok = false;      // multi-GPU: the warp polls the peers' flags before its first patch that needs halo faces
 	if (!ZERO_GUESS && g < npatch) { // the warp's first patch: nothing to hide the gathers behind
 		const int    p    = p0 + g;
-		halo_wait_warp(hs, p, halo_ok);
+		if (EXTRA) halo_wait_warp(hs, p, halo_ok);
 		const double cfac = 2.0 * meta[p].inv_h2;
 		GX[lane]      = cfac * gamma_entry2d32<PROLONG>(meta, p, 0, lane, Fin, uc);
 		GX[32 + lane] = cfac * gamma_entry2d32<PROLONG>(meta, p, 1, lane, Fin, uc);
@@ -103,8 +105,8 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		const int    pn   = p + nw;
 		const double h2   = meta[p].h2;
 		double       v[N];
-		if (!ZERO_GUESS && next) halo_wait_warp(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
-		if (skip_neumann && meta[p].neumann) { // warp-uniform
+		if (EXTRA && !ZERO_GUESS && next) halo_wait_warp(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
+		if (EXTRA && skip_neumann && meta[p].neumann) { // warp-uniform
 			if (!ZERO_GUESS && next) {
 				const double cf = 2.0 * meta[pn].inv_h2;
 				__syncwarp(); // GX of the skipped patch is not needed
@@ -202,6 +204,6 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 		}
 		__syncwarp();
 	}
-	if (!ZERO_GUESS) halo_finish(hs);
+	if (EXTRA && !ZERO_GUESS) halo_finish(hs);
 }
 } // namespace tgpu

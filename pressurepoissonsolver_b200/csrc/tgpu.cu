@@ -370,7 +370,8 @@ static int set_smem_attrs_3d16()
 }
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_2d32()
 {
-	CU(cudaFuncSetAttribute(smooth2d32_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth2d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth2d32_kernel<Z, E, PR, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth2d32_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth2d32_kernel<Z, E, PR, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth2d32_smem_bytes()));
 	return TGPU_OK;
 }
 static int setup_2d32()
@@ -1736,7 +1737,9 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		const int    skipn = mixed2d ? 1 : 0;
 #define Q32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
+	case K: \
+		if (skipn || hs.enabled) return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W, true>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn); \
+		return launch(h->ctx, smooth2d32_kernel<Z, E, PR, W, false>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
 		switch (key) {
 			Q32_CASE(8 | 4 | 1, true, true, false, true)
 			Q32_CASE(8 | 1, true, false, false, true)
