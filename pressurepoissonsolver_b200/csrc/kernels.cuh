@@ -77,7 +77,9 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p)
 // finish advances the generation counter and acknowledges the halo to the peers (ACK flags).
 // cnt[]: 0 data sent, 1 data awaited, 2 ack sent, 3 ack awaited (generation counters of the level, device memory).
 // ---------------------------------------------------------------------------------------------
+struct PushDesc;
 struct HaloSync {
+	const PushDesc *  push          = nullptr; // != nullptr: the kernel also pushes this rank's faces first (halo_push_cta)
 	const uint64_t *  data_flags    = nullptr; // my DATA flag row [nranks], written by the peers
 	const int32_t *   peer_rank     = nullptr; // [npeers]
 	uint64_t *const * peer_ack_flag = nullptr; // [npeers] my entry of each peer's ACK row
@@ -443,6 +445,95 @@ template <int D, int N> __device__ __forceinline__ int parent_cell(int orth, con
 	const int cx = (c[0] + (orth & 1) * N) / 2, cy = (c[1] + ((orth >> 1) & 1) * N) / 2;
 	const int cz = (D == 2) ? 0 : (c[2] + ((orth >> 2) & 1) * N) / 2;
 	return (cz * N + cy) * N + cx;
+}
+// ---------------------------------------------------------------------------------------------
+// Producer side of the halo hand-over inside the consumer kernel: before a CTA of a sweep / face-residual launch touches
+// its patches it stores its share of this rank's boundary faces (optionally + the prolonged coarse correction, as
+// push_faces_kernel) into the peers' halo slots; the last CTA to finish publishes DATA.  The stores then overlap the
+// launch's work on the patches without off-rank neighbours and no separate push launch sits on the critical path.
+// Needs every CTA of the grid to become resident without waiting for another CTA of the same grid to retire (the
+// host clamps the grid to the occupancy, see resident_grid in tgpu.cu): CTAs poll for the peers' faces later on, and the
+// peers' faces are published by the last of THEIR CTAs.
+// Lives in device memory, one per (level, face buffer, with / without prolongation); written once at set-up.
+// ---------------------------------------------------------------------------------------------
+struct PushDesc {
+	const int32_t *   patch, *side, *peer_of, *ridx; // [nfaces] send list (LevelDev)
+	const double *    F;                              // face buffer the faces are read from
+	const double *    uc;                             // != nullptr: + (P uc) on the boundary cells
+	double *const *   peerF;                          // [nranks] the peers' mapping of the same face buffer
+	const uint64_t *  ack_flags;                      // my ACK flag row [nranks]
+	const int32_t *   peer_rank;                      // [npeers]
+	uint64_t *const * peer_data_flag;                 // [npeers] my entry of each peer's DATA row
+	uint64_t *        cnt;                            // generation counters of the level (HaloSync)
+	unsigned *        ticket;
+	int *             abort;
+	int *             host_err;
+	int               nfaces, npeers;
+};
+// every thread of every CTA of the launch calls this once, before any halo wait (contains CTA barriers)
+template <int D, int N> __device__ __noinline__ void halo_push_cta(const PatchMeta *__restrict__ meta, const PushDesc *__restrict__ pd)
+{
+	using G             = Geo<D, N>;
+	const unsigned nctas = gridDim.x * gridDim.y * gridDim.z;
+	const unsigned cta   = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+	const unsigned nthr  = blockDim.x * blockDim.y * blockDim.z;
+	const unsigned tid   = (threadIdx.z * blockDim.y + threadIdx.y) * blockDim.x + threadIdx.x;
+	int *const     abort = pd->abort;
+	uint64_t *const cnt  = pd->cnt;
+	const int      npeers = pd->npeers;
+	if (tid == 0 && !*abort) { // the peers must have consumed the previous generation of my faces before their slots are rewritten
+		const uint64_t expected = cnt[3];
+		for (int k = 0; k < npeers; k++) {
+			const uint64_t *f = pd->ack_flags + pd->peer_rank[k];
+			unsigned long long t0;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+			while (ld_acquire_sys(f) < expected) {
+				unsigned long long t1;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+				if (t1 - t0 > 20000000000ull) { // 20 s
+					atomicExch(abort, 1);
+					*(volatile int *) pd->host_err = pd->peer_rank[k] + 1;
+					__threadfence_system();
+					break;
+				}
+				__nanosleep(100);
+			}
+		}
+	}
+	__syncthreads();
+	const int32_t *patch = pd->patch, *side = pd->side, *peer_of = pd->peer_of, *ridx = pd->ridx;
+	const double * F = pd->F, *uc = pd->uc;
+	double *const *peerF = pd->peerF;
+	const size_t   total = (size_t) pd->nfaces * G::M;
+	for (size_t i = (size_t) cta * nthr + tid; i < total; i += (size_t) nctas * nthr) {
+		const int m = (int) (i % G::M), k = (int) (i / G::M);
+		const int p = patch[k], s = side[k];
+		double    v = F[((size_t) p * G::S + s) * G::M + m];
+		if (uc) {
+			int c[3];
+			face_cell<D, N>(s, m, c);
+			v += __ldg(uc + (size_t) meta[p].parent_idx * G::NC + parent_cell<D, N>(meta[p].orth_on_parent, c));
+		}
+		peerF[peer_of[k]][(size_t) ridx[k] * G::M + m] = v;
+	}
+	__syncthreads();
+	if (tid == 0) { // the last CTA publishes the faces: DATA generation + 1 in every peer's flag row
+		__threadfence_system();
+		if (atomicAdd(pd->ticket, 1u) == nctas - 1) {
+			__threadfence_system();
+			*pd->ticket = 0;
+			if (!*abort) {
+				cnt[3] += 1;
+				const uint64_t v = cnt[0] + 1;
+				for (int k = 0; k < npeers; k++) st_release_sys(pd->peer_data_flag[k], v);
+				cnt[0] = v;
+			}
+		}
+	}
+}
+template <int D, int N> __device__ __forceinline__ void halo_push(const HaloSync &hs, const PatchMeta *__restrict__ meta)
+{
+	if (hs.enabled && hs.push) halo_push_cta<D, N>(meta, hs.push); // grid-uniform
 }
 // Accessor for "boundary value idx on side s of patch q".  Plain: the face buffer entry.  With a
 // coarse vector attached (post-smoothing right after the coarse-grid correction) the piecewise
@@ -1162,7 +1253,7 @@ __device__ __forceinline__ void frr_patch(const PatchMeta *__restrict__ meta, in
 	}
 	__syncthreads();
 }
-template <int D, int N, bool DIFF>
+template <int D, int N, bool DIFF, bool HALO = false>
 __global__ void __launch_bounds__(TGPU_THREADS)
 face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
                               const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
@@ -1170,16 +1261,17 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
 	using G = Geo<D, N>;
 	pdl_launch_dependents();
 	pdl_wait();
+	if (HALO) halo_push<D, N>(hs, meta);
 	__shared__ double R[G::PPB][G::S][G::M];
 	const int t = threadIdx.x, pp = t / G::M, m = t % G::M;
 	const int nblk = (P - p0 + G::PPB - 1) / G::PPB;
 	bool      halo_ok = false;
 	for (int g = blockIdx.x; g < nblk; g += gridDim.x) {
 		const int p = p0 + g * G::PPB + pp;
-		halo_wait_cta(hs, p0 + g * G::PPB + G::PPB - 1, halo_ok); // the last patch of the group decides for the whole CTA
+		if (HALO) halo_wait_cta(hs, p0 + g * G::PPB + G::PPB - 1, halo_ok); // the last patch of the group decides for the whole CTA
 		frr_patch<D, N, DIFF>(meta, p, p < P, m, R[pp], Fnew, Fold, coarse);
 	}
-	halo_finish(hs);
+	if (HALO) halo_finish(hs);
 }
 // D = 3, N = 16: refined patches whose six sides have same-level neighbours (or none) -- every patch of a uniform
 // level -- go through a leaner path: one thread per COARSE face entry (6 x 64 per patch) loads its 2 x 2 block of the
@@ -1189,7 +1281,7 @@ face_residual_restrict_kernel(const PatchMeta *__restrict__ meta, int p0, int P,
 #ifndef FRR16_MINB
 #define FRR16_MINB 8 // 32 registers: every CTA of the grid (8 per SM) resident at once; the kernel is latency bound
 #endif
-template <bool DIFF>
+template <bool DIFF, bool HALO = false>
 __global__ void __launch_bounds__(TGPU_THREADS, FRR16_MINB)
 face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ Fnew,
                                 const double *__restrict__ Fold, double *__restrict__ coarse, HaloSync hs = HaloSync{})
@@ -1197,12 +1289,13 @@ face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int 
 	using G = Geo<3, 16>;
 	pdl_launch_dependents();
 	pdl_wait();
+	if (HALO) halo_push<3, 16>(hs, meta);
 	__shared__ __align__(16) double R[G::S][G::M]; // fast path uses the first 6 x 64 entries as Rc[s][c]
 	const int      t        = threadIdx.x;
 	bool           halo_ok  = false;
 	for (int g = blockIdx.x; g < P - p0; g += gridDim.x) {
 		const int        p  = p0 + g;
-		halo_wait_cta(hs, p, halo_ok);
+		if (HALO) halo_wait_cta(hs, p, halo_ok);
 		const PatchMeta &pm = meta[p];
 		bool             fast = pm.orth_on_parent >= 0;
 #pragma unroll
@@ -1258,7 +1351,7 @@ face_residual_restrict16_kernel(const PatchMeta *__restrict__ meta, int p0, int 
 		}
 		__syncthreads();
 	}
-	halo_finish(hs);
+	if (HALO) halo_finish(hs);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -85,6 +85,7 @@ smooth2d32_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	mg.load();
 	pdl_launch_dependents();
 	pdl_wait();
+	if (EXTRA && !ZERO_GUESS) halo_push<2, 32>(hs, meta);
 	const int npatch = P - p0, nw = gridDim.x * Q32_WARPS;
 	int       g = blockIdx.x * Q32_WARPS + w;
 	double    gy0 = 0.0, gy1 = 0.0; // (2/h^2) gamma of entry x = lane on the two y faces

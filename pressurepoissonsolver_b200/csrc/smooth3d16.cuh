@@ -259,7 +259,8 @@ __device__ __forceinline__ void build_tile_from_fine_faces16(double *S, const Fi
 	}
 }
 
-template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false>
+// HALO = false compiles the multi-GPU hand-over (HaloSync / halo_push_cta) out: the single-GPU instantiations carry none of it
+template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false, bool HALO = false>
 __global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE))
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
@@ -288,6 +289,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	const uint64_t l2keep = l2_policy_evict_last();
 	pdl_launch_dependents();
 	pdl_wait();
+	if (!ZERO_GUESS) if (HALO) halo_push<3, 16>(hs, meta);
 
 	// one thread per side (lane 31 of warps 0-5) resolves the descriptors of patch q into GD[slot]
 	auto describe = [&](const PatchMeta &pm, int q, int slot) {
@@ -299,7 +301,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	// multi-GPU: the CTA polls the peers' flags itself before the first patch whose gamma needs halo faces (HaloSync)
 	bool halo_ok = false;
 	if (g >= npatch) {
-		if (!ZERO_GUESS) halo_finish(hs);
+		if (!ZERO_GUESS) if (HALO) halo_finish(hs);
 		return;
 	}
 	constexpr bool DIRECT = s16_direct(ZERO_GUESS, SRC_FINE); // f goes straight from memory into the z pencils, one tile
@@ -308,7 +310,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	if (!ZERO_GUESS) {
 		// first patch of this CTA: nothing to hide the gathers behind
 		const int p = p0 + g;
-		halo_wait_cta(hs, p, halo_ok);
+		if (HALO) halo_wait_cta(hs, p, halo_ok);
 		describe(meta[p], p, 0);
 		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
 		__syncthreads();
@@ -342,7 +344,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			// the previous patch's last stage has read the tile; Gs and the descriptors written during the
 			// previous iteration become visible
 			__syncthreads();
-			if (!ZERO_GUESS && next) halo_wait_cta(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
+			if (HALO && !ZERO_GUESS && next) halo_wait_cta(hs, pn, halo_ok); // gamma of patch pn is gathered during this iteration
 			h2 = ZERO_GUESS ? meta[p].h2 : GD[b].h2;
 			// table entry of the patch after the next -> metaS (read by describe() after the next barrier but one)
 			if (!ZERO_GUESS && t < MW && gn + (int) gridDim.x < npatch)
@@ -572,6 +574,6 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			Gs[768 + t] = sg.finish(gp, 3, meta, pn, t, Fin, uc);
 		}
 	}
-	if (!ZERO_GUESS) halo_finish(hs);
+	if (!ZERO_GUESS) if (HALO) halo_finish(hs);
 }
 } // namespace tgpu

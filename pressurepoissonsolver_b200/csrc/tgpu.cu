@@ -125,6 +125,7 @@ struct tgpu_ctx {
 	bool         capturing = false;
 	int          pdl       = 1;    // TGPU_PDL: 0 = off, 1 = between small grids only (default), 2 = always
 	bool         last_small = false;
+	bool         clamp_resident = false; // next launch(): clamp the grid to what is resident at once (kernels with halo_push_cta)
 	int64_t      captured  = 0;
 	// multi-GPU
 	ncclComm_t   comm        = nullptr;
@@ -209,6 +210,8 @@ struct LevelDev {
 	uint64_t * data_flags = nullptr, *ack_flags = nullptr;       // my flag rows [nranks] (in the arena, written by peers)
 	uint64_t * cnt = nullptr;                                    // generation counters: data sent / awaited, ack sent / awaited
 	unsigned * tickets = nullptr;                                // [2] finished-CTA counters of the fused push / consumer kernels
+	PushDesc * push_desc = nullptr;                              // device [4]: (Fa | Fb) x (plain | + prolonged correction), see ensure_push_desc
+	const double *push_uc = nullptr;                             // the coarse vector the descriptors were built with
 };
 
 struct GraphEntry {
@@ -266,6 +269,16 @@ static int launch(tgpu_ctx *ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block
 		cudaEventCreate(&e0);
 		cudaEventCreate(&e1);
 		cudaEventRecord(e0, ctx->stream);
+	}
+	if (ctx->clamp_resident) {
+		// every CTA of this grid must be able to become resident without another CTA of the grid retiring (halo_push_cta)
+		ctx->clamp_resident = false;
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (int) (block.x * block.y * block.z), smem) != cudaSuccess || nb < 1)
+			return fail(TGPU_ERR_CUDA, "kernel launch: occupancy query failed");
+		const unsigned cap = (unsigned) nb * (unsigned) ctx->sm_count;
+		if (grid.y != 1 || grid.z != 1) return fail(TGPU_ERR_ARG, "kernel launch: resident clamp needs a 1D grid");
+		if (grid.x > cap) grid.x = cap; // (cap is a multiple of the SM count: even, as the 2-CTA cluster kernel needs)
 	}
 	cudaLaunchConfig_t  cfg = {};
 	cudaLaunchAttribute at[1];
@@ -350,6 +363,7 @@ static bool supported_dn(int D, int N)
 template <bool Z, bool E, bool PR, bool W, bool SF = false> static int set_smem_attr_3d16()
 {
 	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
+	if (!Z && !SF) CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF, !Z && !SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
 	return TGPU_OK;
 }
 static int set_smem_attrs_3d16()
@@ -389,7 +403,7 @@ static int setup_2d32()
 }
 template <bool Z, bool E, bool PR, bool W> static int set_smem_attr_3d32()
 {
-	CU(cudaFuncSetAttribute(smooth3d32c_kernel<Z, E, PR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32c_smem_bytes()));
+	CU(cudaFuncSetAttribute(smooth3d32c_kernel<Z, E, PR, W, !Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d32c_smem_bytes()));
 	return TGPU_OK;
 }
 // 32^3 patches: opt-in shared memory sizes
@@ -411,6 +425,8 @@ static int setup_3d32(tgpu_hier *h)
 	CU(cudaFuncSetAttribute(apply3d32_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) apply3d32_tma_smem_bytes()));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
+	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
+	CU(cudaFuncSetAttribute(face_residual_restrict_big_kernel<3, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 1024 * 8));
 	for (const LevelDev &L : h->levels)
 		if (L.has_neumann && !h->scratch32) CU(cudaMalloc(&h->scratch32, (size_t) h->ctx->sm_count * 2 * 32768 * sizeof(double)));
 	return TGPU_OK;
@@ -1249,6 +1265,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 		cudaFree(L.peer_ack_flag);
 		cudaFree(L.cnt);
 		cudaFree(L.tickets);
+		cudaFree(L.push_desc);
 		for (int e = 0; e < 4; e++)
 			if (L.ev[e]) cudaEventDestroy(L.ev[e]);
 		cudaFree(L.send_patch);
@@ -1514,10 +1531,48 @@ static bool halo_in_kernel(const tgpu_hier *h, int l)
 	const bool kernels = (h->D == 3 && (h->N == 16 || h->N == 32)) || (h->D == 2 && h->N == 32); // smoothers + face residuals that take a HaloSync
 	return !off && L.p2p && kernels && !h->generic_kernels && !L.has_neumann && h->lambda == 0.0;
 }
-static HaloSync halo_sync(tgpu_hier *h, int l)
+// producer side folded into the consumer kernel as well (halo_push_cta): no separate push launch
+static bool push_in_kernel(const tgpu_hier *h, int l)
+{
+	static const bool off = getenv("TGPU_PUSH_IN_KERNEL") && atoi(getenv("TGPU_PUSH_IN_KERNEL")) == 0;
+	return !off && halo_in_kernel(h, l);
+}
+// the four push descriptors of a level: index (F == Fb ? 2 : 0) + (with the prolonged correction of level l + 1's u ? 1 : 0)
+static int ensure_push_desc(tgpu_hier *h, int l)
+{
+	LevelDev &L = h->levels[l];
+	const double *ucv = l + 1 < (int) h->levels.size() ? h->levels[l + 1].u : nullptr;
+	if (!L.p2p || (L.push_desc && L.push_uc == ucv)) return TGPU_OK;
+	PushDesc d[4];
+	for (int i = 0; i < 4; i++) {
+		d[i].patch          = L.send_patch;
+		d[i].side           = L.send_side;
+		d[i].peer_of        = L.send_peer;
+		d[i].ridx           = L.send_ridx;
+		d[i].F              = (i & 2) ? L.Fb : L.Fa;
+		d[i].uc             = (i & 1) ? ucv : nullptr;
+		d[i].peerF          = (i & 2) ? L.peerFb : L.peerFa;
+		d[i].ack_flags      = L.ack_flags;
+		d[i].peer_rank      = L.peer_rank;
+		d[i].peer_data_flag = L.peer_data_flag;
+		d[i].cnt            = L.cnt;
+		d[i].ticket         = L.tickets;
+		d[i].abort          = h->p2p_abort;
+		d[i].host_err       = (int *) h->ctx->p2p_err;
+		d[i].nfaces         = (int) L.nsend;
+		d[i].npeers         = (int) L.peers.size();
+	}
+	if (!L.push_desc) CU(cudaMalloc(&L.push_desc, sizeof(d)));
+	CU(cudaMemcpy(L.push_desc, d, sizeof(d), cudaMemcpyHostToDevice));
+	L.push_uc = ucv;
+	return TGPU_OK;
+}
+// pushF != nullptr: the consumer launch first pushes this rank's faces pushF (+ the prolonged correction if with_uc)
+static HaloSync halo_sync(tgpu_hier *h, int l, const double *pushF = nullptr, bool with_uc = false)
 {
 	LevelDev &L = h->levels[l];
 	HaloSync  hs;
+	if (pushF && L.push_desc) hs.push = L.push_desc + ((pushF == L.Fb ? 2 : 0) + (with_uc ? 1 : 0));
 	hs.data_flags       = L.data_flags;
 	hs.peer_rank        = L.peer_rank;
 	hs.peer_ack_flag    = L.peer_ack_flag;
@@ -1610,6 +1665,11 @@ static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, co
                              const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0)
 {
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * s16_ctas_per_sm(Z, SF))), block(S16_BLOCK);
+	if (hs.enabled) {
+		if (Z || SF) return fail(TGPU_ERR_ARG, "smooth3d16: no halo hand-over in a zero-guess sweep");
+		return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF, !Z && !SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u,
+		              Fin, Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann);
+	}
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
 	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann);
 }
@@ -1634,8 +1694,9 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	LevelDev &L = h->levels[l];
 	TRY(need_smoother(h, l));
 	if (p1 < 0) p1 = L.P;
-	if (p1 <= p0) return TGPU_OK;
+	if (p1 <= p0) return hs.push ? fail(TGPU_ERR_ARG, "k_smooth: a launch that pushes faces needs patches") : TGPU_OK;
 	if (!emit) write_u = true;
+	h->ctx->clamp_resident = hs.push != nullptr; // consumed by the next launch()
 	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
@@ -1659,7 +1720,7 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 		const int    key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		const int    skipn = mixed32 ? 1 : 0;
 #define S32_CASE(K, Z, E, PR, W) \
-	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
+	case K: return launch(h->ctx, smooth3d32c_kernel<Z, E, PR, W, !Z>, grid, block, sm, (const PatchMeta *) L.meta, p0, p1, f, u, Fin, Fout, (const double *) h->tri, uc, hs, skipn);
 		switch (key) {
 			S32_CASE(8 | 4 | 1, true, true, false, true)
 			S32_CASE(8 | 1, true, false, false, true)
@@ -1778,15 +1839,20 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 	const HaloSync hs = hsp ? *hsp : HaloSync{};
 	if (hsp && !halo_in_kernel(h, l)) return fail(TGPU_ERR_ARG, "k_face_residual_restrict: in-kernel halo hand-over is not available for this level");
 	if (p1 < 0) p1 = L.P;
-	if (p1 <= p0) return TGPU_OK;
+	if (p1 <= p0) return hs.push ? fail(TGPU_ERR_ARG, "k_face_residual_restrict: a launch that pushes faces needs patches") : TGPU_OK;
+	h->ctx->clamp_resident = hs.push != nullptr; // consumed by the next launch()
 	Tag tg(h->ctx, "face_residual_restrict", l);
 	if (is_3d32(h)) {
 		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 4)), block(TGPU_THREADS);
+		if (hs.enabled && Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		if (hs.enabled) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 		if (Fold) return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, true>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 		return launch(h->ctx, face_residual_restrict_big_kernel<3, 32, false>, grid, block, 6 * 1024 * 8, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	}
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels) {
 		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 8)), block(TGPU_THREADS);
+		if (hs.enabled && Fold) return launch(h->ctx, face_residual_restrict16_kernel<true, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		if (hs.enabled) return launch(h->ctx, face_residual_restrict16_kernel<false, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 		if (Fold) return launch(h->ctx, face_residual_restrict16_kernel<true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 		return launch(h->ctx, face_residual_restrict16_kernel<false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	}
@@ -1794,6 +1860,11 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 		using G        = Geo<DD, NN>;
 		const int nblk = (p1 - p0 + G::PPB - 1) / G::PPB;
 		const dim3 grid(std::min(nblk, h->ctx->sm_count * 8)), block(TGPU_THREADS);
+		if (hs.enabled && DD == 2 && NN == 32) { // the only generic instantiation with the hand-over (halo_in_kernel)
+			if (Fold) return launch(h->ctx, face_residual_restrict_kernel<2, 32, true, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+			return launch(h->ctx, face_residual_restrict_kernel<2, 32, false, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
+		}
+		if (hs.enabled) return fail(TGPU_ERR_ARG, "k_face_residual_restrict: no in-kernel hand-over for this patch size");
 		if (Fold) return launch(h->ctx, face_residual_restrict_kernel<DD, NN, true>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 		return launch(h->ctx, face_residual_restrict_kernel<DD, NN, false>, grid, block, 0, (const PatchMeta *) L.meta, p0, p1, Fnew, Fold, coarse, hs);
 	});
@@ -2174,8 +2245,9 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		// the faces of the pre-smoothed u go straight into the neighbours' halo slots; theirs arrive while the patches
 		// without off-rank neighbours are swept: ONE launch over all owned patches whose CTAs poll the peers' flags
 		// before their first boundary patch and whose last CTA acknowledges the halo (HaloSync, kernels.cuh)
-		const HaloSync hs = halo_sync(h, l);
-		TRY(p2p_push(h, l, Fcur, nullptr));
+		// (push_in_kernel: the same launch pushes this rank's faces first, halo_push_cta)
+		const HaloSync hs = halo_sync(h, l, push_in_kernel(h, l) ? Fcur : nullptr, false);
+		if (!hs.push) TRY(p2p_push(h, l, Fcur, nullptr));
 		TRY(k_face_residual_restrict(h, l, Fcur, Fold, C.f, 0, L.P, &hs));
 	} else if (overlap && L.p2p) {
 		TRY(p2p_push(h, l, Fcur, nullptr));
@@ -2210,7 +2282,9 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		TRY(fused_visit(h, o, l + 1, C.f, C.u, false));
 	}
 	// same faces + prolonged correction for the neighbours on other GPUs (owned faces add it on the fly)
-	if (overlap && L.p2p) TRY(p2p_push(h, l, Fcur, C.u));
+	const bool push_folded = overlap && L.p2p && o.post_sweeps >= 1 && push_in_kernel(h, l) && L.push_desc && L.push_uc == C.u;
+	if (push_folded) {} // the first post-sweep's launch pushes them itself
+	else if (overlap && L.p2p) TRY(p2p_push(h, l, Fcur, C.u));
 	else if (overlap) TRY(exchange_async(h, l, Fcur, C.u, L.ev[2], L.ev[3]));
 	for (int i = 0; i < o.post_sweeps; i++) {
 		const bool lastsweep = (i + 1 == o.post_sweeps);
@@ -2218,7 +2292,7 @@ static int fused_visit(tgpu_hier *h, const TgpuCycleOpts &o, int l, const double
 		// first post-sweep: boundary values = faces of the pre-smoothed u + prolonged coarse correction
 		if (i > 0) TRY(k_exchange(h, l, Fcur, nullptr));
 		if (i == 0 && overlap && L.p2p && halo_in_kernel(h, l)) {
-			const HaloSync hs = halo_sync(h, l);
+			const HaloSync hs = halo_sync(h, l, push_folded ? Fcur : nullptr, true);
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.P, lastsweep, nullptr, &hs));
 		} else if (i == 0 && overlap) {
 			TRY(k_smooth(h, l, false, emit, f, u, Fcur, Falt, C.u, 0, L.n_interior, lastsweep));
@@ -2280,6 +2354,7 @@ static int cycle_ptr(tgpu_hier *h, const TgpuCycleOpts *opts, const double *f, d
 		const bool fused_sched = fused_schedule(o, ctx->nranks);
 		TRY(ensure_work(h, (int) l, !fused_sched || (o.fused == 2 && is_3d32(h))));
 	}
+	for (int l = 0; l <= h->last_level; l++) TRY(ensure_push_desc(h, l));
 	if (!o.use_graph || ctx->profiling || (ctx->nranks > 1 && o.use_graph < 2)) return run_cycle(h, o, f, u, want_faces);
 	for (GraphEntry &g : h->graphs)
 		if (g.f == f && g.u == u && g.want_faces == want_faces && same_opts(g.opts, o)) {
