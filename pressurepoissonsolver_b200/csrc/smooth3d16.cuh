@@ -66,7 +66,10 @@ __host__ __device__ constexpr bool   s16_direct(bool, bool src_fine) { return !s
 #ifndef S16_GAMMA_CTAS
 #define S16_GAMMA_CTAS 3
 #endif
-__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine) { return src_fine ? 3 : (zero_guess ? 4 : S16_GAMMA_CTAS); }
+__host__ __device__ constexpr int    s16_ctas_per_sm(bool zero_guess, bool src_fine, bool neu = false)
+{
+	return neu ? 2 : (src_fine ? 3 : (zero_guess ? 4 : S16_GAMMA_CTAS)); // (the Neumann variant's general transforms need the registers)
+}
 __host__ __device__ constexpr size_t smooth3d16_smem_bytes(bool zero_guess = false, bool src_fine = false)
 {
 	return sizeof(double) * (s16_direct(zero_guess, src_fine) ? 1 : 2) * S16_TILE;
@@ -259,13 +262,28 @@ __device__ __forceinline__ void build_tile_from_fine_faces16(double *S, const Fi
 	}
 }
 
+// tables of the general patch solve (smooth_kernel's): dense transform matrices by kind and the eigenvalue rows
+struct NeuTabs {
+	const double * mats = nullptr, *lam = nullptr;
+	const int32_t *list = nullptr; // the patches the launch sweeps (those of the range with Neumann sides), ascending
+	int            n    = 0;
+};
 // HALO = false compiles the multi-GPU hand-over (HaloSync / halo_push_cta) out: the single-GPU instantiations carry none of it
-template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false, bool HALO = false>
-__global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE))
+// NEU = true: the instantiation for the patches WITH Neumann domain sides of a level (it sweeps exactly those of the range,
+// from the list in NeuTabs; the plain instantiation launched with skip_neumann sweeps the others): same pipeline - f straight into the z
+// pencils, interface values of the next patch gathered behind the transforms, slices emitted from registers - with the
+// transform of each axis chosen by the patch's boundary kinds (general_transform: DST-II/III, DST-IV / DCT-IV in generated
+// fast form, DCT-II/III dense) and the y axis transformed and divided by the eigenvalue sums like the others instead of the
+// tridiagonal solve (whose multiplier table is the all-Dirichlet one).  Same arithmetic per patch as smooth_kernel's
+// general path (DftPatchSolver.h:173-216 with the kinds of DftPatchSolver.h:237-289).
+template <bool ZERO_GUESS, bool EMIT, bool PROLONG, bool WRITE_U, bool SRC_FINE = false, bool HALO = false, bool NEU = false>
+__global__ void __launch_bounds__(TGPU_THREADS, s16_ctas_per_sm(ZERO_GUESS, SRC_FINE, NEU))
 smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const double *__restrict__ f, double *__restrict__ u,
                   const double *__restrict__ Fin, double *__restrict__ Fout, const double *__restrict__ eig,
-                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0)
+                  const double *__restrict__ uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0,
+                  NeuTabs nt = NeuTabs{})
 {
+	static_assert(!NEU || (!SRC_FINE && !HALO), "the Neumann instantiation is single-GPU, right-hand side from memory");
 	// skip_neumann != 0: patches with Neumann domain sides are left alone (their patch solve is not the plain Dirichlet
 	// one; the general path of smooth_kernel sweeps them in a second launch over the same range); the interface values of
 	// the next patch are still gathered while one is skipped
@@ -283,7 +301,8 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	// (the z-face values stay in the registers of the thread that needs them)
 	__shared__ double Gs[ZERO_GUESS ? 1 : 4 * 256];
 	const int t = threadIdx.x, lo = t & 15, hi = t >> 4;
-	const int npatch = P - p0;
+	const int npatch = NEU ? nt.n : P - p0;
+	auto      pid    = [&](int gg) { return NEU ? (int) __ldg(nt.list + gg) : p0 + gg; }; // patch of work item gg (CTA-uniform)
 	Mags<N> mg;
 	mg.load();
 	const uint64_t l2keep = l2_policy_evict_last();
@@ -309,10 +328,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	SideGamma16<PROLONG> sg;
 	if (!ZERO_GUESS) {
 		// first patch of this CTA: nothing to hide the gathers behind
-		const int p = p0 + g;
+		const int p = pid(g);
 		if (HALO) halo_wait_cta(hs, p, halo_ok);
 		describe(meta[p], p, 0);
-		if (g + (int) gridDim.x < npatch) describe(meta[p + gridDim.x], p + gridDim.x, 1);
+		if (g + (int) gridDim.x < npatch) {
+			const int p2 = pid(g + gridDim.x);
+			describe(meta[p2], p2, 1);
+		}
 		__syncthreads();
 		// all six sides' loads in flight at once (no transform registers are live yet): one memory round trip instead
 		// of six, which is most of the latency of a coarse level where every CTA solves a single patch
@@ -331,12 +353,14 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 	for (int it = 0; g < npatch; g += gridDim.x, it++) {
 		const int       b    = it & 1;
 		double *        S    = smem + (DIRECT ? 0 : b) * S16_TILE;
-		const int       p    = p0 + g;
+		const int       p    = pid(g);
 		const int       gn   = g + gridDim.x;
 		const bool      next = gn < npatch;
-		const int       pn   = p0 + gn;  // patch whose gamma is gathered during this iteration
+		const int       pn   = NEU ? (next ? pid(gn) : p) : p0 + gn; // patch whose gamma is gathered during this iteration
+		const int       pnn  = (gn + (int) gridDim.x < npatch) ? pid(gn + gridDim.x) : p; // the one after it
 		const GPatch16 &gp   = GD[b ^ 1]; // its descriptors
 		double          h2;
+		int             neu_p = 0; // Neumann bits of patch p
 		if (SRC_FINE) {
 			h2 = meta[p].h2;
 			build_tile_from_fine_faces16(S, src, p, t); // (tile b was last read two iterations ago)
@@ -348,8 +372,9 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 			h2 = ZERO_GUESS ? meta[p].h2 : GD[b].h2;
 			// table entry of the patch after the next -> metaS (read by describe() after the next barrier but one)
 			if (!ZERO_GUESS && t < MW && gn + (int) gridDim.x < npatch)
-				cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pn + gridDim.x) + t, true);
-			if (skip_neumann && (ZERO_GUESS ? meta[p].neumann : GD[b].neu)) { // CTA-uniform: this patch belongs to the general path
+				cp_async8(&metaS[t], reinterpret_cast<const double *>(meta + pnn) + t, true);
+			if (NEU || skip_neumann) neu_p = ZERO_GUESS ? meta[p].neumann : GD[b].neu;
+			if (NEU ? neu_p == 0 : (skip_neumann && neu_p)) { // CTA-uniform: this patch belongs to the other launch
 				if (!ZERO_GUESS) {
 					// keep the pipeline of the next patch's interface values going: all six sides at once, nothing to hide behind
 					SideGamma16<PROLONG> s6[6];
@@ -368,7 +393,7 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 						for (int s = 0; s < 4; s++) Gs[s * 256 + t] = s6[s].finish(gp, s, meta, pn, t, Fin, uc);
 						gz0 = s6[4].finish(gp, 4, meta, pn, t, Fin, uc);
 						gz1 = s6[5].finish(gp, 5, meta, pn, t, Fin, uc);
-						if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + gridDim.x, b);
+						if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pnn, b);
 					}
 				}
 				continue;
@@ -410,9 +435,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				}
 				if (next) sg.template issue<2>(gp.d[4], t, lo, hi, Fin, uc);
 			}
-			dst2_forward<N>(v, mg);
+			if (NEU) {
+				general_transform<N>(nt.mats, axis_kind(neu_p, 2).fwd, v, q, PL, mg);
+			} else {
+				dst2_forward<N>(v, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) q[k * PL] = v[k];
+				for (int k = 0; k < N; k++) q[k * PL] = v[k];
+			}
 			if (!ZERO_GUESS && next) gz0 = sg.finish(gp, 4, meta, pn, t, Fin, uc);
 		}
 		__syncwarp(); // rows (y, k_z) with y in {2w, 2w+1} were produced by this warp
@@ -425,9 +454,13 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j + 1]    = d.y;
 			}
 			if (!ZERO_GUESS && next) sg.template issue<2>(gp.d[5], t, lo, hi, Fin, uc);
-			dst2_forward<N>(v, mg);
+			if (NEU) {
+				general_transform<N>(nt.mats, axis_kind(neu_p, 0).fwd, v, reinterpret_cast<double *>(rowp), 1, mg);
+			} else {
+				dst2_forward<N>(v, mg);
 #pragma unroll
-			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+				for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			}
 			if (!ZERO_GUESS && next) gz1 = sg.finish(gp, 5, meta, pn, t, Fin, uc);
 		}
 		if (!ZERO_GUESS) cp_async_wait_all(); // metaS has landed (made visible by the barrier)
@@ -437,33 +470,48 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * ROW];
 			if (!ZERO_GUESS && next) sg.template issue<0>(gp.d[0], t, lo, hi, Fin, uc);
-#if TGPU_S16_TRIDIAG
-			// z and x are diagonalised: what is left per (k_x, k_z) is a tridiagonal system along y
-			TriSolve<N>::forward(v, eig + t, h2 * (4.0 / (N * N)));
-#else
-			dst2_forward<N>(v, mg);
-			const double *er = eig + t; // eig[k_y * 256 + k_x + 16 k_z] (the table is symmetric in the axes)
+			if (NEU) {
+				// transform along y as well and divide by the eigenvalue sum of (k_x, k_y, k_z) = (lo, k, hi)
+				const AxisKind kx = axis_kind(neu_p, 0), ky = axis_kind(neu_p, 1), kz = axis_kind(neu_p, 2);
+				general_transform<N>(nt.mats, ky.fwd, v, q, ROW, mg);
+				const double rest     = __ldg(nt.lam + kx.lam * N + lo) + __ldg(nt.lam + kz.lam * N + hi);
+				const double scale    = h2 * (8.0 / (N * N * N));
+				const bool   singular = neu_p == 63 && t == 0; // all-Neumann patch: the constant mode is left out
 #pragma unroll
-			for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
+				for (int k = 0; k < N; k++) v[k] = (singular && k == 0) ? 0.0 : q[k * ROW] * scale / (__ldg(nt.lam + ky.lam * N + k) + rest);
+			} else {
+#if TGPU_S16_TRIDIAG
+				// z and x are diagonalised: what is left per (k_x, k_z) is a tridiagonal system along y
+				TriSolve<N>::forward(v, eig + t, h2 * (4.0 / (N * N)));
+#else
+				dst2_forward<N>(v, mg);
+				const double *er = eig + t; // eig[k_y * 256 + k_x + 16 k_z] (the table is symmetric in the axes)
+#pragma unroll
+				for (int k = 0; k < N; k++) v[k] *= h2 * __ldg(er + k * G::M);
 #endif
+			}
 			double gx0 = 0.0, gx1 = 0.0;
 			if (!ZERO_GUESS && next) {
 				gx0 = sg.finish(gp, 0, meta, pn, t, Fin, uc);
 				sg.template issue<0>(gp.d[1], t, lo, hi, Fin, uc);
 			}
+			if (NEU) {
+				general_transform<N>(nt.mats, axis_kind(neu_p, 1).inv, v, q, ROW, mg);
+			} else {
 #if TGPU_S16_TRIDIAG
-			TriSolve<N>::backward(v, eig + t);
+				TriSolve<N>::backward(v, eig + t);
 #else
-			dst3_inverse<N>(v, mg);
+				dst3_inverse<N>(v, mg);
 #endif
 #pragma unroll
-			for (int k = 0; k < N; k++) q[k * ROW] = v[k];
+				for (int k = 0; k < N; k++) q[k * ROW] = v[k];
+			}
 			if (!ZERO_GUESS && next) {
 				gx1 = sg.finish(gp, 1, meta, pn, t, Fin, uc);
 				Gs[t]       = gx0; // (this patch's values were consumed before the barrier above)
 				Gs[256 + t] = gx1;
 				// descriptors of the patch after the next; GD[b] was last read before this iteration's first barrier
-				if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pn + gridDim.x, b);
+				if (gn + (int) gridDim.x < npatch) describe(*reinterpret_cast<const PatchMeta *>(metaS), pnn, b);
 			}
 		}
 		__syncthreads();
@@ -476,21 +524,33 @@ smooth3d16_kernel(const PatchMeta *__restrict__ meta, int p0, int P, const doubl
 				v[2 * j + 1]    = d.y;
 			}
 			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[2], t, lo, hi, Fin, uc);
-			dst3_inverse<N>(v, mg);
+			if (NEU) {
+				general_transform<N>(nt.mats, axis_kind(neu_p, 0).inv, v, reinterpret_cast<double *>(rowp), 1, mg);
+			} else {
+				dst3_inverse<N>(v, mg);
 #pragma unroll
-			for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+				for (int j = 0; j < N / 2; j++) rowp[j] = make_double2(v[2 * j], v[2 * j + 1]);
+			}
 			if (!ZERO_GUESS && next) gy0 = sg.finish(gp, 2, meta, pn, t, Fin, uc);
 		}
-		if (WRITE_U) {
+		if (WRITE_U || NEU) { // (the Neumann instantiation has no slices-only shortcut: full inverse, u stored only if wanted)
 			__syncwarp();
 			double *q = S + lo + hi * ROW; // z inverse: pencil (x, y) = (lo, hi)
 #pragma unroll
 			for (int k = 0; k < N; k++) v[k] = q[k * PL];
 			if (!ZERO_GUESS && next) sg.template issue<1>(gp.d[3], t, lo, hi, Fin, uc);
-			dst3_inverse<N>(v, mg);
-			double *up = u + (size_t) p * G::NC + t;
+			if (NEU) {
+				general_transform<N>(nt.mats, axis_kind(neu_p, 2).inv, v, q, PL, mg);
 #pragma unroll
-			for (int k = 0; k < N; k++) __stcs(up + k * G::M, v[k]); // streaming store: u is not read again soon, the face buffers should stay in L2
+				for (int k = 0; k < N; k++) v[k] = q[k * PL];
+			} else {
+				dst3_inverse<N>(v, mg);
+			}
+			double *up = u + (size_t) p * G::NC + t;
+			if (WRITE_U) {
+#pragma unroll
+				for (int k = 0; k < N; k++) __stcs(up + k * G::M, v[k]); // streaming store: u is not read again soon, the face buffers should stay in L2
+			}
 			if (EMIT) {
 				double *Fp       = Fout + (size_t) p * G::S * G::M;
 				st_keep_l2(&Fp[4 * G::M + t], v[0], l2keep);

@@ -201,6 +201,8 @@ struct LevelDev {
 	double *   Fa = nullptr, *Fb = nullptr; // face buffers
 	double *   u = nullptr, *f = nullptr, *r = nullptr; // cycle work vectors (lazily allocated)
 	bool       has_neumann = false;
+	int32_t *  neu_list = nullptr;          // device: owned patches with Neumann domain sides, ascending (smooth3d16_kernel<.., NEU>)
+	std::vector<int32_t> neu_host;          // the same list on the host (sub-ranges are found by binary search)
 	int32_t *  children = nullptr; // [P][8] patches of the next finer level per octant ([1] == -2: [0] is the same patch there); null: incomplete
 	// peer-to-peer halo exchange: peers' face buffers and flags mapped with CUDA IPC (see setup_p2p)
 	bool       p2p = false;
@@ -364,6 +366,7 @@ template <bool Z, bool E, bool PR, bool W, bool SF = false> static int set_smem_
 {
 	CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
 	if (!Z && !SF) CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, SF, !Z && !SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
+	if (!SF) CU(cudaFuncSetAttribute(smooth3d16_kernel<Z, E, PR, W, false, false, !SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smooth3d16_smem_bytes(Z, SF)));
 	return TGPU_OK;
 }
 static int set_smem_attrs_3d16()
@@ -742,6 +745,7 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 			pm.inv_h2         = 1.0 / (hx * hx);
 			pm.neumann        = d.neumann_bits ? d.neumann_bits[p] : 0;
 			if (pm.neumann) L.has_neumann = true;
+			if (pm.neumann && p < L.P) L.neu_host.push_back(p);
 			pm.parent_idx     = d.parent_idx ? d.parent_idx[p] : -1;
 			pm.orth_on_parent = d.orth_on_parent ? d.orth_on_parent[p] : -1;
 			if (l + 1 < nlevels && p < L.P) {
@@ -776,6 +780,7 @@ static int hierarchy_create_impl(tgpu_ctx *ctx, int D, int n, int nlevels, const
 			}
 		}
 		TRY(dev_upload(&L.meta, meta.data(), meta.size()));
+		if (!L.neu_host.empty()) TRY(dev_upload(&L.neu_list, L.neu_host.data(), L.neu_host.size()));
 		TRY(dev_upload(&L.spacing, d.spacing, (size_t) d.npatch * D));
 		if (d.starts) TRY(dev_upload(&L.starts, d.starts, (size_t) d.npatch * D));
 		CU(cudaMalloc(&L.Fa, L.nface * sizeof(double)));
@@ -1249,6 +1254,7 @@ extern "C" int tgpu_hierarchy_destroy(tgpu_hier *h)
 	if (h->s_out) cudaStreamDestroy(h->s_out);
 	for (LevelDev &L : h->levels) {
 		cudaFree(L.meta);
+		cudaFree(L.neu_list);
 		cudaFree(L.children);
 		cudaFree(L.starts);
 		cudaFree(L.spacing);
@@ -1660,18 +1666,30 @@ static int k_apply(tgpu_hier *h, int l, int mode, const double *u, const double 
 // zero_guess: gamma = 0 (Fin unused); emit: write the faces of the new u to Fout;
 // uc != nullptr: face values are Fin + (P uc) on the boundary cells (fused prolongation);
 // write_u = false (needs emit): only the faces of the new u are wanted (the generic kernel still writes u)
+// neu: the instantiation for the patches with Neumann domain sides (it sweeps exactly those of the range)
 template <bool Z, bool E, bool PR, bool W, bool SF = false>
 static int launch_smooth3d16(tgpu_hier *h, const LevelDev &L, int p0, int p1, const double *f, double *u, const double *Fin, double *Fout,
-                             const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0)
+                             const double *uc, FineSrc16 src = FineSrc16{}, HaloSync hs = HaloSync{}, int skip_neumann = 0, bool neu = false)
 {
+	if (neu) {
+		if (SF || hs.enabled) return fail(TGPU_ERR_ARG, "smooth3d16: the Neumann instantiation is single-GPU, right-hand side from memory");
+		// the patches of [p0, p1) with Neumann sides: a contiguous piece of the level's (ascending) list
+		const auto b0 = std::lower_bound(L.neu_host.begin(), L.neu_host.end(), p0), b1 = std::lower_bound(L.neu_host.begin(), L.neu_host.end(), p1);
+		const int  nn = (int) (b1 - b0);
+		if (nn == 0) return TGPU_OK;
+		const dim3 gridn(std::min(nn, h->ctx->sm_count * s16_ctas_per_sm(Z, false, true))), blockn(S16_BLOCK);
+		return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, false, false, !SF>, gridn, blockn, smooth3d16_smem_bytes(Z, false), (const PatchMeta *) L.meta, p0,
+		              p1, f, u, Fin, Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, FineSrc16{}, HaloSync{}, 0,
+		              NeuTabs{h->mats, h->lam, L.neu_list + (b0 - L.neu_host.begin()), nn});
+	}
 	const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * s16_ctas_per_sm(Z, SF))), block(S16_BLOCK);
 	if (hs.enabled) {
 		if (Z || SF) return fail(TGPU_ERR_ARG, "smooth3d16: no halo hand-over in a zero-guess sweep");
 		return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF, !Z && !SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u,
-		              Fin, Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann);
+		              Fin, Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann, NeuTabs{});
 	}
 	return launch(h->ctx, smooth3d16_kernel<Z, E, PR, W, SF>, grid, block, smooth3d16_smem_bytes(Z, SF), (const PatchMeta *) L.meta, p0, p1, f, u, Fin,
-	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann);
+	              Fout, (const double *) (TGPU_S16_TRIDIAG ? h->tri : h->eig), uc, src, hs, skip_neumann, NeuTabs{});
 }
 // can the first (zero-guess) sweep on level lc assemble its right-hand side from level lc - 1's faces?
 // Opt-in (TGPU_FINE_SOURCE=1): measured on config B the assembly stage's dependent gathers (children -> neighbour
@@ -1749,7 +1767,23 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	if (h->D == 3 && h->N == 16 && !h->generic_kernels && (!general || mixed16)) { // the generic kernel has the Neumann path
 		const int key = (zero_guess ? 8 : 0) | (emit ? 4 : 0) | (uc ? 2 : 0) | (write_u ? 1 : 0);
 		const int skipn = mixed16 ? 1 : 0;
-		if (mixed16) { // the general path first (it always writes u), then the specialised kernel on the rest
+		// the Neumann instantiation of the same kernel first, then the plain one on the rest (TGPU_NEUMANN_FAST=0: smooth_kernel's
+		// general path instead, which always writes u)
+		static const bool neu_fast = !(getenv("TGPU_NEUMANN_FAST") && atoi(getenv("TGPU_NEUMANN_FAST")) == 0);
+		if (mixed16 && neu_fast) {
+			switch (key) {
+			case 8 | 4 | 1: TRY((launch_smooth3d16<true, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 8 | 1: TRY((launch_smooth3d16<true, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 8 | 4: TRY((launch_smooth3d16<true, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 4 | 1: TRY((launch_smooth3d16<false, true, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 1: TRY((launch_smooth3d16<false, false, false, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 4: TRY((launch_smooth3d16<false, true, false, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 4 | 2 | 1: TRY((launch_smooth3d16<false, true, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 2 | 1: TRY((launch_smooth3d16<false, false, true, true>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			case 4 | 2: TRY((launch_smooth3d16<false, true, true, false>(h, L, p0, p1, f, u, Fin, Fout, uc, FineSrc16{}, HaloSync{}, 0, true))); break;
+			default: return fail(TGPU_ERR_ARG, "k_smooth: bad variant");
+			}
+		} else if (mixed16) {
 			using G        = Geo<3, 16>;
 			const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * smooth_min_blocks<16>())), block(TGPU_THREADS);
 			const size_t sm = smooth_smem_bytes<3, 16, true>();
