@@ -1714,7 +1714,11 @@ static int k_smooth(tgpu_hier *h, int l, bool zero_guess, bool emit, const doubl
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return hs.push ? fail(TGPU_ERR_ARG, "k_smooth: a launch that pushes faces needs patches") : TGPU_OK;
 	if (!emit) write_u = true;
-	h->ctx->clamp_resident = hs.push != nullptr; // consumed by the next launch()
+	struct ClampScope { // the flag is consumed by the next launch(); never leave it set behind an error return
+		tgpu_ctx *c;
+		~ClampScope() { c->clamp_resident = false; }
+	} clamp_scope{h->ctx};
+	h->ctx->clamp_resident = hs.push != nullptr;
 	Tag tg(h->ctx, zero_guess ? (write_u ? "smooth_zero_guess" : "smooth_zero_guess_faces")
 	                          : (uc ? (write_u ? "smooth_prolong" : "smooth_prolong_faces") : (write_u ? "smooth" : "smooth_faces")),
 	       l);
@@ -1874,7 +1878,11 @@ static int k_face_residual_restrict(tgpu_hier *h, int l, const double *Fnew, con
 	if (hsp && !halo_in_kernel(h, l)) return fail(TGPU_ERR_ARG, "k_face_residual_restrict: in-kernel halo hand-over is not available for this level");
 	if (p1 < 0) p1 = L.P;
 	if (p1 <= p0) return hs.push ? fail(TGPU_ERR_ARG, "k_face_residual_restrict: a launch that pushes faces needs patches") : TGPU_OK;
-	h->ctx->clamp_resident = hs.push != nullptr; // consumed by the next launch()
+	struct ClampScope { // the flag is consumed by the next launch(); never leave it set behind an error return
+		tgpu_ctx *c;
+		~ClampScope() { c->clamp_resident = false; }
+	} clamp_scope{h->ctx};
+	h->ctx->clamp_resident = hs.push != nullptr;
 	Tag tg(h->ctx, "face_residual_restrict", l);
 	if (is_3d32(h)) {
 		const dim3 grid(std::min(p1 - p0, h->ctx->sm_count * 4)), block(TGPU_THREADS);

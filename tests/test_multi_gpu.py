@@ -117,10 +117,11 @@ def test_distributed_cycle_specialised_kernels_match_oracle(mesh_file, D, n, div
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
 
 
-@pytest.mark.parametrize("env", [{"TGPU_HALO_IN_KERNEL": "0"}, {"TGPU_P2P": "0"}])
+@pytest.mark.parametrize("env", [{"TGPU_PUSH_IN_KERNEL": "0"}, {"TGPU_HALO_IN_KERNEL": "0"}, {"TGPU_P2P": "0"}])
 def test_alternative_exchange_paths_match_reference(env):
-    """the exchange paths behind the diagnostic switches - separate wait / signal kernels with split interior / boundary
-    launches, and pack -> ncclSend/ncclRecv -> unpack (the fallback when peer mapping is unavailable) - give the same cycle"""
+    """the exchange paths behind the diagnostic switches - a separate push launch instead of the consumer launch's own
+    prologue, separate wait / signal kernels with split interior / boundary launches, and pack -> ncclSend/ncclRecv -> unpack
+    (the fallback when peer mapping is unavailable) - give the same cycle"""
     world = min(_ngpu(), 2)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
