@@ -49,6 +49,10 @@ def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret, env=Non
     h.vcycle(f, ug, g)
     h.vcycle(f, ug, g)
     out["vcycle_graph"] = ug.download().reshape(-1, nc)
+    # several sweeps per visit: the in-kernel hand-over of a level's first exchanges mixed with the separate push / wait
+    # kernels of the later ones, all on the same generation counters
+    h.vcycle(f, ug, pps.CycleOpts.default(use_graph=2, pre_sweeps=2, post_sweeps=2, coarse_sweeps=2))
+    out["vcycle22"] = ug.download().reshape(-1, nc)
     out["fnorm"] = f.two_norm()
     out["integral"] = h.integrate(f)  # (Domain::integrate(f), Domain::volume()) summed over the ranks
     h.apply(0, f, r)
@@ -115,6 +119,8 @@ def test_distributed_cycle_specialised_kernels_match_oracle(mesh_file, D, n, div
     ref = go.vcycle(levels, fn)
     assert rel_l2(gather("vcycle"), ref.reshape(-1, n ** D)) < 1e-12
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
+    ref22 = go.vcycle(levels, fn, pre=2, post=2, coarse_sweeps=2)
+    assert rel_l2(gather("vcycle22"), ref22.reshape(-1, n ** D)) < 1e-12
 
 
 @pytest.mark.parametrize("env", [{"TGPU_PUSH_IN_KERNEL": "0"}, {"TGPU_HALO_IN_KERNEL": "0"}, {"TGPU_P2P": "0"}])
