@@ -239,11 +239,16 @@ def test_neumann_vs_oracle_seeded(ctx):
         mesh.close()
 
 
-@pytest.mark.parametrize("mesh_file,D,n,divide", [("2refine.bin", 3, 16, 1), ("2uni.bin", 3, 32, 0), ("2d2ref.bin", 2, 32, 1)])
-def test_cycle_is_bitwise_reproducible(ctx, mesh_file, D, n, divide):
+@pytest.mark.parametrize("mesh_file,D,n,divide,neumann", [("2refine.bin", 3, 16, 1, False), ("2uni.bin", 3, 32, 0, False), ("2d2ref.bin", 2, 32, 1, False),
+                                                          ("2refine.bin", 3, 16, 1, True)])  # Neumann instantiation + plain one on mixed levels
+def test_cycle_is_bitwise_reproducible(ctx, mesh_file, D, n, divide, neumann):
     """the specialised kernels hand data between warps, CTAs of a cluster and kernels through shared memory, distributed
     shared memory and face buffers: a missing barrier would show up as bits that change from run to run"""
-    h, mesh = build(ctx, mesh_file, D, n, divide)
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D)
+    if neumann:
+        mesh.set_neumann(True)
+    mesh.refine_leaves(divide)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
     fn = np.random.default_rng(21).standard_normal(h.ncells(0))
     f, u = h.new_vec(0, fn), h.new_vec(0)
     ref_bits = None

@@ -14,7 +14,9 @@ import pressurepoissonsolver_b200 as pps  # noqa: E402
 
 MESHES = os.path.join(ROOT, "tests", "golden", "meshes")
 ctx = pps.Context(0)
-cases = [("2refine.bin", 3, 16, 1, False), ("2uni.bin", 3, 32, 0, False), ("2d2ref.bin", 2, 32, 1, False), ("2uni.bin", 3, 32, 0, True)]
+cases = [("2refine.bin", 3, 16, 1, False), ("2uni.bin", 3, 32, 0, False), ("2d2ref.bin", 2, 32, 1, False), ("2uni.bin", 3, 32, 0, True),
+         ("2refine.bin", 3, 16, 0, True)]  # the last: Neumann instantiation of smooth3d16_kernel on a refined mesh
+REPS = int(os.environ.get("REPS", "30"))
 if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
 for mesh_file, D, n, divide, neumann in cases:
@@ -34,7 +36,7 @@ for mesh_file, D, n, divide, neumann in cases:
     e2 = np.linalg.norm(u.download() - go.vcycle(levels, fn, pre=2, post=2).ravel()) / np.linalg.norm(u.download())
     # run-to-run determinism (a shared-memory or halo race would show up as differing bits), graph replay included
     ref_bits = None
-    for rep in range(30):
+    for rep in range(REPS):
         h.vcycle(f, u, pps.CycleOpts.default(use_graph=rep & 1))
         bits = u.download().tobytes()
         ref_bits = ref_bits or bits
