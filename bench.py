@@ -414,6 +414,19 @@ def e2e_block(env, h, f, u, opts, steps, cells, total_cells):
             "bit_identical_to_device_resident_cycle": same}
 
 
+def nvlink_block(env, part, D, n, ms_per_step):
+    """bytes every rank stores into its peers' face buffers per V(1,1) cycle (two hand-overs per distributed level: the
+    faces of the pre-smoothed u, then faces + prolonged correction), max over ranks, against NVLink 5's nominal 900 GB/s
+    per direction per GPU (north star: fraction of the NVLink roofline where sharded)"""
+    M = n ** (D - 1)
+    faces = [sum(len(p["send_patch"]) for p in part.level(l)["peers"]) for l in range(part.ndist)]
+    sent = float(sum(faces) * M * 8 * 2)
+    sent_max, = env.reduce_max(sent)
+    gbs = sent_max / (ms_per_step * 1e-3) / 1e9
+    return {"bytes_sent_per_rank_per_cycle": sent_max, "faces_sent_per_level_rank0": faces, "achieved_gbs_per_rank": gbs, "peak_gbs": 900.0,
+            "frac": gbs / 900.0, "note": "halo faces only; the exchange is latency-bound (two hand-overs per level visit), not bandwidth-bound"}
+
+
 def multi_gpu_parity(env):
     """driver-run numerical evidence for the N > 1 path, outside every timed region: distributed V-cycles against the
     reference's golden vectors (tests/golden/*.npz, produced by the reference's own code) and, for the specialised 16^3 /
@@ -542,6 +555,8 @@ def main():
         "setup_s": res["setup_s"], "cells_rank0": cells, "level_cells_rank0": level_cells,
         "kernel_profile_ms_per_step": res["kernel_profile_ms_per_step"],
     }
+    if env.world > 1 and part is not None:
+        line["nvlink"] = nvlink_block(env, part, D, n, res["ms_per_step"])
     if not args.cycle_only:
         line["time_to_solution"] = time_to_solution(env, h, f, opts, total_cells)
         line["e2e"] = e2e_block(env, h, f, u, opts, args.steps, cells, total_cells)
