@@ -308,7 +308,11 @@ def roofline_block(cfg, D, n, cells, level_cells, agg, ms_per_step, steps):
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "ms_per_launch": tot_ms / nl if nl else None, "algorithmic_bytes_per_launch": tot_b / nl if nl else None,
             "per_instantiation": per, "share_of_step": share,
-            "vcycle_algorithmic_gbs": cycle_gbs, "vcycle_frac": cycle_gbs / peak, "vcycle_bytes_per_dof": cycle_bytes / cells}
+            "vcycle_algorithmic_gbs": cycle_gbs, "vcycle_frac": cycle_gbs / peak, "vcycle_bytes_per_dof": cycle_bytes / cells,
+            # also against B200's nominal 8 TB/s, and the traffic of the unfused call-by-call sequence the
+            # reference executes (104 B per cell per level visit instead of the compulsory 48) moved in the same time
+            "vcycle_frac_of_nominal_8000_gbs": cycle_gbs / 8000.0,
+            "vcycle_gbs_if_unfused_104_bytes_per_cell_visit": cycle_gbs * 104.0 / ALGO_BYTES_PER_CELL_VISIT}
 
 
 def time_to_solution(env, h, f, opts, total_cells):
