@@ -138,3 +138,30 @@ def test_halo_exchange_over_gloo_world_size_2():
         p.join(120)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def test_bench_nvlink_block_counts_the_send_lists():
+    """bench.py's `nvlink` figure = 8 bytes x face size x send-list length x 2 hand-overs per distributed level; on two ranks
+    what one rank sends the other receives"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(MESHES), "..", "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class OneRankEnv:
+        def reduce_max(self, *vals):
+            return list(vals)
+
+    mesh = pps.Mesh.load(os.path.join(MESHES, "2refine.bin"), 3).refine_leaves(1)
+    parts = [pps.Partition(mesh, 8, r, 2, min_patches_per_rank=2) for r in range(2)]
+    blocks = [bench.nvlink_block(OneRankEnv(), p, 3, 8, 1.0) for p in parts]
+    for r, (p, b) in enumerate(zip(parts, blocks)):
+        assert p.ndist >= 1 and len(b["faces_sent_per_level_rank0"]) == p.ndist
+        sent = sum(len(q["send_patch"]) for l in range(p.ndist) for q in p.level(l)["peers"])
+        recv_other = sum(len(q["recv_slot"]) for l in range(p.ndist) for q in parts[1 - r].level(l)["peers"])
+        assert sent == recv_other > 0
+        assert b["bytes_sent_per_rank_per_cycle"] == sent * 64 * 8 * 2
+        assert abs(b["frac"] - b["achieved_gbs_per_rank"] / 900.0) < 1e-15
+    for p in parts:
+        p.close()
+    mesh.close()
