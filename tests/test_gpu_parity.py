@@ -664,6 +664,62 @@ def test_full_size_properties(config_b):
     assert np.all(c.download() == 3.0)
 
 
+def test_full_size_config_d_properties(ctx):
+    """BASELINE config D itself (4uni.bin --divide 2, n = 32: 32,768 patches, 1,073,741,824 cells, the workload bench.py
+    reports): size-independent properties evaluated on the device (no 8.6 GB host round trips): V(2 f) = 2 V(f) bit for bit,
+    additivity V(f1 + f2) = V(f1) + V(f2) to rounding, the face-residual schedule against the one that forms the residual
+    from u and f, the stationary iteration's contraction, and second-order accuracy of the converged solution."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs a 180 GB B200")
+    mesh = pps.Mesh.load(os.path.join(MESHES, "4uni.bin"), 3).refine_leaves(2)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, 32)
+    assert h.ncells(0) == 1073741824 and h.nlevels == 6
+    f, e, u, u2, w = (h.new_vec(0) for _ in range(5))
+    h.init_trig_rhs(f, e)
+    h.vcycle(f, u)
+    w.copy(f)
+    w.scale(2.0)
+    h.vcycle(w, u2)
+    u2.scale(0.5)
+    u2.add_scaled(-1.0, u)
+    assert u2.inf_norm() == 0.0                      # powers of two commute with every operation of the cycle
+    # additivity with a second, unrelated right-hand side (the first cycle's result)
+    w.copy(f)
+    w.add(u)                                         # w = f + u
+    h.vcycle(u, u2)                                  # V(u)
+    u2.add(u)                                        # ... + V(f)   (u still holds V(f): the cycle does not touch its input)
+    r = h.new_vec(0)
+    h.vcycle(w, r)                                   # V(f + u)
+    r.add_scaled(-1.0, u2)
+    assert r.two_norm() / u2.two_norm() < 1e-13
+    h.vcycle(f, u2, pps.CycleOpts.default(fused=2, use_graph=0))
+    u2.add_scaled(-1.0, u)
+    assert u2.two_norm() / u.two_norm() < 1e-13
+    u.set(0.0)
+    hist = []
+    fn = f.two_norm()
+    for k in range(5):
+        h.residual(0, f, u, r)
+        hist.append(r.two_norm() / fn)
+        h.vcycle(r, u2)
+        u.add(u2)
+    fac = [hist[i + 1] / hist[i] for i in range(4)]
+    assert max(fac) < 0.35, fac
+    for v in (u2, w, r):
+        v.close()
+    h.trim()
+    x = h.new_vec(0)
+    its, rel = h.bicgstab(f, x, tol=1e-10, max_it=30)
+    assert its <= 10 and rel <= 1e-10
+    x.add_scaled(-1.0, e)
+    assert x.inf_norm() < 2e-5                       # h = 1/1024: second-order discretisation error (config B, h = 1/256: < 2e-4)
+    for v in (x, f, e, u):
+        v.close()
+    h.close()
+    mesh.close()
+
+
 def test_medium_size_vs_reference_binary(ctx):
     """If the reference-built oracle binary travelled with the repo, compare a 2.1 M-cell V-cycle
     and its per-cycle residual reduction against the reference run on the same inputs."""
