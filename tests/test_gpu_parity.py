@@ -720,6 +720,53 @@ def test_full_size_config_d_properties(ctx):
     mesh.close()
 
 
+@pytest.mark.parametrize("mesh_file,D,n,divide,cells", [("2refine.bin", 3, 16, 3, 31457280), ("2d_multi_refine_8.bin", 2, 32, 4, 41943040)])
+def test_full_size_adaptive_config_properties(ctx, mesh_file, D, n, divide, cells):
+    """BASELINE configs C (2refine --divide 3, 16^3 patches) and E (2D multi_refine_8 --divide 4, 32^2 patches, 13 levels) at
+    the sizes bench.py reports: exact homogeneity, additivity, the three schedules against each other, a contracting
+    stationary iteration and a converging BiCGStab, all evaluated on the device"""
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
+    h = pps.Hierarchy.from_mesh(ctx, mesh, n)
+    assert h.ncells(0) == cells
+    f, e, u, u2, w, r = (h.new_vec(0) for _ in range(6))
+    h.init_trig_rhs(f, e)
+    h.vcycle(f, u)
+    w.copy(f)
+    w.scale(4.0)
+    h.vcycle(w, u2)
+    u2.scale(0.25)
+    u2.add_scaled(-1.0, u)
+    assert u2.inf_norm() == 0.0
+    w.copy(f)
+    w.add(u)
+    h.vcycle(u, u2)
+    u2.add(u)
+    h.vcycle(w, r)
+    r.add_scaled(-1.0, u2)
+    assert r.two_norm() / u2.two_norm() < 1e-13
+    for fused in (0, 2):
+        h.vcycle(f, u2, pps.CycleOpts.default(fused=fused, use_graph=0))
+        u2.add_scaled(-1.0, u)
+        assert u2.two_norm() / u.two_norm() < 1e-13, fused
+    u.set(0.0)
+    hist = []
+    fn = f.two_norm()
+    for k in range(6):
+        h.residual(0, f, u, r)
+        hist.append(r.two_norm() / fn)
+        h.vcycle(r, u2)
+        u.add(u2)
+    fac = [hist[i + 1] / hist[i] for i in range(5)]
+    assert max(fac) < 0.8 and hist[-1] < 0.05 * hist[0], (fac, hist)
+    x = h.new_vec(0)
+    its, rel = h.bicgstab(f, x, tol=1e-10, max_it=60)
+    assert rel <= 1e-10 and its <= 40, (its, rel)
+    h.residual(0, f, x, r)
+    assert r.two_norm() / fn < 2e-10                 # the recurrence residual BiCGStab reports is the true one
+    h.close()
+    mesh.close()
+
+
 def test_medium_size_vs_reference_binary(ctx):
     """If the reference-built oracle binary travelled with the repo, compare a 2.1 M-cell V-cycle
     and its per-cycle residual reduction against the reference run on the same inputs."""
