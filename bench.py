@@ -409,7 +409,9 @@ def e2e_block(env, h, f, u, opts, steps, cells, total_cells):
         b_.close()
     e2e_ms, serial_ms, copy_ms = env.reduce_max(e2e_ms, serial_ms, copy_ms)
     assert same, "e2e result differs from the device-resident cycle"
-    return {"value": total_cells / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": cells * 8, "d2h_bytes_per_step": cells * 8,
+    # bytes of the whole job per step, like `value` (every rank copies its own patches' share: cells * 8 each way)
+    return {"value": total_cells / (e2e_ms * 1e-3), "unit": "DOF/s", "h2d_bytes_per_step": total_cells * 8, "d2h_bytes_per_step": total_cells * 8,
+            "h2d_bytes_per_step_rank0": cells * 8, "d2h_bytes_per_step_rank0": cells * 8,
             "ms_per_step": e2e_ms, "steps": n_pipe,
             "api": "tgpu_vcycle_host_async + tgpu_vcycle_host_wait (per step: pinned host f -> device, V-cycle, u -> pinned host; consecutive steps pipelined over copy-in / compute / copy-out streams)",
             "serial_ms_per_step": serial_ms, "serial_value": total_cells / (serial_ms * 1e-3), "serial_api": "tgpu_vcycle_host (one blocking call per step)",
