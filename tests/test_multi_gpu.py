@@ -34,7 +34,10 @@ def _worker(rank, world, idfile, mesh_file, D, n, divide, f_global, ret, env=Non
             time.sleep(0.05)
         uid = open(idfile, "rb").read()
     ctx.comm_init(uid, rank, world)
-    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D).refine_leaves(divide)
+    mesh = pps.Mesh.load(os.path.join(MESHES, mesh_file), D)
+    if (env or {}).get("TEST_NEUMANN"):
+        mesh.set_neumann(True)
+    mesh.refine_leaves(divide)
     part = pps.Partition(mesh, n, rank, world, min_patches_per_rank=2)
     h = pps.Hierarchy.from_partition(ctx, part)
     pl = part.level(0)
@@ -138,6 +141,24 @@ def test_alternative_exchange_paths_match_reference(env):
     ret, gather, ncells = run_distributed(world, "2refine.bin", 3, 16, 1, fn, env=env)
     assert rel_l2(gather("vcycle"), go.vcycle(levels, fn).reshape(-1, 16 ** 3)) < 1e-12
     assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
+
+
+def test_distributed_neumann_cycle_matches_oracle():
+    """Neumann domain boundaries across GPUs: mixed levels (the plain and the Neumann instantiation of smooth3d16_kernel on
+    the interior / boundary ranges of every rank, separate hand-over kernels) against the oracle"""
+    world = min(_ngpu(), 2)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gmg_oracle as go
+    levels = go.build_hierarchy(os.path.join(MESHES, "3uni.bin"), 3, 16, 1, neumann=True)
+    fn = np.random.default_rng(13).standard_normal(levels[0].shape)
+    fn -= fn.mean()
+    ret, gather, ncells = run_distributed(world, "3uni.bin", 3, 16, 1, fn, env={"TEST_NEUMANN": "1"})
+    assert ret[0]["ndist"] >= 1 and ncells == fn.size
+    assert rel_l2(gather("vcycle"), go.vcycle(levels, fn).reshape(-1, 16 ** 3)) < 1e-10
+    assert np.array_equal(gather("vcycle_graph"), gather("vcycle"))
+    assert rel_l2(gather("vcycle22"), go.vcycle(levels, fn, pre=2, post=2, coarse_sweeps=2).reshape(-1, 16 ** 3)) < 1e-10
 
 
 def _replicated_worker(rank, world, idfile, ret):
