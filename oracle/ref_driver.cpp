@@ -18,6 +18,8 @@
  *   meta:OUT                         hierarchy metadata (format: see dump_meta)
  *   rhs:F_OUT:EXACT_OUT              trig manufactured problem, Dirichlet data folded into f
  *   apply:L:U_IN:OUT                 OUT = A_L U                (level 0 = finest)
+ *   matapply:L:U_IN:OUT              3D only: OUT = (MatrixHelper(domain_L).formCRSMatrix()) U - the reference's independent ASSEMBLED
+ *                                    form of the same operator (StencilHelper.h: per-side stencils incl. coarse/fine weights)
  *   smooth:L:F_IN:U_IN:OUT           one block-Jacobi sweep on level L
  *   restrict:L:FINE_IN:OUT           AvgRstr from level L to level L+1
  *   interp:L:COARSE_IN:FINE_IN:OUT   DrctIntp from level L+1 into level L (adds)
@@ -59,6 +61,7 @@
 #include <Thunderegg/BilinearInterpolator.h>
 #include <Thunderegg/GMG/CycleFactory2d.h>
 #include <Thunderegg/GMG/CycleFactory3d.h>
+#include <Thunderegg/MatrixHelper.h>
 #include <Thunderegg/Operators/DomainWrapOp.h>
 #include <Thunderegg/PatchSolvers/DftPatchSolver.h>
 #include <Thunderegg/PatchSolvers/FftwPatchSolver.h>
@@ -101,6 +104,12 @@ template <size_t D> struct Traits;
 template <> struct Traits<3> {
 	using Factory = GMG::CycleFactory3d;
 	using Interp  = TriLinInterp;
+	static void matapply(shared_ptr<Domain<3>> d, Vec u, Vec out)
+	{
+		MatrixHelper  mh(d);
+		PW<Mat>       A = mh.formCRSMatrix();
+		MatMult(A, u, out);
+	}
 	static void rhs(Domain<3> &d, Vec f, Vec e)
 	{
 		auto ffun = [](double x, double y, double z) {
@@ -156,6 +165,12 @@ template <> struct Traits<3> {
 template <> struct Traits<2> {
 	using Factory = GMG::CycleFactory2d;
 	using Interp  = BilinearInterpolator;
+	static void matapply(shared_ptr<Domain<2>>, Vec, Vec)
+	{
+		/* StencilHelper2d.h assembles a different (quadratic) coarse/fine stencil: not the matrix-free operator */
+		cerr << "matapply: 3D only\n";
+		exit(2);
+	}
 	static void rhs(Domain<2> &d, Vec f, Vec e)
 	{
 		auto ffun = [](double x, double y) { return (double) (-5 * M_PI * M_PI * sinl(M_PI * y) * cosl(2 * M_PI * x)); };
@@ -329,6 +344,12 @@ template <size_t D> static int run(int argc, char **argv)
 			auto u = newvec(l), o = newvec(l);
 			read_into(p[2], u->vec);
 			c.levels[l]->getOperator().apply(u, o);
+			write_from(p[3], o->vec);
+		} else if (cmd == "matapply") {
+			int  l = stoi(p[1]);
+			auto u = newvec(l), o = newvec(l);
+			read_into(p[2], u->vec);
+			Traits<D>::matapply(c.domains[l], u->vec, o->vec);
 			write_from(p[3], o->vec);
 		} else if (cmd == "smooth") {
 			int  l = stoi(p[1]);

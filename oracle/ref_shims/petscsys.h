@@ -1,5 +1,5 @@
 /* Single-rank stand-in for the slice of PETSc the reference's GMG path touches
- * (Vec, IS, VecScatter, AO; Mat/PC/KSP only as link stubs).  TEST INFRASTRUCTURE.
+ * (Vec, IS, VecScatter, AO, a minimal assembled Mat; PC/KSP only as link stubs).  TEST INFRASTRUCTURE.
  * Semantics follow SURVEY.md App. C: new Vecs are zero-initialised; block scatters are
  * FORWARD/INSERT y[j*bs+k] = x[idx[j]*bs+k] and REVERSE/ADD x[idx[j]*bs+k] += y[j*bs+k]. */
 #ifndef ORACLE_SHIM_PETSCSYS_H
@@ -35,7 +35,7 @@ struct _p_VecScatter : _p_PetscObject { int bs; std::vector<int> idx; };
 typedef _p_VecScatter *VecScatter;
 struct _p_AO : _p_PetscObject { std::map<int, int> map; };
 typedef _p_AO *AO;
-struct _p_Mat : _p_PetscObject {};
+struct _p_Mat : _p_PetscObject { std::vector<std::map<int, double>> rows; /* assembled rows (MatSetValues), single rank */ };
 typedef _p_Mat *Mat;
 struct _p_PC : _p_PetscObject {};
 typedef _p_PC *PC;
@@ -72,7 +72,8 @@ PetscErrorCode VecScatterBegin(VecScatter, Vec from, Vec to, InsertMode, Scatter
 PetscErrorCode VecScatterEnd(VecScatter, Vec from, Vec to, InsertMode, ScatterMode);
 PetscErrorCode AOCreateMapping(MPI_Comm, PetscInt n, const PetscInt app[], const PetscInt petsc[], AO *);
 PetscErrorCode AOApplicationToPetsc(AO, PetscInt n, PetscInt ia[]);
-/* Mat / PC: link stubs only - the matrix-free GMG path never reaches them */
+/* Mat: a row-map sparse matrix, enough for MatrixHelper::formCRSMatrix + MatMult (the assembled-operator cross-check of
+ * ref_driver's `matapply`); the matrix-free GMG path never reaches it.  PC: link stubs only */
 PetscErrorCode MatCreate(MPI_Comm, Mat *);
 PetscErrorCode MatSetSizes(Mat, PetscInt, PetscInt, PetscInt, PetscInt);
 PetscErrorCode MatSetType(Mat, MatType);

@@ -106,15 +106,37 @@ PetscErrorCode AOApplicationToPetsc(AO ao, PetscInt n, PetscInt ia[])
 	return 0;
 }
 
-/* ---- Mat / PC link stubs ---- */
-PetscErrorCode MatCreate(MPI_Comm, Mat *) { shim_unreachable("MatCreate"); return 1; }
-PetscErrorCode MatSetSizes(Mat, PetscInt, PetscInt, PetscInt, PetscInt) { shim_unreachable("MatSetSizes"); return 1; }
-PetscErrorCode MatSetType(Mat, MatType) { shim_unreachable("MatSetType"); return 1; }
-PetscErrorCode MatMPIAIJSetPreallocation(Mat, PetscInt, const PetscInt *, PetscInt, const PetscInt *) { shim_unreachable("MatMPIAIJSetPreallocation"); return 1; }
-PetscErrorCode MatSetValues(Mat, PetscInt, const PetscInt *, PetscInt, const PetscInt *, const PetscScalar *, InsertMode) { shim_unreachable("MatSetValues"); return 1; }
-PetscErrorCode MatAssemblyBegin(Mat, MatAssemblyType) { shim_unreachable("MatAssemblyBegin"); return 1; }
-PetscErrorCode MatAssemblyEnd(Mat, MatAssemblyType) { shim_unreachable("MatAssemblyEnd"); return 1; }
-PetscErrorCode MatMult(Mat, Vec, Vec) { shim_unreachable("MatMult"); return 1; }
+/* ---- Mat: rows of (column -> value) maps, one rank ---- */
+PetscErrorCode MatCreate(MPI_Comm, Mat *m) { *m = new _p_Mat(); return 0; }
+PetscErrorCode MatSetSizes(Mat m, PetscInt local_rows, PetscInt, PetscInt, PetscInt) { m->rows.assign(local_rows, std::map<int, double>()); return 0; }
+PetscErrorCode MatSetType(Mat, MatType) { return 0; }
+PetscErrorCode MatMPIAIJSetPreallocation(Mat, PetscInt, const PetscInt *, PetscInt, const PetscInt *) { return 0; }
+PetscErrorCode MatSetValues(Mat m, PetscInt nr, const PetscInt *r, PetscInt nc, const PetscInt *c, const PetscScalar *v, InsertMode mode)
+{
+	for (PetscInt i = 0; i < nr; i++) {
+		if (r[i] < 0 || r[i] >= (PetscInt) m->rows.size()) shim_unreachable("MatSetValues: row outside the local range");
+		for (PetscInt j = 0; j < nc; j++) {
+			if (mode == ADD_VALUES) m->rows[r[i]][c[j]] += v[i * nc + j];
+			else m->rows[r[i]][c[j]] = v[i * nc + j];
+		}
+	}
+	return 0;
+}
+PetscErrorCode MatAssemblyBegin(Mat, MatAssemblyType) { return 0; }
+PetscErrorCode MatAssemblyEnd(Mat, MatAssemblyType) { return 0; }
+PetscErrorCode MatMult(Mat m, Vec x, Vec y)
+{
+	if (x->data.size() != m->rows.size() || y->data.size() != m->rows.size()) shim_unreachable("MatMult: size mismatch");
+	for (size_t i = 0; i < m->rows.size(); i++) {
+		double s = 0;
+		for (const auto &e : m->rows[i]) {
+			if (e.first < 0 || e.first >= (int) x->data.size()) shim_unreachable("MatMult: column outside the vector");
+			s += e.second * x->data[e.first];
+		}
+		y->data[i] = s;
+	}
+	return 0;
+}
 PetscErrorCode MatGetRow(Mat, PetscInt, PetscInt *, const PetscInt **, const PetscScalar **) { shim_unreachable("MatGetRow"); return 1; }
 PetscErrorCode MatRestoreRow(Mat, PetscInt, PetscInt *, const PetscInt **, const PetscScalar **) { shim_unreachable("MatRestoreRow"); return 1; }
 PetscErrorCode PCSetType(PC, PCType) { shim_unreachable("PCSetType"); return 1; }

@@ -146,7 +146,30 @@ def cycle_variant_cases():
         print(name + "_cycles", sorted(k for k in out if k.startswith("cycle_")))
 
 
+def assembled_operator_case():
+    """the reference's independent ASSEMBLED form of the operator (MatrixHelper::formCRSMatrix, per-side stencils of
+    StencilHelper.h:298-538 incl. the coarse/fine weights; ref_gmg `matapply`) applied to the per-level inputs of the 3D
+    Dirichlet and Neumann goldens: pins the matrix-free operator (and with it the ghost-fill weights) by a second
+    implementation.  3D only: the 2D assembled stencil is a different discretisation."""
+    out = {}
+    for name, D, mesh, div, n in CASES + NEUMANN_CASES:
+        if D != 3:
+            continue
+        base = np.load(os.path.join(HERE, name + ".npz"))
+        solver = "dft-neumann" if name.endswith("_neumann") else "dft"
+        with tempfile.TemporaryDirectory() as tmp:
+            t = lambda k: os.path.join(tmp, k)  # noqa: E731
+            for l in range(int(base["nlevels"])):
+                base["L%d_in_u" % l].tofile(t("u"))
+                ref(D, mesh, div, n, "matapply:%d:%s:%s" % (l, t("u"), t("m")), solver=solver)
+                out["%s_L%d_matapply" % (name, l)] = np.fromfile(t("m"))
+    np.savez_compressed(os.path.join(HERE, "3d_assembled_operator.npz"), **out)
+    print("3d_assembled_operator", len(out), "vectors")
+
+
 def main():
+    if "--assembled-only" in sys.argv:
+        return assembled_operator_case()
     if "--cycles-only" in sys.argv:
         return cycle_variant_cases()
     if "--neumann-init-only" in sys.argv:
@@ -157,6 +180,7 @@ def main():
     neumann_cases()
     _base_cases()
     cycle_variant_cases()
+    assembled_operator_case()
 
 
 def _base_cases():

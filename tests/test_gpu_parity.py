@@ -185,6 +185,31 @@ def test_specialised_3d16_kernels_vs_generic(ctx, mesh_file, divide):
     mesh.close()
 
 
+def test_apply_vs_the_references_assembled_matrix(ctx):
+    """the operator kernels against the reference's second, independent implementation of the operator: the assembled
+    matrix of MatrixHelper::formCRSMatrix / StencilHelper.h (golden 3d_assembled_operator, see make_golden.py), on every
+    level of the refined 3D goldens, Dirichlet and Neumann"""
+    a = load_golden("3d_assembled_operator")
+    seen = 0
+    for name in list(GOLDEN_CASES) + list(NEUMANN_CASES):
+        g = load_golden(name)
+        if int(g["D"]) != 3:
+            continue
+        mesh = pps.Mesh.load(os.path.join(MESHES, str(g["mesh"])), 3)
+        if name.endswith("_neumann"):
+            mesh.set_neumann(True)
+        mesh.refine_leaves(int(g["divide"]))
+        h = pps.Hierarchy.from_mesh(ctx, mesh, int(g["n"]))
+        for l in range(h.nlevels):
+            u, out = h.new_vec(l, g["L%d_in_u" % l]), h.new_vec(l)
+            h.apply(l, u, out)
+            assert rel_l2(out.download(), a["%s_L%d_matapply" % (name, l)]) < TOL, (name, l)
+            seen += 1
+        h.close()
+        mesh.close()
+    assert seen == 19
+
+
 @pytest.mark.parametrize("name", NEUMANN_CASES)
 def test_neumann_vs_reference(ctx, name):
     """Neumann domain boundaries: per-level operator and smoother and the V-cycle against the reference's
